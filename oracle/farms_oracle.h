@@ -1,0 +1,62 @@
+/* oracle/farms_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Tier-2 oracle: a plain-C, sequential, CPU restatement of the reference's batch path
+ * (vFlowManager::runFileCopy -> computeLocalFlow -> computeGrads -> computeTrueFlow;
+ * reference src/vFlow.cpp:111-460, 841-949, 1214-1381, 952-1210; include/EventMatrix.h:32-34).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this.  The product
+ * (libfarms_b200.so) never links, loads or calls it.
+ *
+ * Pinning: validated byte-for-byte (11-column text) against oracle/_ref/FARMS_Flow, which is the
+ * UNMODIFIED reference sources compiled against oracle/shim/ (Eigen3 and Boost headers are absent
+ * from the image).  The FP64 operation order inside Eigen (At*A, determinant, A2*At*Y) is therefore
+ * the shim's, not real Eigen's: that slice of parity is unpinned (see DESIGN.md "Oracle").
+ */
+#ifndef FARMS_ORACLE_H
+#define FARMS_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct farms_oracle farms_oracle;
+
+/* Per-event outputs, SoA, caller-allocated, n entries each.  Any pointer may be NULL. */
+typedef struct {
+  int32_t *t_rel;       /* column 3: (u32)(t - t0) printed as int           vFlow.cpp:241, 373 */
+  int32_t *pol;         /* column 4: polarity after clamping <0 to 0        vFlow.cpp:246      */
+  double *global_r;     /* column 5                                         vFlow.cpp:365      */
+  double *global_theta; /* column 6                                         vFlow.cpp:366      */
+  double *vx;           /* column 7 (raw local result, also for invalid)    vFlow.cpp:378, 394 */
+  double *vy;           /* column 8                                                            */
+  double *local_r;      /* column 9                                         vFlow.cpp:324      */
+  double *local_theta;  /* column 10                                        vFlow.cpp:325      */
+  int32_t *scale;       /* column 11                                        vFlow.cpp:380      */
+  uint8_t *valid;       /* the test at vFlow.cpp:315                                           */
+  /* intermediates the reference never prints (for bit-exact GPU checks) */
+  int8_t *best_window;  /* 0..8 = 3*di+dj index (i outer, j inner) of the winning window, -1 none */
+  int32_t *inliers;     /* return value of computeGrads (0 when DET<1 or no window)            */
+  double *det;          /* DET as returned by determinant(); NaN when no window                */
+} farms_oracle_out;
+
+/* width/height/filtersize/inlier_check as given on the reference CLI (filtersize is normalised
+ * inside exactly like vFlow.cpp:32-36).  Returns NULL on bad arguments. */
+farms_oracle *farms_oracle_create(int width, int height, int filtersize, int inlier_check);
+void farms_oracle_destroy(farms_oracle *o);
+
+/* Process n more events in order.  State persists between calls; t0 is the first timestamp ever
+ * seen (vFlow.cpp:194).  Returns 0, or -1 if an event lies outside the sensor. */
+int farms_oracle_process(farms_oracle *o, const int32_t *x, const int32_t *y, const uint32_t *t,
+                         const int32_t *p, uint64_t n, const farms_oracle_out *out);
+
+/* Copy out the per-pixel state (x-major flat index a*height+b like EventMatrix): last event time,
+ * hit flag, flow length and theta.  Any pointer may be NULL. */
+void farms_oracle_state(const farms_oracle *o, double *last_time, uint8_t *hit, double *len,
+                        double *theta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
