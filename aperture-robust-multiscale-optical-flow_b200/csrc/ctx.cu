@@ -1,0 +1,559 @@
+// ctx.cu -- host side of the C ABI (include/farms_b200.h): context, device memory, batch pipeline.
+//
+// Replaces vFlowManager's constructor and the runFileCopy event loop (src/vFlow.cpp:22-108, 223-414).
+// A submit is cut into internal batches; each batch is [halo | new] where the halo is the tail of the
+// stream already processed (the events young enough to still matter for pooling, src/vFlow.cpp:1002).
+// Per batch:  K1 ingest -> K2 sort by pixel + links -> K3 (SAE advance, plane fit) per chunk ->
+//             K4a bin by (time slab, tile) -> K4b pooling -> copy results out -> keep the new tail.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/farms_b200.h"
+#include "farms_dev.cuh"
+
+namespace {
+
+constexpr uint64_t DEFAULT_MAX_BATCH = 16ull << 20;
+constexpr uint32_t DEFAULT_SLACK_US = 1000;
+constexpr size_t HALO_CAP = 8ull << 20;       // events carried across a batch boundary at most
+constexpr int FIT_CHUNK = 1 << 18;            // events per SAE snapshot
+constexpr size_t CSR_BUDGET = 96ull << 20;    // max (slab, tile) cells of the pooling index per batch
+
+enum { EV_START, EV_H2D, EV_INGEST, EV_INDEX, EV_FIT, EV_BIN, EV_POOL, EV_END, EV_COUNT };
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct farms_ctx {
+  farms_config cfg{};
+  int W = 0, H = 0, fs = 0, r = 0, P = 0, min_inl = 0;
+  size_t npx = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[EV_COUNT]{};
+  std::string err;
+  bool have_t0 = false;
+  uint64_t t0 = 0;
+  uint64_t total_events = 0;
+  uint32_t last_M = 0;
+  size_t halo = 0;  // events in the halo store
+  size_t cap = 0;   // capacity (events) of the per-event working arrays
+  size_t cap_in = 0;
+  farms_timings tm{};
+
+  uint2 *sae = nullptr;
+  // per-event working arrays (capacity cap)
+  uint16_t *ex = nullptr, *ey = nullptr;
+  uint32_t *et = nullptr, *em = nullptr, *keyA = nullptr, *valA = nullptr, *keyB = nullptr, *valB = nullptr,
+           *pixkeep = nullptr, *flags = nullptr, *slab_ids = nullptr;
+  int2 *prevp = nullptr;
+  int32_t *nextp = nullptr;
+  double *vx = nullptr, *vy = nullptr, *len = nullptr, *theta = nullptr, *lcx = nullptr, *lcy = nullptr,
+         *det = nullptr, *gr = nullptr, *gth = nullptr, *pay = nullptr;
+  uint8_t *valid = nullptr, *scale = nullptr;
+  int8_t *bw = nullptr;
+  uint16_t *inl = nullptr;
+  uint4 *rec = nullptr;
+  // halo store
+  uint16_t *hx = nullptr, *hy = nullptr;
+  uint32_t *ht = nullptr, *hm = nullptr;
+  double *hlen = nullptr, *hlcx = nullptr, *hlcy = nullptr;
+  // staging for the host path
+  uint16_t *in_x = nullptr, *in_y = nullptr;
+  uint64_t *in_t = nullptr;
+  // misc
+  DevBuf sort_temp, scan_temp, cell_start;
+  int *d_err = nullptr;
+  unsigned long long *d_counters = nullptr;  // [0] valid events, [1] pool candidates
+  unsigned int *d_work = nullptr;
+  uint32_t *d_small = nullptr;  // device scratch words
+  uint32_t *h_small = nullptr;  // pinned host scratch words
+  std::vector<void *> owned;
+};
+
+namespace {
+
+int fail(farms_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess)                                                                                \
+      return fail(c, e_ == cudaErrorMemoryAllocation ? FARMS_ERR_NOMEM : FARMS_ERR_CUDA, "%s: %s (%s:%d)", \
+                  #call, cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
+  } while (0)
+
+template <class T>
+int dalloc(farms_ctx *c, T **p, size_t count) {
+  void *q = nullptr;
+  CU(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  *p = (T *)q;
+  c->owned.push_back(q);
+  return 0;
+}
+
+void free_owned(farms_ctx *c) {
+  for (void *p : c->owned) cudaFree(p);
+  c->owned.clear();
+}
+
+int ensure(farms_ctx *c, DevBuf &b, size_t bytes) {
+  if (b.bytes >= bytes) return 0;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  CU(cudaMalloc(&b.p, want));
+  b.bytes = want;
+  return 0;
+}
+
+// (re)allocate the per-event working arrays for `cap` events
+int alloc_working(farms_ctx *c, size_t cap) {
+  if (cap <= c->cap) return 0;
+  CU(cudaStreamSynchronize(c->stream));
+  // keep the persistent pieces (sae, halo store, staging, counters) -- they are not in `owned`
+  free_owned(c);
+  c->cap = 0;
+  int rc = 0;
+#define A(ptr, n) if ((rc = dalloc(c, &c->ptr, (n)))) return rc;
+  A(ex, cap) A(ey, cap) A(et, cap) A(em, cap) A(keyA, cap) A(valA, cap) A(keyB, cap) A(valB, cap)
+  A(pixkeep, cap) A(flags, cap) A(slab_ids, cap + 1) A(prevp, cap) A(nextp, cap)
+  A(vx, cap) A(vy, cap) A(len, cap) A(theta, cap) A(lcx, cap) A(lcy, cap) A(gr, cap) A(gth, cap)
+  A(pay, 3 * cap) A(valid, cap) A(scale, cap) A(bw, cap) A(inl, cap) A(rec, cap)
+  if (c->cfg.flags & FARMS_FLAG_DEBUG_DET) { A(det, cap) } else c->det = nullptr;
+#undef A
+  if ((rc = ensure(c, c->sort_temp, radix_sort_temp_bytes(cap)))) return rc;
+  if ((rc = ensure(c, c->scan_temp, scan_temp_bytes(cap)))) return rc;
+  c->cap = cap;
+  return 0;
+}
+
+int bits_for(uint64_t n) {  // bits needed to represent values in [0, n)
+  int b = 1;
+  while (b < 32 && (1ull << b) < n) b++;
+  return b;
+}
+
+__global__ void k_tail_start(const uint32_t *__restrict__ em, uint32_t m, uint32_t window, uint32_t *out) {
+  // first j with em[j] + window > em[m-1]  (em is non-decreasing)
+  const uint32_t last = em[m - 1];
+  uint32_t lo = 0, hi = m;  // answer in [lo, hi)
+  while (lo < hi) {
+    uint32_t mid = lo + (hi - lo) / 2;
+    if ((uint64_t)em[mid] + window > last) hi = mid; else lo = mid + 1;
+  }
+  out[0] = lo;
+  out[1] = last;
+}
+
+__global__ void k_nslabs(const uint32_t *__restrict__ em, const uint32_t *__restrict__ excl, uint32_t m, uint32_t *out) {
+  const bool first = m == 1 || (em[m - 2] >> FARMS_SLAB_SHIFT) != (em[m - 1] >> FARMS_SLAB_SHIFT);
+  out[0] = excl[m - 1] + ((m > 1 && first) ? 1u : 0u) + 1u;
+}
+
+struct Loc {  // where the caller's buffers live
+  bool device;
+};
+
+template <class T>
+int copy_out(farms_ctx *c, T *dst, const T *src, size_t n, bool to_device) {
+  if (!dst || !n) return 0;
+  CU(cudaMemcpyAsync(dst, src, n * sizeof(T), to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+
+// One internal batch: n new events already on the device at (dx, dy, dt).
+int run_batch(farms_ctx *c, const uint16_t *dx, const uint16_t *dy, const uint64_t *dt, size_t n, const farms_out *out,
+              size_t out_off, bool out_device, float *stage_ms) {
+  cudaStream_t s = c->stream;
+  const size_t h = c->halo, m = h + n;
+  int rc;
+  if (m > c->cap && (rc = alloc_working(c, m + m / 8 + 1024))) return rc;
+  uint64_t *L = &c->tm.kernel_launches;
+
+  // ---- halo to the front of the working arrays ----
+  if (h) {
+    CU(cudaMemcpyAsync(c->ex, c->hx, h * 2, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(c->ey, c->hy, h * 2, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(c->et, c->ht, h * 4, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(c->em, c->hm, h * 4, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(c->len, c->hlen, h * 8, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(c->lcx, c->hlcx, h * 8, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(c->lcy, c->hlcy, h * 8, cudaMemcpyDeviceToDevice, s));
+  }
+  CU(cudaEventRecord(c->ev[EV_H2D], s));
+
+  // ---- K1 ingest ----
+  CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), s));
+  launch_ingest(dx, dy, dt, c->t0, n, c->W, c->H, c->ex + h, c->ey + h, c->et + h, c->keyA + h, c->valA + h,
+                (uint32_t)h, c->d_err, s);
+  launch_halo_keys(c->ex, c->ey, h, c->H, c->keyA, c->valA, s);
+  inclusive_max_scan_u32(c->et + h, c->em + h, n, c->last_M, c->scan_temp.p, s, L);
+  CU(cudaMemcpyAsync(c->pixkeep, c->keyA, m * 4, cudaMemcpyDeviceToDevice, s));
+  *L += 2;
+  CU(cudaMemcpyAsync(c->h_small, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(c->ev[EV_INGEST], s));
+
+  // ---- K2 history index: stable sort by pixel, prev/next links ----
+  int which = radix_sort_pairs(c->keyA, c->valA, c->keyB, c->valB, m, bits_for(c->npx), c->sort_temp.p, s, L);
+  const uint32_t *skeys = which ? c->keyB : c->keyA, *svals = which ? c->valB : c->valA;
+  launch_links(skeys, svals, c->et, c->sae, m, c->prevp, c->nextp, s);
+  *L += 1;
+  CU(cudaEventRecord(c->ev[EV_INDEX], s));
+
+  // range errors are known by now without having stalled the sort
+  CU(cudaStreamSynchronize(s));
+  if (((int *)c->h_small)[0]) return fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
+
+  // ---- K3 plane fit, chunk by chunk against the chunk-end SAE snapshot ----
+  FitParams fp{c->W, c->H, c->r, c->P, c->min_inl};
+  FitOut fo{c->vx, c->vy, c->len, c->theta, c->lcx, c->lcy, c->valid, c->bw, c->inl, c->det};
+  for (size_t c0 = 0; c0 < m; c0 += FIT_CHUNK) {
+    const size_t c1 = std::min(m, c0 + (size_t)FIT_CHUNK);
+    launch_sae_advance(c->sae, c->pixkeep, c->et, c->nextp, (int)c0, (int)c1, s);
+    *L += 1;
+    if (c1 > h) {
+      launch_plane_fit(c->sae, c->prevp, c->ex, c->ey, c->et, (int)std::max(c0, h), (int)c1, fp, fo, c->d_counters, s);
+      *L += 1;
+    }
+  }
+  launch_sae_finalize(c->sae, c->pixkeep, c->nextp, (int)m, s);
+  *L += 1;
+  CU(cudaEventRecord(c->ev[EV_FIT], s));
+
+  // ---- K4a pooling index: dense time slabs x tiles ----
+  launch_slab_flags(c->em, m, c->flags, s);
+  exclusive_scan_u32(c->flags, c->flags, m, c->scan_temp.p, s, L);
+  k_nslabs<<<1, 1, 0, s>>>(c->em, c->flags, (uint32_t)m, c->d_small);
+  *L += 2;
+  CU(cudaMemcpyAsync(c->h_small, c->d_small, 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  const size_t nslabs = c->h_small[0];
+  PoolGeom g{};
+  g.W = c->W;
+  g.H = c->H;
+  g.tile_shift = 4;
+  for (;;) {
+    g.ntx = (c->W + (1 << g.tile_shift) - 1) >> g.tile_shift;
+    g.nty = (c->H + (1 << g.tile_shift) - 1) >> g.tile_shift;
+    if (nslabs * (size_t)g.ntx * g.nty <= CSR_BUDGET || (g.ntx == 1 && g.nty == 1)) break;
+    g.tile_shift++;
+  }
+  const size_t ncells = nslabs * (size_t)g.ntx * g.nty;
+  if (ncells >= (1ull << 32)) return fail(c, FARMS_ERR_NOMEM, "pooling index too large (%zu cells)", ncells);
+  if ((rc = ensure(c, c->cell_start, (ncells + 1) * sizeof(uint32_t)))) return rc;
+  launch_cell_keys(c->ex, c->ey, c->em, c->flags, m, g, c->keyA, c->valA, c->slab_ids, s);
+  which = radix_sort_pairs(c->keyA, c->valA, c->keyB, c->valB, m, bits_for(ncells), c->sort_temp.p, s, L);
+  skeys = which ? c->keyB : c->keyA;
+  svals = which ? c->valB : c->valA;
+  launch_build_records(skeys, svals, m, c->ex, c->ey, c->et, c->nextp, c->len, c->lcx, c->lcy, c->rec, c->pay,
+                       (uint32_t *)c->cell_start.p, ncells, s);
+  *L += 2;
+  CU(cudaEventRecord(c->ev[EV_BIN], s));
+
+  // ---- K4b pooling ----
+  CU(cudaMemsetAsync(c->gr, 0, n * 8, s));
+  CU(cudaMemsetAsync(c->gth, 0, n * 8, s));
+  CU(cudaMemsetAsync(c->scale, 0, n, s));
+  CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), s));
+  launch_pooling(c->rec, c->pay, (const uint32_t *)c->cell_start.p, skeys, c->slab_ids, m, (int)h, g, c->gr, c->gth,
+                 c->scale, c->d_work, c->d_counters + 1, c->num_sms, s);
+  *L += 1;
+  CU(cudaEventRecord(c->ev[EV_POOL], s));
+
+  // ---- results of the new events ----
+  if (out) {
+    if ((rc = copy_out(c, out->t_rel ? out->t_rel + out_off : nullptr, c->et + h, n, out_device))) return rc;
+    if ((rc = copy_out(c, out->global_r ? out->global_r + out_off : nullptr, c->gr, n, out_device))) return rc;
+    if ((rc = copy_out(c, out->global_theta ? out->global_theta + out_off : nullptr, c->gth, n, out_device))) return rc;
+    if ((rc = copy_out(c, out->vx ? out->vx + out_off : nullptr, c->vx + h, n, out_device))) return rc;
+    if ((rc = copy_out(c, out->vy ? out->vy + out_off : nullptr, c->vy + h, n, out_device))) return rc;
+    if ((rc = copy_out(c, out->local_r ? out->local_r + out_off : nullptr, c->len + h, n, out_device))) return rc;
+    if ((rc = copy_out(c, out->local_theta ? out->local_theta + out_off : nullptr, c->theta + h, n, out_device))) return rc;
+    if ((rc = copy_out(c, out->scale ? out->scale + out_off : nullptr, c->scale, n, out_device))) return rc;
+    if ((rc = copy_out(c, out->valid ? out->valid + out_off : nullptr, c->valid + h, n, out_device))) return rc;
+    if ((rc = copy_out(c, out->best_window ? out->best_window + out_off : nullptr, c->bw + h, n, out_device))) return rc;
+    if ((rc = copy_out(c, out->inliers ? out->inliers + out_off : nullptr, c->inl + h, n, out_device))) return rc;
+    if (out->det && c->det)
+      if ((rc = copy_out(c, out->det + out_off, c->det + h, n, out_device))) return rc;
+  }
+
+  // ---- new tail -> halo store ----
+  const uint32_t window = FARMS_KILL_OLD_FLOW_TIME + (c->cfg.reorder_slack_us ? c->cfg.reorder_slack_us : DEFAULT_SLACK_US);
+  k_tail_start<<<1, 1, 0, s>>>(c->em, (uint32_t)m, window, c->d_small);
+  *L += 1;
+  CU(cudaMemcpyAsync(c->h_small, c->d_small, 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(c->ev[EV_END], s));
+  CU(cudaStreamSynchronize(s));
+  size_t ts = c->h_small[0];
+  c->last_M = c->h_small[1];
+  if (m - ts > HALO_CAP) ts = m - HALO_CAP;
+  const size_t nh = m - ts;
+  CU(cudaMemcpyAsync(c->hx, c->ex + ts, nh * 2, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(c->hy, c->ey + ts, nh * 2, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(c->ht, c->et + ts, nh * 4, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(c->hm, c->em + ts, nh * 4, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(c->hlen, c->len + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(c->hlcx, c->lcx + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(c->hlcy, c->lcy + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
+  c->halo = nh;
+  CU(cudaStreamSynchronize(s));
+
+  // stage times of this batch
+  float ms = 0;
+  static const int order[] = {EV_H2D, EV_INGEST, EV_INDEX, EV_FIT, EV_BIN, EV_POOL, EV_END};
+  for (int k = 1; k < 7; k++) {
+    CU(cudaEventElapsedTime(&ms, c->ev[order[k - 1]], c->ev[order[k]]));
+    stage_ms[k] += ms;
+  }
+  return 0;
+}
+
+int process(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t n, const farms_out *out,
+            bool device) {
+  if (!c) return FARMS_ERR_ARG;
+  c->err.clear();
+  if (n == 0) return FARMS_OK;
+  if (!x || !y || !t) return fail(c, FARMS_ERR_ARG, "null event array");
+  CU(cudaSetDevice(c->cfg.device));
+  cudaStream_t s = c->stream;
+  if (!c->have_t0) {  // src/vFlow.cpp:194
+    if (device) {
+      CU(cudaMemcpy(&c->t0, t, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    } else {
+      c->t0 = t[0];
+    }
+    c->have_t0 = true;
+  }
+  const uint64_t maxb = c->cfg.max_batch ? c->cfg.max_batch : DEFAULT_MAX_BATCH;
+  farms_timings &tm = c->tm;
+  tm = farms_timings{};
+  CU(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), s));
+  float stage[8] = {0};
+  float h2d_ms = 0, d2h_ms = 0;
+  CU(cudaEventRecord(c->ev[EV_START], s));
+  if (!device && c->cap_in < std::min<uint64_t>(n, maxb)) {
+    size_t want = (size_t)std::min<uint64_t>(n, maxb);
+    if (c->in_x) { cudaFree(c->in_x); cudaFree(c->in_y); cudaFree(c->in_t); c->in_x = nullptr; }
+    CU(cudaMalloc((void **)&c->in_x, want * 2));
+    CU(cudaMalloc((void **)&c->in_y, want * 2));
+    CU(cudaMalloc((void **)&c->in_t, want * 8));
+    c->cap_in = want;
+  }
+  for (uint64_t off = 0; off < n; off += maxb) {
+    const size_t nb = (size_t)std::min<uint64_t>(maxb, n - off);
+    const uint16_t *dx = x + off, *dy = y + off;
+    const uint64_t *dt = t + off;
+    if (!device) {
+      cudaEvent_t a = c->ev[EV_H2D];
+      CU(cudaEventRecord(c->ev[EV_INGEST], s));
+      CU(cudaMemcpyAsync(c->in_x, x + off, nb * 2, cudaMemcpyHostToDevice, s));
+      CU(cudaMemcpyAsync(c->in_y, y + off, nb * 2, cudaMemcpyHostToDevice, s));
+      CU(cudaMemcpyAsync(c->in_t, t + off, nb * 8, cudaMemcpyHostToDevice, s));
+      CU(cudaEventRecord(a, s));
+      CU(cudaEventSynchronize(a));
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, c->ev[EV_INGEST], a));
+      h2d_ms += ms;
+      dx = c->in_x;
+      dy = c->in_y;
+      dt = c->in_t;
+    }
+    int rc = run_batch(c, dx, dy, dt, nb, out, (size_t)off, device, stage);
+    if (rc) return rc;
+    c->total_events += nb;
+  }
+  CU(cudaEventRecord(c->ev[EV_END], s));
+  CU(cudaStreamSynchronize(s));
+  float total = 0;
+  CU(cudaEventElapsedTime(&total, c->ev[EV_START], c->ev[EV_END]));
+  unsigned long long counters[2];
+  CU(cudaMemcpy(counters, c->d_counters, sizeof counters, cudaMemcpyDeviceToHost));
+  tm.total_ms = total;
+  tm.h2d_ms = h2d_ms;
+  tm.ingest_ms = stage[1];
+  tm.index_ms = stage[2];
+  tm.fit_ms = stage[3];
+  tm.bin_ms = stage[4];
+  tm.pool_ms = stage[5];
+  tm.d2h_ms = device ? 0.f : stage[6];
+  (void)d2h_ms;
+  tm.events = n;
+  tm.valid_events = counters[0];
+  tm.pool_candidates = counters[1];
+  return FARMS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int farms_abi_version(void) { return FARMS_B200_ABI_VERSION; }
+
+int farms_create(farms_ctx **out, const farms_config *cfg) {
+  if (!out || !cfg) return FARMS_ERR_ARG;
+  *out = nullptr;
+  if (cfg->width <= 0 || cfg->height <= 0 || cfg->width > 65535 || cfg->height > 65535) return FARMS_ERR_ARG;
+  if ((uint64_t)cfg->width * (uint64_t)cfg->height >= (1ull << 31)) return FARMS_ERR_ARG;
+  farms_ctx *c = new (std::nothrow) farms_ctx();
+  if (!c) return FARMS_ERR_NOMEM;
+  c->cfg = *cfg;
+  c->W = cfg->width;
+  c->H = cfg->height;
+  int fs = cfg->filtersize;  // src/vFlow.cpp:32-38
+  if (fs < 5) fs = 3;
+  if (!(fs % 2)) fs--;
+  c->fs = fs;
+  c->r = fs / 2;
+  c->P = fs * fs;
+  c->min_inl = cfg->inlier_check;
+  c->npx = (size_t)c->W * c->H;
+  auto bail = [&](int code) {
+    farms_destroy(c);
+    return code;
+  };
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+    cudaGetLastError();
+    return bail(FARMS_ERR_CUDA);  // no CPU fallback
+  }
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+  if (prop.major < 10) return bail(FARMS_ERR_CUDA);  // built for sm_100a only
+  c->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+  for (int i = 0; i < EV_COUNT; i++)
+    if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+  bool ok = true;
+  ok &= cudaMalloc((void **)&c->sae, c->npx * sizeof(uint2)) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->hx, HALO_CAP * 2) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->hy, HALO_CAP * 2) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->ht, HALO_CAP * 4) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->hm, HALO_CAP * 4) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->hlen, HALO_CAP * 8) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->hlcx, HALO_CAP * 8) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->hlcy, HALO_CAP * 8) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->d_err, sizeof(int)) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->d_counters, 2 * sizeof(unsigned long long)) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->d_work, sizeof(unsigned int)) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->d_small, 64) == cudaSuccess;
+  ok &= cudaMallocHost((void **)&c->h_small, 64) == cudaSuccess;
+  if (!ok) return bail(FARMS_ERR_NOMEM);
+  launch_sae_init(c->sae, c->npx, c->stream);
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+  *out = c;
+  return FARMS_OK;
+}
+
+void farms_destroy(farms_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_owned(c);
+  void *ps[] = {c->sae, c->hx, c->hy, c->ht, c->hm, c->hlen, c->hlcx, c->hlcy, c->d_err, c->d_counters, c->d_work,
+                c->d_small, c->in_x, c->in_y, c->in_t, c->sort_temp.p, c->scan_temp.p, c->cell_start.p};
+  for (void *p : ps)
+    if (p) cudaFree(p);
+  if (c->h_small) cudaFreeHost(c->h_small);
+  for (int i = 0; i < EV_COUNT; i++)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char *farms_last_error(const farms_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int farms_get_params(const farms_ctx *c, int32_t *filtersize, int32_t *radius, int32_t *plane_size) {
+  if (!c) return FARMS_ERR_ARG;
+  if (filtersize) *filtersize = c->fs;
+  if (radius) *radius = c->r;
+  if (plane_size) *plane_size = c->P;
+  return FARMS_OK;
+}
+
+int farms_process_host(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *t, const uint8_t *p,
+                       uint64_t n, const farms_out *out) {
+  (void)p;
+  return process(c, x, y, t, n, out, false);
+}
+
+int farms_process_device(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *t, const uint8_t *p,
+                         uint64_t n, const farms_out *out) {
+  (void)p;
+  return process(c, x, y, t, n, out, true);
+}
+
+uint64_t farms_num_events(const farms_ctx *c) { return c ? c->total_events : 0; }
+
+int farms_get_timings(const farms_ctx *c, farms_timings *out) {
+  if (!c || !out) return FARMS_ERR_ARG;
+  *out = c->tm;
+  return FARMS_OK;
+}
+
+int farms_set_t0(farms_ctx *c, uint64_t t0) {
+  if (!c) return FARMS_ERR_ARG;
+  if (c->total_events) return fail(c, FARMS_ERR_STATE, "farms_set_t0 after events were processed");
+  c->t0 = t0;
+  c->have_t0 = true;
+  return FARMS_OK;
+}
+
+int farms_state_export(farms_ctx *c, uint32_t *d_last_t, uint8_t *d_hit) {
+  if (!c || !d_last_t || !d_hit) return FARMS_ERR_ARG;
+  CU(cudaSetDevice(c->cfg.device));
+  launch_sae_export(c->sae, c->npx, d_last_t, d_hit, c->stream);
+  CU(cudaStreamSynchronize(c->stream));
+  return FARMS_OK;
+}
+
+int farms_state_fold(farms_ctx *c, const uint32_t *d_last_t, const uint8_t *d_hit) {
+  if (!c || !d_last_t || !d_hit) return FARMS_ERR_ARG;
+  CU(cudaSetDevice(c->cfg.device));
+  launch_sae_fold(c->sae, c->npx, d_last_t, d_hit, c->stream);
+  CU(cudaStreamSynchronize(c->stream));
+  return FARMS_OK;
+}
+
+int farms_slice_surface(farms_ctx *c, const uint16_t *d_x, const uint16_t *d_y, const uint64_t *d_t, uint64_t n,
+                        uint64_t t0, uint32_t *d_last_t, uint8_t *d_hit) {
+  if (!c || !d_last_t || !d_hit || (n && (!d_x || !d_y || !d_t))) return FARMS_ERR_ARG;
+  if (n >= (1ull << 32) - 1) return fail(c, FARMS_ERR_ARG, "slice too long");
+  CU(cudaSetDevice(c->cfg.device));
+  int rc;
+  DevBuf tmp;
+  if ((rc = ensure(c, tmp, c->npx * sizeof(unsigned long long)))) return rc;
+  cudaError_t e = cudaMemsetAsync(tmp.p, 0, c->npx * sizeof(unsigned long long), c->stream);
+  if (e == cudaSuccess) {
+    launch_slice_surface(d_x, d_y, d_t, (size_t)n, t0, c->H, (unsigned long long *)tmp.p, c->stream);
+    launch_unpack_surface((const unsigned long long *)tmp.p, c->npx, d_last_t, d_hit, c->stream);
+    e = cudaStreamSynchronize(c->stream);
+  }
+  cudaFree(tmp.p);
+  if (e != cudaSuccess) return fail(c, FARMS_ERR_CUDA, "farms_slice_surface: %s", cudaGetErrorString(e));
+  return FARMS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// index.cu -- K1 ingest and the link half of K2 (per-pixel event-history index).
+//
+// K1 replaces the per-event prologue of the reference loop (src/vFlow.cpp:238-247): rebase the timestamp
+// by t0 into an unsigned 32-bit value, check the pixel against the sensor, and derive the flat pixel key
+// x*H + y (include/EventMatrix.h:32-34).  After the stable sort by pixel (sort.cu) the link kernel turns
+// each pixel's run into prev/next pointers, which is what lets every event find "the latest event at
+// pixel q with index <= i" without replaying the stream (planefit.cu: sae_lookup).
+#include "farms_dev.cuh"
+
+namespace {
+
+__global__ void k_ingest(const uint16_t *__restrict__ x, const uint16_t *__restrict__ y,
+                         const uint64_t *__restrict__ t, uint64_t t0, size_t n, int W, int H,
+                         uint16_t *__restrict__ ex, uint16_t *__restrict__ ey, uint32_t *__restrict__ et,
+                         uint32_t *__restrict__ pix, uint32_t *__restrict__ idx, uint32_t idx_base,
+                         int *__restrict__ err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t xx = x[i], yy = y[i];
+  if (xx >= (uint32_t)W || yy >= (uint32_t)H) {
+    atomicOr(err, 1);
+    xx = 0;
+    yy = 0;
+  }
+  ex[i] = (uint16_t)xx;
+  ey[i] = (uint16_t)yy;
+  et[i] = (uint32_t)(t[i] - t0);  // unsigned wrap like `time_ = time_ - t0` (src/vFlow.cpp:241)
+  pix[i] = xx * (uint32_t)H + yy;
+  idx[i] = idx_base + (uint32_t)i;
+}
+
+__global__ void k_halo_keys(const uint16_t *__restrict__ ex, const uint16_t *__restrict__ ey, size_t h, int H,
+                            uint32_t *__restrict__ pix, uint32_t *__restrict__ idx) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h) return;
+  pix[i] = (uint32_t)ex[i] * (uint32_t)H + ey[i];
+  idx[i] = (uint32_t)i;
+}
+
+// skeys/svals: events sorted by pixel, stream order inside a pixel.  One thread per sorted slot.
+__global__ void k_links(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
+                        const uint32_t *__restrict__ et, const uint2 *__restrict__ sae, size_t m,
+                        int2 *__restrict__ prevp, int32_t *__restrict__ nextp) {
+  size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= m) return;
+  const uint32_t key = skeys[s];
+  const uint32_t j = svals[s];
+  int2 pp;
+  if (s > 0 && skeys[s - 1] == key) {
+    uint32_t pj = svals[s - 1];
+    pp.x = (int)pj;
+    pp.y = (int)et[pj];
+  } else {
+    uint2 c = sae[key];  // state left by earlier batches: index code is SAE_OLD or SAE_NEVER
+    pp.x = (int)c.y;
+    pp.y = (int)c.x;
+  }
+  prevp[j] = pp;
+  nextp[j] = (s + 1 < m && skeys[s + 1] == key) ? (int32_t)svals[s + 1] : NEXT_NONE;
+}
+
+__global__ void k_slab_flags(const uint32_t *__restrict__ em, size_t m, uint32_t *__restrict__ flags) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  flags[j] = (j > 0 && (em[j] >> FARMS_SLAB_SHIFT) != (em[j - 1] >> FARMS_SLAB_SHIFT)) ? 1u : 0u;
+}
+
+__global__ void k_slice_surface(const uint16_t *__restrict__ x, const uint16_t *__restrict__ y,
+                                const uint64_t *__restrict__ t, size_t n, uint64_t t0, int H,
+                                unsigned long long *__restrict__ packed) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t tr = (uint32_t)(t[i] - t0);
+  // later index wins: index in the high word
+  atomicMax(&packed[(size_t)x[i] * H + y[i]], ((unsigned long long)(i + 1) << 32) | tr);
+}
+
+__global__ void k_unpack_surface(const unsigned long long *__restrict__ packed, size_t npx,
+                                 uint32_t *__restrict__ last_t, uint8_t *__restrict__ hit) {
+  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= npx) return;
+  unsigned long long v = packed[q];
+  last_t[q] = (uint32_t)v;
+  hit[q] = v != 0ull;
+}
+
+inline unsigned nb(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+void launch_ingest(const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t t0, size_t n, int W, int H,
+                   uint16_t *ex, uint16_t *ey, uint32_t *et, uint32_t *pix, uint32_t *idx, uint32_t idx_base,
+                   int *err_flag, cudaStream_t s) {
+  if (n) k_ingest<<<nb(n, 256), 256, 0, s>>>(x, y, t, t0, n, W, H, ex, ey, et, pix, idx, idx_base, err_flag);
+}
+void launch_halo_keys(const uint16_t *ex, const uint16_t *ey, size_t h, int H, uint32_t *pix, uint32_t *idx,
+                      cudaStream_t s) {
+  if (h) k_halo_keys<<<nb(h, 256), 256, 0, s>>>(ex, ey, h, H, pix, idx);
+}
+void launch_links(const uint32_t *skeys, const uint32_t *svals, const uint32_t *et, const uint2 *sae, size_t m,
+                  int2 *prevp, int32_t *nextp, cudaStream_t s) {
+  if (m) k_links<<<nb(m, 256), 256, 0, s>>>(skeys, svals, et, sae, m, prevp, nextp);
+}
+void launch_slab_flags(const uint32_t *em, size_t m, uint32_t *flags, cudaStream_t s) {
+  if (m) k_slab_flags<<<nb(m, 256), 256, 0, s>>>(em, m, flags);
+}
+void launch_slice_surface(const uint16_t *x, const uint16_t *y, const uint64_t *t, size_t n, uint64_t t0, int H,
+                          unsigned long long *packed, cudaStream_t s) {
+  if (n) k_slice_surface<<<nb(n, 256), 256, 0, s>>>(x, y, t, n, t0, H, packed);
+}
+void launch_unpack_surface(const unsigned long long *packed, size_t npx, uint32_t *last_t, uint8_t *hit,
+                           cudaStream_t s) {
+  k_unpack_surface<<<nb(npx, 256), 256, 0, s>>>(packed, npx, last_t, hit);
+}

@@ -1,0 +1,175 @@
+"""farms_b200 -- thin ctypes view of libfarms_b200.so (include/farms_b200.h) for the test and bench harness.
+
+The product is the C-ABI shared library and the FARMS_Flow CLI; this module only marshals numpy arrays
+and torch CUDA tensors into that ABI.  There is no fallback: if the library is missing, or no B200 is
+visible, calls fail loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfarms_b200.so")
+
+OK, ERR_ARG, ERR_RANGE, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4, -5
+FLAG_DEBUG_DET = 1
+
+EXPORTS = [
+    "farms_abi_version", "farms_create", "farms_destroy", "farms_last_error", "farms_get_params",
+    "farms_process_host", "farms_process_device", "farms_num_events", "farms_get_timings", "farms_set_t0",
+    "farms_state_export", "farms_state_fold", "farms_slice_surface",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("filtersize", C.c_int32),
+                ("inlier_check", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32),
+                ("max_batch", C.c_uint64), ("reorder_slack_us", C.c_uint32), ("reserved", C.c_uint32 * 7)]
+
+
+class Out(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("t_rel", "global_r", "global_theta", "vx", "vy", "local_r",
+                                          "local_theta", "scale", "valid", "best_window", "inliers", "det")]
+
+
+OUT_DTYPES = {"t_rel": np.uint32, "global_r": np.float64, "global_theta": np.float64, "vx": np.float64,
+              "vy": np.float64, "local_r": np.float64, "local_theta": np.float64, "scale": np.uint8,
+              "valid": np.uint8, "best_window": np.int8, "inliers": np.uint16, "det": np.float64}
+
+
+class Timings(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("h2d_ms", C.c_float), ("ingest_ms", C.c_float),
+                ("index_ms", C.c_float), ("fit_ms", C.c_float), ("bin_ms", C.c_float), ("pool_ms", C.c_float),
+                ("d2h_ms", C.c_float), ("events", C.c_uint64), ("valid_events", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("pool_candidates", C.c_uint64), ("reserved", C.c_uint64 * 4)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+_lib = None
+
+
+def lib():
+    """Load the C-ABI library (built in-tree by `make` / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.farms_abi_version.restype = C.c_int
+        L.farms_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Config)]
+        L.farms_destroy.argtypes = [C.c_void_p]
+        L.farms_destroy.restype = None
+        L.farms_last_error.argtypes = [C.c_void_p]
+        L.farms_last_error.restype = C.c_char_p
+        L.farms_get_params.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 3
+        for f in (L.farms_process_host, L.farms_process_device):
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Out)]
+        L.farms_num_events.argtypes = [C.c_void_p]
+        L.farms_num_events.restype = C.c_uint64
+        L.farms_get_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
+        L.farms_set_t0.argtypes = [C.c_void_p, C.c_uint64]
+        L.farms_state_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.farms_state_fold.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.farms_slice_surface.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                          C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class FarmsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"farms_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Farms:
+    """Mirror of `vFlowManager(height, width, filterSize, minEvtsOnPlane, ...)` + `runFileCopy`
+    (reference include/vFlow.h:99-104) on top of the C ABI."""
+
+    def __init__(self, width, height, filtersize=3, inlier_check=5, device=0, flags=0, max_batch=0,
+                 reorder_slack_us=0):
+        L = lib()
+        cfg = Config(width=width, height=height, filtersize=filtersize, inlier_check=inlier_check, device=device,
+                     flags=flags, max_batch=max_batch, reorder_slack_us=reorder_slack_us)
+        self._h = C.c_void_p()
+        rc = L.farms_create(C.byref(self._h), C.byref(cfg))
+        if rc != OK:
+            raise FarmsError(rc, "farms_create failed (no usable sm_100 CUDA device?)" if rc == ERR_CUDA else "farms_create")
+        self.width, self.height, self.device, self.flags = width, height, device, flags
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().farms_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != OK:
+            raise FarmsError(rc, lib().farms_last_error(self._h).decode())
+
+    def params(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(lib().farms_get_params(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"filtersize": a.value, "radius": b.value, "plane_size": c.value}
+
+    def set_t0(self, t0):
+        self._check(lib().farms_set_t0(self._h, int(t0)))
+
+    def num_events(self):
+        return lib().farms_num_events(self._h)
+
+    def timings(self):
+        t = Timings()
+        self._check(lib().farms_get_timings(self._h, C.byref(t)))
+        return t.as_dict()
+
+    def _columns(self, columns):
+        cols = list(columns) if columns is not None else [k for k in OUT_DTYPES if k != "det"]
+        if columns is None and self.flags & FLAG_DEBUG_DET:
+            cols.append("det")
+        return cols
+
+    def process(self, x, y, t, p=None, columns=None, out=None):
+        """Host arrays in (any integer dtype; copied to u16/u16/u64), dict of numpy columns out."""
+        x = np.ascontiguousarray(x, dtype=np.uint16)
+        y = np.ascontiguousarray(y, dtype=np.uint16)
+        t = np.ascontiguousarray(t, dtype=np.uint64)
+        n = len(x)
+        assert len(y) == n and len(t) == n
+        cols = self._columns(columns)
+        res = out if out is not None else {k: np.empty(n, OUT_DTYPES[k]) for k in cols}
+        o = Out()
+        for k in cols:
+            setattr(o, k, res[k].ctypes.data)
+        self._check(lib().farms_process_host(self._h, x.ctypes.data, y.ctypes.data, t.ctypes.data, None, n, C.byref(o)))
+        return res
+
+    def process_device(self, x, y, t, columns=None, out=None):
+        """torch CUDA tensors in (uint16, uint16, uint64 viewed as int64 is fine), dict of CUDA tensors out."""
+        import torch
+        n = x.numel()
+        cols = self._columns(columns)
+        tdt = {np.uint32: torch.int32, np.float64: torch.float64, np.uint8: torch.uint8, np.int8: torch.int8,
+               np.uint16: torch.int16}
+        res = out if out is not None else {k: torch.empty(n, dtype=tdt[OUT_DTYPES[k]], device=x.device) for k in cols}
+        o = Out()
+        for k in cols:
+            setattr(o, k, res[k].data_ptr())
+        torch.cuda.current_stream(x.device).synchronize()
+        self._check(lib().farms_process_device(self._h, x.data_ptr(), y.data_ptr(), t.data_ptr(), None, n, C.byref(o)))
+        return res
+
+    # --- state hand-over (device pointers) ---
+    def state_export(self, d_last_t, d_hit):
+        self._check(lib().farms_state_export(self._h, d_last_t.data_ptr(), d_hit.data_ptr()))
+
+    def state_fold(self, d_last_t, d_hit):
+        self._check(lib().farms_state_fold(self._h, d_last_t.data_ptr(), d_hit.data_ptr()))
+
+    def slice_surface(self, x, y, t, t0, d_last_t, d_hit):
+        self._check(lib().farms_slice_surface(self._h, x.data_ptr(), y.data_ptr(), t.data_ptr(), x.numel(), int(t0),
+                                              d_last_t.data_ptr(), d_hit.data_ptr()))

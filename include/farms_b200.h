@@ -1,0 +1,141 @@
+/* farms_b200.h -- C ABI of the B200-native FARMS (Fast Aperture-Robust Multi-Scale) event-flow path.
+ *
+ * The reference (himstien/aperture-robust-multiscale-optical-flow) has no FFI/plugin interface; its
+ * only internal seam is the public surface of `vFlowManager` (reference include/vFlow.h:99-114):
+ *     vFlowManager(int height, int width, int filterSize, int minEvtsOnPlane, std::string fileName);
+ *     long runFileCopy(unsigned long numEvents);   // batch path, src/vFlow.cpp:111-460
+ *     double getNumEvents();
+ * Each entry point below cites the piece of that seam it replaces.  Plain pointers and sizes only;
+ * no C++ or torch types cross the boundary.  All functions return 0 (FARMS_OK) or a negative
+ * farms_status and never throw.  A context is not re-entrant (one per host thread, like the
+ * reference object, whose scratch matrices are mutable members: include/vFlow.h:76-79).  The caller
+ * owns every buffer it passes in; the context owns all device memory, streams and events.
+ *
+ * There is no CPU fallback: farms_create fails with FARMS_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef FARMS_B200_H
+#define FARMS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FARMS_B200_ABI_VERSION 1
+
+typedef enum {
+  FARMS_OK = 0,
+  FARMS_ERR_ARG = -1,      /* bad argument (NULL, non-positive size, ...)                          */
+  FARMS_ERR_RANGE = -2,    /* an event lies outside the width x height sensor (the reference would
+                              index out of bounds: src/vFlow.cpp:264-267)                           */
+  FARMS_ERR_CUDA = -3,     /* CUDA runtime failure; farms_last_error() has the text                 */
+  FARMS_ERR_NOMEM = -4,    /* host or device allocation failed                                     */
+  FARMS_ERR_STATE = -5     /* call order violated (e.g. results before any submit)                 */
+} farms_status;
+
+typedef struct farms_ctx farms_ctx;
+
+/* Replaces the vFlowManager constructor arguments (src/main.cpp:186-187, src/vFlow.cpp:22-40).
+ * filtersize and inlier_check take the raw CLI values; filtersize is normalised exactly like
+ * src/vFlow.cpp:32-36 (<5 -> 3, even -> -1). Zero-initialise, then set what you need. */
+typedef struct {
+  int32_t width;            /* --width   (default 320, src/main.cpp:22)                            */
+  int32_t height;           /* --height  (default 320, src/main.cpp:21)                            */
+  int32_t filtersize;       /* --filtersize (default 3, src/main.cpp:23)                           */
+  int32_t inlier_check;     /* --inlierCheck = minEvtsOnPlane (default 5, src/main.cpp:24)         */
+  int32_t device;           /* CUDA device ordinal                                                 */
+  uint32_t flags;           /* FARMS_FLAG_*                                                        */
+  uint64_t max_batch;       /* events per internal device batch; 0 = default (16 Mi)               */
+  uint32_t reorder_slack_us;/* extra history (us) kept across batch boundaries for streams whose
+                               timestamps are not perfectly sorted; 0 = default (1000)            */
+  uint32_t reserved[7];
+} farms_config;
+
+#define FARMS_FLAG_DEBUG_DET 1u /* also produce the determinant column (farms_out.det)             */
+
+/* Per-event results, structure of arrays, n entries each, caller-allocated.  Any pointer may be
+ * NULL (that column is skipped).  Columns follow the reference's batch output row
+ * `x y t p globalR globalTheta Vx Vy localR localTheta scale` (src/vFlow.cpp:438); x, y, p are
+ * echoes of the input and stay with the caller.  For events without valid flow every column is 0
+ * except vx/vy, which carry the raw local result (src/vFlow.cpp:386-396). */
+typedef struct {
+  uint32_t *t_rel;       /* column 3: (uint32)(t - t0)                   src/vFlow.cpp:241, 373    */
+  double *global_r;      /* column 5                                     src/vFlow.cpp:365         */
+  double *global_theta;  /* column 6                                     src/vFlow.cpp:366         */
+  double *vx;            /* column 7                                     src/vFlow.cpp:378, 394    */
+  double *vy;            /* column 8                                                               */
+  double *local_r;       /* column 9                                     src/vFlow.cpp:324         */
+  double *local_theta;   /* column 10                                    src/vFlow.cpp:325         */
+  uint8_t *scale;        /* column 11: 0,5,...,50                        src/vFlow.cpp:380         */
+  uint8_t *valid;        /* 1 iff the event has valid local flow         src/vFlow.cpp:315         */
+  int8_t *best_window;   /* diagnostic: winning candidate window 0..8 (i outer, j inner,
+                            src/vFlow.cpp:870-910), -1 if none fits inside the sensor              */
+  uint16_t *inliers;     /* diagnostic: computeGrads' return value       src/vFlow.cpp:1352-1369   */
+  double *det;           /* diagnostic (FARMS_FLAG_DEBUG_DET): DET       src/vFlow.cpp:1316        */
+} farms_out;
+
+/* Stage timings of the most recent farms_process_* call, measured with CUDA events on the
+ * context's own stream (milliseconds, summed over internal batches). */
+typedef struct {
+  float total_ms;        /* first kernel/copy enqueued -> last result resident                    */
+  float h2d_ms;          /* host->device copies (host path only; overlapped time is not removed)  */
+  float ingest_ms;       /* K1: rebase, range check, pixel keys, prefix-max time                  */
+  float index_ms;        /* K2: stable radix sort by pixel + prev/next links                      */
+  float fit_ms;          /* K3: SAE advance + local plane fit                                     */
+  float bin_ms;          /* K4a: (time slab, tile) binning of flow events                         */
+  float pool_ms;         /* K4b: multi-scale pooling                                              */
+  float d2h_ms;          /* device->host copies (host path only)                                  */
+  uint64_t events;       /* events processed                                                       */
+  uint64_t valid_events; /* events with valid local flow                                           */
+  uint64_t kernel_launches;
+  uint64_t pool_candidates; /* candidate flow events inspected by the pooling kernel               */
+  uint64_t reserved[4];
+} farms_timings;
+
+/* ---- lifetime: replaces `vFlowManager vFlowM(...)` (src/main.cpp:186) ---- */
+int farms_create(farms_ctx **out, const farms_config *cfg);
+void farms_destroy(farms_ctx *ctx);
+const char *farms_last_error(const farms_ctx *ctx); /* never NULL; "" when no error */
+int farms_abi_version(void);
+
+/* Normalised parameters actually in use (src/vFlow.cpp:32-38): filtersize, radius, plane size. */
+int farms_get_params(const farms_ctx *ctx, int32_t *filtersize, int32_t *radius, int32_t *plane_size);
+
+/* ---- the hot path: replaces the event loop of runFileCopy (src/vFlow.cpp:223-414) ----
+ * Processes n more events in stream order.  State (surface of active events, flow surfaces, t0)
+ * persists across calls, so feeding a stream in pieces is equivalent to one call.  t0 is the first
+ * timestamp ever submitted (src/vFlow.cpp:194) unless farms_set_t0 was called.
+ * x,y: pixel coordinates (u16); t: timestamp in microseconds (u64; t - t0 is reduced to u32 exactly
+ * like the reference's `unsigned int`, include/vFlow.h:113); p: polarity (u8; has no effect on the
+ * numbers -- the ON and OFF surfaces always hold identical values, src/vFlow.cpp:349-353 -- and
+ * may be NULL).
+ *   _host  : x,y,t,p,out are host pointers (pinned or pageable); copies are inside the call.
+ *   _device: x,y,t,p,out are device pointers on cfg.device; the call returns after the work is
+ *            complete (it synchronises the context's stream). */
+int farms_process_host(farms_ctx *ctx, const uint16_t *x, const uint16_t *y, const uint64_t *t,
+                       const uint8_t *p, uint64_t n, const farms_out *out);
+int farms_process_device(farms_ctx *ctx, const uint16_t *x, const uint16_t *y, const uint64_t *t,
+                         const uint8_t *p, uint64_t n, const farms_out *out);
+
+/* replaces `getNumEvents()` (include/vFlow.h:108): events processed so far */
+uint64_t farms_num_events(const farms_ctx *ctx);
+int farms_get_timings(const farms_ctx *ctx, farms_timings *out);
+
+/* ---- state hand-over for time-sliced multi-GPU runs (no counterpart in the reference, which is
+ * single-threaded; the state is the reference's cSurf surface, src/vFlow.cpp:93, 267) ----
+ * All pointers are DEVICE pointers with width*height entries, flat index x*height + y like
+ * EventMatrix (include/EventMatrix.h:32-34). */
+int farms_set_t0(farms_ctx *ctx, uint64_t t0);
+/* last event time (relative to t0) and hit flag of every pixel */
+int farms_state_export(farms_ctx *ctx, uint32_t *d_last_t, uint8_t *d_hit);
+/* overwrite the state where d_hit != 0 (call in stream order: later slices win) */
+int farms_state_fold(farms_ctx *ctx, const uint32_t *d_last_t, const uint8_t *d_hit);
+/* stateless helper: last event per pixel of a device-resident event slice (t rebased by t0) */
+int farms_slice_surface(farms_ctx *ctx, const uint16_t *d_x, const uint16_t *d_y, const uint64_t *d_t,
+                        uint64_t n, uint64_t t0, uint32_t *d_last_t, uint8_t *d_hit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FARMS_B200_H */
