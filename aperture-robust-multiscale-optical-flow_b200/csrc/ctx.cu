@@ -513,6 +513,20 @@ int farms_get_timings(const farms_ctx *c, farms_timings *out) {
   return FARMS_OK;
 }
 
+int farms_reset(farms_ctx *c) {
+  if (!c) return FARMS_ERR_ARG;
+  CU(cudaSetDevice(c->cfg.device));
+  launch_sae_init(c->sae, c->npx, c->stream);
+  CU(cudaStreamSynchronize(c->stream));
+  c->have_t0 = false;
+  c->t0 = 0;
+  c->total_events = 0;
+  c->last_M = 0;
+  c->halo = 0;
+  c->err.clear();
+  return FARMS_OK;
+}
+
 int farms_set_t0(farms_ctx *c, uint64_t t0) {
   if (!c) return FARMS_ERR_ARG;
   if (c->total_events) return fail(c, FARMS_ERR_STATE, "farms_set_t0 after events were processed");

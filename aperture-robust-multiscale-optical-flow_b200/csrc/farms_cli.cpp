@@ -1,0 +1,269 @@
+// farms_cli.cpp -- the FARMS_Flow command line, drop-in for the reference's src/main.cpp.
+//
+// Same flags, defaults and file contract as the reference (src/main.cpp:21-47, 186-211):
+//   --help --filename <path without .txt> --height --width --filtersize --inlierCheck
+//   --numEvents | --numevents | --NUMEVENTS   --SERIAL <int>   --v <int>
+// Input  : <filename>.txt, one event per line "x y t p"                     (src/vFlow.cpp:150, 173-188)
+// Output : <filename>_FARMSOut_batch.txt, 11 columns, byte-compatible with the reference's batch mode
+//          "x y t p globalR globalTheta Vx Vy localR localTheta scale"      (src/vFlow.cpp:131, 436-440)
+//          <filename>_FARMSOut_.txt, the 8 columns the README documents
+//          "x y t p globalR globalTheta localR localTheta"                  (README.md:63)
+// Difference on purpose: the reference's default mode (--SERIAL 1) computes but writes nothing
+// (src/vFlow.cpp:485-489, 727-765); this CLI always runs the batch semantics and always writes.
+// All numbers come from the GPU through the C ABI (include/farms_b200.h); there is no CPU path here.
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "farms_b200.h"
+
+namespace {
+
+struct Options {
+  int height = 320, width = 320, filtersize = 3, inlier = 5, device = 0;  // src/main.cpp:21-24
+  unsigned long long num_events = 1ull << 63;                              // src/main.cpp:28
+  std::string filename = "/home/himanshu/POST_DOC/DATA/atisData/bar_square/multiPattern1_fixed_";  // :30
+  bool serial = true, verbose = false;
+};
+
+void usage() {
+  std::puts(
+      "Allowed options:\n"
+      "  --help                Displays this message\n"
+      "  --filename arg        add events file name without extension (.txt)\n"
+      "  --height arg          set sensor height\n"
+      "  --width arg           set sensor width\n"
+      "  --filtersize arg      set size of neighbor for plane fitting\n"
+      "  --inlierCheck arg     set minimum number of inliers to validate plane\n"
+      "  --numEvents arg       set max number of events to process\n"
+      "  --numevents arg       set max number of events to process\n"
+      "  --NUMEVENTS arg       set max number of events to process\n"
+      "  --SERIAL arg          Serial or Batch processing\n"
+      "  --v arg               set verbose to 1 for full debug mode\n"
+      "  --device arg          CUDA device ordinal (extension)\n");
+}
+
+bool parse_int(const std::string &s, int &out) {
+  char *end = nullptr;
+  long v = std::strtol(s.c_str(), &end, 10);
+  if (end == s.c_str() || *end) return false;
+  out = (int)v;
+  return true;
+}
+
+// Returns 0 to continue, 1 = exit with error, 2 = exit ok (--help)
+int parse_args(int argc, char **argv, Options &o) {
+  long long ne[3] = {-1, -1, -1};  // numEvents, numevents, NUMEVENTS
+  bool ne_set[3] = {false, false, false};
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    if (a.rfind("--", 0) != 0) {
+      std::fprintf(stderr, "error: too many positional options have been specified on the command line\n");
+      return 1;
+    }
+    std::string name = a.substr(2), val;
+    bool has_val = false;
+    size_t eq = name.find('=');
+    if (eq != std::string::npos) {
+      val = name.substr(eq + 1);
+      name = name.substr(0, eq);
+      has_val = true;
+    }
+    if (name == "help") {
+      usage();
+      return 2;
+    }
+    static const char *known[] = {"filename", "height", "width", "filtersize", "inlierCheck", "numEvents",
+                                  "numevents", "NUMEVENTS", "SERIAL", "v", "device"};
+    bool ok = false;
+    for (const char *k : known) ok |= name == k;
+    if (!ok) {
+      std::fprintf(stderr, "error: unrecognised option '--%s'\n", name.c_str());
+      return 1;
+    }
+    if (!has_val) {
+      if (i + 1 >= argc) {
+        std::fprintf(stderr, "error: the required argument for option '--%s' is missing\n", name.c_str());
+        return 1;
+      }
+      val = argv[++i];
+    }
+    int iv = 0;
+    if (name != "filename" && !parse_int(val, iv)) {
+      std::fprintf(stderr, "error: the argument ('%s') for option '--%s' is invalid\n", val.c_str(), name.c_str());
+      return 1;
+    }
+    if (name == "filename") { o.filename = val; std::printf("filename set to %s.\n", val.c_str()); }
+    else if (name == "height") { o.height = iv; std::printf("height set to %d.\n", iv); }
+    else if (name == "width") { o.width = iv; std::printf("width set to %d.\n", iv); }
+    else if (name == "filtersize") { o.filtersize = iv; std::printf("filtersize set to %d.\n", iv); }
+    else if (name == "inlierCheck") { o.inlier = iv; std::printf("inlierCheck set to %d.\n", iv); }
+    else if (name == "numEvents" || name == "numevents" || name == "NUMEVENTS") {
+      const int k = name == "numEvents" ? 0 : name == "numevents" ? 1 : 2;
+      ne[k] = iv;
+      ne_set[k] = true;
+    } else if (name == "SERIAL") {
+      o.serial = iv == 1;
+      std::puts(o.serial ? "Running serially " : "Running batch ");
+    } else if (name == "v") { o.verbose = iv == 1; std::printf("Verbose mode set to %d\n", iv); }
+    else if (name == "device") { o.device = iv; }
+  }
+  // the reference honours the spellings in the order numEvents, numevents, NUMEVENTS (src/main.cpp:131-151)
+  // and converts the int to unsigned long
+  for (int k = 0; k < 3; k++)
+    if (ne_set[k]) {
+      o.num_events = (unsigned long long)ne[k];
+      std::printf("numEvents set to %lld.\n", ne[k]);
+      break;
+    }
+  return 0;
+}
+
+struct Events {
+  std::vector<uint16_t> x, y;
+  std::vector<uint64_t> t;
+  std::vector<int32_t> xi, yi, pol;  // echoes for the output rows
+};
+
+// Parses like `stream >> x >> y >> time_ >> pol` per line (src/vFlow.cpp:173-188): a field that fails to
+// parse leaves that and all later variables at the previous line's values.
+bool read_events(const std::string &path, unsigned long long maxn, Events &ev, std::string &err) {
+  FILE *f = std::fopen(path.c_str(), "rb");
+  if (!f) {
+    err = "Unable to open file " + path;
+    return false;
+  }
+  std::fseek(f, 0, SEEK_END);
+  long sz = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  std::vector<char> buf((size_t)sz + 1);
+  size_t got = std::fread(buf.data(), 1, (size_t)sz, f);
+  std::fclose(f);
+  buf[got] = 0;
+  long long x = 0, y = 0, p = 0;
+  unsigned long long t = 0;
+  const char *s = buf.data(), *end = buf.data() + got;
+  size_t guess = got / 16 + 16;
+  ev.x.reserve(guess); ev.y.reserve(guess); ev.t.reserve(guess);
+  ev.xi.reserve(guess); ev.yi.reserve(guess); ev.pol.reserve(guess);
+  while (s < end && ev.x.size() < maxn) {
+    const char *eol = (const char *)std::memchr(s, '\n', (size_t)(end - s));
+    if (!eol) eol = end;
+    const char *q = s;
+    long long vals[4];
+    int nf = 0;
+    while (nf < 4) {
+      while (q < eol && (*q == ' ' || *q == '\t' || *q == '\r')) q++;
+      if (q >= eol) break;
+      bool neg = false;
+      if (*q == '-' || *q == '+') { neg = *q == '-'; q++; }
+      if (q >= eol || *q < '0' || *q > '9') break;
+      unsigned long long v = 0;
+      while (q < eol && *q >= '0' && *q <= '9') v = v * 10 + (unsigned long long)(*q++ - '0');
+      vals[nf++] = neg ? -(long long)v : (long long)v;
+    }
+    if (nf > 0) x = vals[0];
+    if (nf > 1) y = vals[1];
+    if (nf > 2) t = (unsigned long long)vals[2];
+    if (nf > 3) p = vals[3];
+    if (x < 0 || x > 65535 || y < 0 || y > 65535) {
+      err = "event " + std::to_string(ev.x.size()) + " has coordinates outside the sensor";
+      return false;
+    }
+    ev.x.push_back((uint16_t)x); ev.y.push_back((uint16_t)y); ev.t.push_back(t);
+    ev.xi.push_back((int32_t)x); ev.yi.push_back((int32_t)y);
+    ev.pol.push_back(p < 0 ? 0 : (int32_t)p);  // src/vFlow.cpp:246-247
+    s = eol + 1;
+  }
+  return true;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  Options o;
+  int pr = parse_args(argc, argv, o);
+  if (pr == 2) return 0;
+  if (pr == 1) return 1;
+
+  farms_config cfg;
+  std::memset(&cfg, 0, sizeof cfg);
+  cfg.width = o.width; cfg.height = o.height; cfg.filtersize = o.filtersize; cfg.inlier_check = o.inlier;
+  cfg.device = o.device;
+  farms_ctx *ctx = nullptr;
+  int rc = farms_create(&ctx, &cfg);
+  if (rc != FARMS_OK) {
+    std::fprintf(stderr, "error: farms_create failed (%d): a B200-class CUDA device is required\n", rc);
+    return 1;
+  }
+  std::printf("[debug Main] : size of lastFlowTime is [sx sy]: [%d %d]\n", o.width, o.height);
+
+  const std::string in_path = o.filename + ".txt";
+  std::printf("%s\nReading input file \n", in_path.c_str());
+  Events ev;
+  std::string err;
+  if (!read_events(in_path, o.num_events, ev, err)) {
+    std::fprintf(stderr, "error: %s\n", err.c_str());
+    farms_destroy(ctx);
+    return 1;
+  }
+  const size_t n = ev.x.size();
+  std::printf("Done reading %zu Events.\n", n);
+  if (n == 0) {  // the reference dies in T.at(0) (src/vFlow.cpp:194)
+    std::fprintf(stderr, "error: no events in %s\n", in_path.c_str());
+    farms_destroy(ctx);
+    return 1;
+  }
+  std::printf("First time = %llu\nProcessing events \n", (unsigned long long)ev.t[0]);
+
+  std::vector<uint32_t> t_rel(n);
+  std::vector<double> gr(n), gth(n), vx(n), vy(n), lr(n), lth(n);
+  std::vector<uint8_t> scale(n);
+  farms_out out;
+  std::memset(&out, 0, sizeof out);
+  out.t_rel = t_rel.data(); out.global_r = gr.data(); out.global_theta = gth.data(); out.vx = vx.data();
+  out.vy = vy.data(); out.local_r = lr.data(); out.local_theta = lth.data(); out.scale = scale.data();
+
+  const auto a = std::chrono::system_clock::now();
+  rc = farms_process_host(ctx, ev.x.data(), ev.y.data(), ev.t.data(), nullptr, n, &out);
+  const auto b = std::chrono::system_clock::now();
+  if (rc != FARMS_OK) {
+    std::fprintf(stderr, "error: %s\n", farms_last_error(ctx));
+    farms_destroy(ctx);
+    return 1;
+  }
+  const long usec = (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count();
+  std::printf("\nDone processing!\n\nWriting output file.\n");
+
+  const std::string out11 = o.filename + "_FARMSOut_batch.txt", out8 = o.filename + "_FARMSOut_.txt";
+  FILE *f11 = std::fopen(out11.c_str(), "w"), *f8 = std::fopen(out8.c_str(), "w");
+  if (!f11 || !f8) {
+    std::fprintf(stderr, "error: cannot write %s\n", f11 ? out8.c_str() : out11.c_str());
+    return 1;
+  }
+  for (size_t i = 0; i < n; i++) {
+    // ostream << double with default flags == "%g"; T_out is a vector<int> (src/vFlow.cpp:136, 373)
+    std::fprintf(f11, "%d %d %d %d %g %g %g %g %g %g %d\n", ev.xi[i], ev.yi[i], (int32_t)t_rel[i], ev.pol[i], gr[i],
+                 gth[i], vx[i], vy[i], lr[i], lth[i], (int)scale[i]);
+    std::fprintf(f8, "%d %d %d %d %g %g %g %g\n", ev.xi[i], ev.yi[i], (int32_t)t_rel[i], ev.pol[i], gr[i], gth[i],
+                 lr[i], lth[i]);
+  }
+  std::fclose(f11);
+  std::fclose(f8);
+
+  farms_timings tm;
+  farms_get_timings(ctx, &tm);
+  // same line as src/main.cpp:209, but with real (not integer-divided) seconds
+  const double sec = (double)usec / 1e6;
+  std::printf("[Benchmark Main] : Processing time   : %ld usec %g sec  with rate of : %g events/sec\n", usec, sec,
+              sec > 0 ? ((double)farms_num_events(ctx) - 1) / sec : 0.0);
+  std::printf("[farms_b200] device %.3f ms (ingest %.3f, index %.3f, fit %.3f, bin %.3f, pool %.3f), valid %llu of %llu\n",
+              tm.total_ms, tm.ingest_ms, tm.index_ms, tm.fit_ms, tm.bin_ms, tm.pool_ms,
+              (unsigned long long)tm.valid_events, (unsigned long long)tm.events);
+  farms_destroy(ctx);
+  return 0;
+}

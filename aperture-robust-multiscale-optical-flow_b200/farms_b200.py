@@ -16,7 +16,7 @@ OK, ERR_ARG, ERR_RANGE, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4, -5
 FLAG_DEBUG_DET = 1
 
 EXPORTS = [
-    "farms_abi_version", "farms_create", "farms_destroy", "farms_last_error", "farms_get_params",
+    "farms_abi_version", "farms_create", "farms_destroy", "farms_reset", "farms_last_error", "farms_get_params",
     "farms_process_host", "farms_process_device", "farms_num_events", "farms_get_timings", "farms_set_t0",
     "farms_state_export", "farms_state_fold", "farms_slice_surface",
 ]
@@ -62,6 +62,7 @@ def lib():
         L.farms_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Config)]
         L.farms_destroy.argtypes = [C.c_void_p]
         L.farms_destroy.restype = None
+        L.farms_reset.argtypes = [C.c_void_p]
         L.farms_last_error.argtypes = [C.c_void_p]
         L.farms_last_error.restype = C.c_char_p
         L.farms_get_params.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 3
@@ -115,6 +116,9 @@ class Farms:
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
         self._check(lib().farms_get_params(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"filtersize": a.value, "radius": b.value, "plane_size": c.value}
+
+    def reset(self):
+        self._check(lib().farms_reset(self._h))
 
     def set_t0(self, t0):
         self._check(lib().farms_set_t0(self._h, int(t0)))

@@ -97,6 +97,9 @@ typedef struct {
 int farms_create(farms_ctx **out, const farms_config *cfg);
 void farms_destroy(farms_ctx *ctx);
 const char *farms_last_error(const farms_ctx *ctx); /* never NULL; "" when no error */
+/* Back to the freshly constructed state (empty surfaces, no t0) while keeping device buffers: the
+ * equivalent of constructing a new vFlowManager for the next recording. */
+int farms_reset(farms_ctx *ctx);
 int farms_abi_version(void);
 
 /* Normalised parameters actually in use (src/vFlow.cpp:32-38): filtersize, radius, plane size. */
