@@ -62,7 +62,7 @@ struct farms_ctx {
   int32_t *nextp = nullptr;
   double *vx = nullptr, *vy = nullptr, *len = nullptr, *theta = nullptr, *lcx = nullptr, *lcy = nullptr,
          *det = nullptr, *gr = nullptr, *gth = nullptr, *pay = nullptr;
-  uint8_t *valid = nullptr, *scale = nullptr;
+  uint8_t *valid = nullptr, *scale = nullptr, *done = nullptr;
   int8_t *bw = nullptr;
   uint16_t *inl = nullptr;
   uint4 *rec = nullptr;
@@ -140,7 +140,7 @@ int alloc_working(farms_ctx *c, size_t cap) {
   A(ex, cap) A(ey, cap) A(et, cap) A(em, cap) A(keyA, cap) A(valA, cap) A(keyB, cap) A(valB, cap)
   A(pixkeep, cap) A(flags, cap) A(slab_ids, cap + 1) A(prevp, cap) A(nextp, cap)
   A(vx, cap) A(vy, cap) A(len, cap) A(theta, cap) A(lcx, cap) A(lcy, cap) A(gr, cap) A(gth, cap)
-  A(pay, 3 * cap) A(valid, cap) A(scale, cap) A(bw, cap) A(inl, cap) A(rec, cap)
+  A(pay, 3 * cap) A(done, cap) A(valid, cap) A(scale, cap) A(bw, cap) A(inl, cap) A(rec, cap)
   if (c->cfg.flags & FARMS_FLAG_DEBUG_DET) { A(det, cap) } else c->det = nullptr;
 #undef A
   if ((rc = ensure(c, c->sort_temp, radix_sort_temp_bytes(cap)))) return rc;
@@ -243,13 +243,15 @@ int run_batch(farms_ctx *c, const uint16_t *dx, const uint16_t *dy, const uint64
   CU(cudaEventRecord(c->ev[EV_FIT], s));
 
   // ---- K4a pooling index: dense time slabs x tiles ----
-  launch_slab_flags(c->em, m, c->flags, s);
+  CU(cudaMemsetAsync(c->d_small, 0, 16, s));
+  launch_slab_flags(c->em, c->et, m, c->flags, c->d_small + 1, s);
   exclusive_scan_u32(c->flags, c->flags, m, c->scan_temp.p, s, L);
   k_nslabs<<<1, 1, 0, s>>>(c->em, c->flags, (uint32_t)m, c->d_small);
   *L += 2;
-  CU(cudaMemcpyAsync(c->h_small, c->d_small, 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(c->h_small, c->d_small, 8, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   const size_t nslabs = c->h_small[0];
+  const int monotone = c->h_small[1] == 0;
   PoolGeom g{};
   g.W = c->W;
   g.H = c->H;
@@ -261,14 +263,15 @@ int run_batch(farms_ctx *c, const uint16_t *dx, const uint16_t *dy, const uint64
     g.tile_shift++;
   }
   const size_t ncells = nslabs * (size_t)g.ntx * g.nty;
-  if (ncells >= (1ull << 32)) return fail(c, FARMS_ERR_NOMEM, "pooling index too large (%zu cells)", ncells);
+  if (ncells >= (1ull << 31)) return fail(c, FARMS_ERR_NOMEM, "pooling index too large (%zu cells)", ncells);
   if ((rc = ensure(c, c->cell_start, (ncells + 1) * sizeof(uint32_t)))) return rc;
-  launch_cell_keys(c->ex, c->ey, c->em, c->flags, m, g, c->keyA, c->valA, c->slab_ids, s);
-  which = radix_sort_pairs(c->keyA, c->valA, c->keyB, c->valB, m, bits_for(ncells), c->sort_temp.p, s, L);
+  CU(cudaMemsetAsync(c->cell_start.p, 0, (ncells + 1) * sizeof(uint32_t), s));
+  launch_cell_keys(c->ex, c->ey, c->em, c->flags, c->len, m, g, (uint32_t)ncells, c->keyA, c->valA, c->slab_ids, s);
+  which = radix_sort_pairs(c->keyA, c->valA, c->keyB, c->valB, m, bits_for(ncells + 1), c->sort_temp.p, s, L);
   skeys = which ? c->keyB : c->keyA;
   svals = which ? c->valB : c->valA;
-  launch_build_records(skeys, svals, m, c->ex, c->ey, c->et, c->nextp, c->len, c->lcx, c->lcy, c->rec, c->pay,
-                       (uint32_t *)c->cell_start.p, ncells, s);
+  launch_build_records(skeys, svals, m, c->ex, c->ey, c->et, c->nextp, c->len, c->lcx, c->lcy, monotone, c->rec,
+                       c->pay, (uint32_t *)c->cell_start.p, (uint32_t)ncells, s);
   *L += 2;
   CU(cudaEventRecord(c->ev[EV_BIN], s));
 
@@ -276,10 +279,12 @@ int run_batch(farms_ctx *c, const uint16_t *dx, const uint16_t *dy, const uint64
   CU(cudaMemsetAsync(c->gr, 0, n * 8, s));
   CU(cudaMemsetAsync(c->gth, 0, n * 8, s));
   CU(cudaMemsetAsync(c->scale, 0, n, s));
-  CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), s));
-  launch_pooling(c->rec, c->pay, (const uint32_t *)c->cell_start.p, skeys, c->slab_ids, m, (int)h, g, c->gr, c->gth,
-                 c->scale, c->d_work, c->d_counters + 1, c->num_sms, s);
-  *L += 1;
+  CU(cudaMemsetAsync(c->d_work, 0, 2 * sizeof(unsigned int), s));
+  CU(cudaMemsetAsync(c->done, 0, m, s));
+  const int fast = monotone && !(c->cfg.flags & FARMS_FLAG_GENERIC_POOLING);
+  *L += launch_pooling(c->rec, c->pay, (const uint32_t *)c->cell_start.p, c->slab_ids, c->done, m, (uint32_t)ncells,
+                       (int)h, (int)nslabs, g, fast, c->gr, c->gth, c->scale, c->d_work, c->d_counters + 1,
+                       c->num_sms, s);
   CU(cudaEventRecord(c->ev[EV_POOL], s));
 
   // ---- results of the new events ----
@@ -457,7 +462,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   ok &= cudaMalloc((void **)&c->hlcy, HALO_CAP * 8) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->d_err, sizeof(int)) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->d_counters, 2 * sizeof(unsigned long long)) == cudaSuccess;
-  ok &= cudaMalloc((void **)&c->d_work, sizeof(unsigned int)) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->d_work, 2 * sizeof(unsigned int)) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->d_small, 64) == cudaSuccess;
   ok &= cudaMallocHost((void **)&c->h_small, 64) == cudaSuccess;
   if (!ok) return bail(FARMS_ERR_NOMEM);

@@ -66,7 +66,8 @@ void launch_halo_keys(const uint16_t *ex, const uint16_t *ey, size_t h, int H, u
                       cudaStream_t s);
 void launch_links(const uint32_t *skeys, const uint32_t *svals, const uint32_t *et, const uint2 *sae, size_t m,
                   int2 *prevp, int32_t *nextp, cudaStream_t s);
-void launch_slab_flags(const uint32_t *em, size_t m, uint32_t *flags, cudaStream_t s);
+void launch_slab_flags(const uint32_t *em, const uint32_t *et, size_t m, uint32_t *flags, uint32_t *nonmono,
+                       cudaStream_t s);
 void launch_slice_surface(const uint16_t *x, const uint16_t *y, const uint64_t *t, size_t n, uint64_t t0, int H,
                           unsigned long long *packed, cudaStream_t s);
 void launch_unpack_surface(const unsigned long long *packed, size_t npx, uint32_t *last_t, uint8_t *hit,
@@ -84,13 +85,16 @@ void launch_sae_export(const uint2 *sae, size_t npx, uint32_t *last_t, uint8_t *
 void launch_sae_fold(uint2 *sae, size_t npx, const uint32_t *last_t, const uint8_t *hit, cudaStream_t s);
 
 // ---- pooling.cu ----
-void launch_cell_keys(const uint16_t *ex, const uint16_t *ey, const uint32_t *em, const uint32_t *excl, size_t m,
-                      PoolGeom g, uint32_t *keys, uint32_t *idx, uint32_t *slab_ids, cudaStream_t s);
+void launch_cell_keys(const uint16_t *ex, const uint16_t *ey, const uint32_t *em, const uint32_t *excl,
+                      const double *len, size_t m, PoolGeom g, uint32_t ncells, uint32_t *keys, uint32_t *idx,
+                      uint32_t *slab_ids, cudaStream_t s);
 void launch_build_records(const uint32_t *skeys, const uint32_t *sidx, size_t m, const uint16_t *ex,
                           const uint16_t *ey, const uint32_t *et, const int32_t *nextp, const double *len,
-                          const double *lcx, const double *lcy, uint4 *rec, double *pay, uint32_t *cell_start,
-                          size_t ncells, cudaStream_t s);
-void launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_start, const uint32_t *skeys,
-                    const uint32_t *slab_ids, size_t m, int h, PoolGeom g, double *global_r, double *global_theta,
-                    uint8_t *scale, unsigned int *work_counter, unsigned long long *cand_count, int num_sms,
-                    cudaStream_t s);
+                          const double *lcx, const double *lcy, int monotone, uint4 *rec, double *pay,
+                          uint32_t *cell_start, uint32_t ncells, cudaStream_t s);
+// returns the number of kernels launched.  work_counter: two zeroed words; done: m zeroed bytes.
+int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_start, const uint32_t *slab_ids,
+                   uint8_t *done, size_t m, uint32_t ncells, int h, int nslabs, PoolGeom g, int fast,
+                   double *global_r, double *global_theta, uint8_t *scale, unsigned int *work_counter,
+                   unsigned long long *cand_count, int num_sms, cudaStream_t s);
+int pool_tile_smem_bytes();

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libfarms_b200.so")
 
 OK, ERR_ARG, ERR_RANGE, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4, -5
 FLAG_DEBUG_DET = 1
+FLAG_GENERIC_POOLING = 2
 
 EXPORTS = [
     "farms_abi_version", "farms_create", "farms_destroy", "farms_reset", "farms_last_error", "farms_get_params",

@@ -52,7 +52,8 @@ typedef struct {
   uint32_t reserved[7];
 } farms_config;
 
-#define FARMS_FLAG_DEBUG_DET 1u /* also produce the determinant column (farms_out.det)             */
+#define FARMS_FLAG_DEBUG_DET 1u       /* also produce the determinant column (farms_out.det)       */
+#define FARMS_FLAG_GENERIC_POOLING 2u /* pool every event with the general kernel (testing aid)    */
 
 /* Per-event results, structure of arrays, n entries each, caller-allocated.  Any pointer may be
  * NULL (that column is skipped).  Columns follow the reference's batch output row
