@@ -416,6 +416,14 @@ extern "C" {
 
 int farms_abi_version(void) { return FARMS_B200_ABI_VERSION; }
 
+int farms_normalize_filtersize(int fs, int32_t *radius, int32_t *plane_size) {
+  if (fs < 5) fs = 3;        // src/vFlow.cpp:33
+  if (!(fs % 2)) fs--;       // :34
+  if (radius) *radius = fs / 2;        // :36
+  if (plane_size) *plane_size = fs * fs;  // :38
+  return fs;
+}
+
 int farms_create(farms_ctx **out, const farms_config *cfg) {
   if (!out || !cfg) return FARMS_ERR_ARG;
   *out = nullptr;
@@ -426,12 +434,10 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   c->cfg = *cfg;
   c->W = cfg->width;
   c->H = cfg->height;
-  int fs = cfg->filtersize;  // src/vFlow.cpp:32-38
-  if (fs < 5) fs = 3;
-  if (!(fs % 2)) fs--;
-  c->fs = fs;
-  c->r = fs / 2;
-  c->P = fs * fs;
+  int32_t rr = 0, pp = 0;
+  c->fs = farms_normalize_filtersize(cfg->filtersize, &rr, &pp);
+  c->r = rr;
+  c->P = pp;
   c->min_inl = cfg->inlier_check;
   c->npx = (size_t)c->W * c->H;
   auto bail = [&](int code) {

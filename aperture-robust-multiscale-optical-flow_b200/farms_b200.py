@@ -17,7 +17,7 @@ FLAG_DEBUG_DET = 1
 FLAG_GENERIC_POOLING = 2
 
 EXPORTS = [
-    "farms_abi_version", "farms_create", "farms_destroy", "farms_reset", "farms_last_error", "farms_get_params",
+    "farms_abi_version", "farms_create", "farms_destroy", "farms_reset", "farms_last_error", "farms_normalize_filtersize", "farms_get_params",
     "farms_process_host", "farms_process_device", "farms_num_events", "farms_get_timings", "farms_set_t0",
     "farms_state_export", "farms_state_fold", "farms_slice_surface",
 ]
@@ -66,6 +66,7 @@ def lib():
         L.farms_reset.argtypes = [C.c_void_p]
         L.farms_last_error.argtypes = [C.c_void_p]
         L.farms_last_error.restype = C.c_char_p
+        L.farms_normalize_filtersize.argtypes = [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.farms_get_params.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 3
         for f in (L.farms_process_host, L.farms_process_device):
             f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Out)]

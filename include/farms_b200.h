@@ -103,6 +103,9 @@ const char *farms_last_error(const farms_ctx *ctx); /* never NULL; "" when no er
 int farms_reset(farms_ctx *ctx);
 int farms_abi_version(void);
 
+/* The reference's filter-size normalisation (src/vFlow.cpp:32-38) as a pure host function: returns the
+ * normalised filtersize and stores fRad and planeSize.  Needs no device. */
+int farms_normalize_filtersize(int filtersize, int32_t *radius, int32_t *plane_size);
 /* Normalised parameters actually in use (src/vFlow.cpp:32-38): filtersize, radius, plane size. */
 int farms_get_params(const farms_ctx *ctx, int32_t *filtersize, int32_t *radius, int32_t *plane_size);
 

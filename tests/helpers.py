@@ -102,8 +102,18 @@ def compare(got, ref, what=""):
             bad = ~same & ~(np.abs(a - b) <= R_RTOL * np.abs(b))
         return bad
 
-    rep["vx"] = int(np.count_nonzero(rel_bad(got["vx"], ref["vx"])))
-    rep["vy"] = int(np.count_nonzero(rel_bad(got["vy"], ref["vy"])))
+    # Vx, Vy (columns 7, 8) are components of one vector: a component that is ~1e-16 of the length (flow along
+    # an axis: cos(pi/2) = 6e-17) carries no digits, so each is checked against 1e-4 of the vector's length.
+    with np.errstate(invalid="ignore", over="ignore"):
+        mag = np.hypot(ref["vx"], ref["vy"])
+
+    def comp_bad(a, b):
+        with np.errstate(invalid="ignore"):
+            same = (a == b) | (np.isnan(a) & np.isnan(b))
+            return ~same & ~(np.abs(a - b) <= R_RTOL * mag)
+
+    rep["vx"] = int(np.count_nonzero(comp_bad(got["vx"], ref["vx"])))
+    rep["vy"] = int(np.count_nonzero(comp_bad(got["vy"], ref["vy"])))
     rep["local_r"] = int(np.count_nonzero(rel_bad(got["local_r"], ref["local_r"])))
     rep["local_theta"] = int(np.count_nonzero(angle_diff(got["local_theta"], ref["local_theta"])[v] > ANGLE_ATOL))
     rep["global_r"] = int(np.count_nonzero(rel_bad(got["global_r"], ref["global_r"])))

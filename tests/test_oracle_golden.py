@@ -1,0 +1,105 @@
+"""The CPU oracle (oracle/farms_oracle.c) pinned against golden vectors produced by the reference's own
+sources (tests/golden/make_golden.py -> oracle/_ref/FARMS_Flow).  CPU only."""
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, run_oracle
+from kat_streams import HASH_CASES, SYNTH_CASES, TEXT_CASES, write_txt
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+META = json.load(open(os.path.join(GOLDEN, "golden.json")))
+CLI = os.path.join(ROOT, "oracle", "farms_oracle_cli")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cli():
+    if not os.path.exists(CLI):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "farms_oracle_cli"])
+
+
+def oracle_text(tmp_path, name, w, h, fs, inl, x, y, t, p):
+    base = str(tmp_path / name)
+    write_txt(base + ".txt", x, y, t, p)
+    subprocess.run([CLI, str(w), str(h), str(fs), str(inl), base], check=True, capture_output=True)
+    return open(base + "_FARMSOut_oracle.txt", "rb").read()
+
+
+@pytest.mark.parametrize("name", sorted(TEXT_CASES))
+def test_text_golden(name, tmp_path):
+    w, h, fs, inl, build = TEXT_CASES[name]
+    got = oracle_text(tmp_path, name, w, h, fs, inl, *build()).decode().splitlines()
+    ref = open(os.path.join(GOLDEN, name + ".ref.txt")).read().splitlines()
+    assert len(got) == len(ref) == META[name]["rows"]
+    if name == "kat_plane_16x12":
+        # width > height on a heap-allocated surface: the reference reads past the end of its vectors
+        # (src/vFlow.cpp:1000-1002) and its scale choice for 5 early events depends on heap contents.
+        # Everything but the scale column must still agree; the scale column may differ on those rows only.
+        diff = [i for i, (a, b) in enumerate(zip(got, ref)) if a != b]
+        assert all(got[i].split()[:10] == ref[i].split()[:10] for i in diff)
+        assert len(diff) <= 5 and all(int(ref[i].split()[2]) < 500 for i in diff)
+    else:
+        assert got == ref
+
+
+def test_appendix_b_known_answer():
+    """analytic plane a = 1e-4 s/px, b = 3e-5 s/px on a 16x12 sensor."""
+    w, h, fs, inl, build = TEXT_CASES["kat_plane_16x12"]
+    x, y, t, p = build()
+    r = run_oracle(w, h, fs, inl, x, y, t, p)
+    assert int(r["valid"].sum()) == 184
+    inval = sorted((int(a), int(b)) for a, b, v in zip(x, y, r["valid"]) if not v)
+    assert inval == [(0, 0), (0, 1), (0, 2), (0, 3), (1, 0), (1, 1), (1, 2), (1, 3)]
+    v = r["valid"].astype(bool)
+    a, b = 1e-4, 3e-5
+    assert np.allclose(r["vx"][v], b / (a * a + b * b), rtol=1e-9)   # axes are swapped in the reference
+    assert np.allclose(r["vy"][v], a / (a * a + b * b), rtol=1e-9)
+    assert np.allclose(r["local_r"][v], 9578.26, rtol=1e-6)
+    assert np.allclose(r["local_theta"][v], 1.27934, atol=1e-5)
+    # pixel (0,4): exactly 5 inliers >= inlierCheck 5; pixel (1,1): singular AtA => DET < 1
+    i04 = [i for i in range(len(x)) if (x[i], y[i]) == (0, 4)][0]
+    i11 = [i for i in range(len(x)) if (x[i], y[i]) == (1, 1)][0]
+    assert r["inliers"][i04] == 5 and r["valid"][i04] == 1
+    assert r["det"][i11] < 1 and r["valid"][i11] == 0
+
+
+@pytest.mark.parametrize("name", sorted(HASH_CASES))
+def test_hash_golden(name, tmp_path):
+    w, h, fs, inl, build = HASH_CASES[name]
+    raw = oracle_text(tmp_path, name, w, h, fs, inl, *build())
+    assert hashlib.sha256(raw).hexdigest() == META[name]["sha256"]
+
+
+@pytest.mark.parametrize("name", sorted(SYNTH_CASES))
+def test_synthetic_scene_golden(name, tmp_path):
+    from farms_synth import Synth
+    cfg, n, start = SYNTH_CASES[name]
+    s = Synth(cfg)
+    x, y, t, p = s.first(n, start)
+    inp = np.stack([x.astype(np.int64), y.astype(np.int64), t.astype(np.int64), p.astype(np.int64)], 1)
+    assert hashlib.sha256(inp.tobytes()).hexdigest() == META[name]["input_sha256"], "generator changed"
+    raw = oracle_text(tmp_path, name, s.width, s.height, s.filtersize, 5, x, y, t, p)
+    assert hashlib.sha256(raw).hexdigest() == META[name]["sha256"]
+    assert raw.decode().splitlines()[:0] == []
+    rows = raw.decode().splitlines()
+    assert sum(1 for r in rows if float(r.split()[4]) > 0) == META[name]["valid"]
+
+
+def test_oracle_streaming_equals_one_shot():
+    from helpers import Oracle
+    w, h, fs, inl, build = HASH_CASES["sweeps_160x120_fs5"]
+    x, y, t, p = build()
+    x, y, t, p = x[:20000], y[:20000], t[:20000], p[:20000]
+    full = run_oracle(w, h, fs, inl, x, y, t, p)
+    o = Oracle(w, h, fs, inl)
+    # t0 is the first timestamp ever seen, so later pieces must be rebased by the caller: feed raw times
+    parts = []
+    o2 = Oracle(w, h, fs, inl)
+    for a, b in [(0, 7000), (7000, 7001), (7001, 20000)]:
+        parts.append(o2.process(x[a:b], y[a:b], t[a:b], p[a:b]))
+    for k in ("valid", "inliers", "scale", "global_r", "vx"):
+        assert np.array_equal(np.concatenate([q[k] for q in parts]), full[k], equal_nan=(k in ("global_r", "vx")))
