@@ -177,18 +177,16 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    # this rank's time slice (stream microseconds), with the causal halo in front
+    # this rank's time slice (stream microseconds), with the causal halo in front (slicing.py)
+    import slicing
     D = int(args.events / syn.rate * 1e6)
-    t_begin = rank * D
-    t_lo = max(0, t_begin - HALO_US)
-    t_end = (rank + 1) * D
+    plan = slicing.slice_plan(rank, world, D, HALO_US)
     tg0 = time.time()
-    x, y, t, p = syn.time_range(t_lo, t_end, pinned=True)
+    x, y, t, p = syn.time_range(plan.t_lo, plan.t_end, pinned=True)
     gen_s = time.time() - tg0
     n_all = len(x)
-    t_stream = t.astype(np.int64) - 1000
-    n_halo = int(np.searchsorted(t_stream, t_begin, side="left"))   # outputs of [0, n_halo) are discarded
-    n_surf = int(np.searchsorted(t_stream, t_end - HALO_US, side="left"))  # this rank's share of the SAE exchange
+    # outputs of [0, n_halo) are discarded; [0, n_surf) is this rank's share of the SAE exchange
+    n_halo, n_surf = slicing.split_counts(t.astype(np.int64) - 1000, plan)
     n_owned = n_all - n_halo
     # global t0 = first timestamp of the whole stream (reference src/vFlow.cpp:194)
     t0_t = torch.tensor([int(t[0]) if rank == 0 else 0], dtype=torch.int64, device=dev)
