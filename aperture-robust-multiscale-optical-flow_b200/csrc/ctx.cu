@@ -48,6 +48,7 @@ struct farms_ctx {
   uint64_t t0 = 0;
   uint64_t total_events = 0;
   uint32_t last_M = 0;
+  unsigned long long valid_seen = 0;  // flow events counted so far in the current process call
   size_t halo = 0;  // events in the halo store
   size_t cap = 0;   // capacity (events) of the per-event working arrays
   size_t cap_in = 0;
@@ -249,9 +250,14 @@ int run_batch(farms_ctx *c, const uint16_t *dx, const uint16_t *dy, const uint64
   k_nslabs<<<1, 1, 0, s>>>(c->em, c->flags, (uint32_t)m, c->d_small);
   *L += 2;
   CU(cudaMemcpyAsync(c->h_small, c->d_small, 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(c->h_small + 2, c->d_counters, 8, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   const size_t nslabs = c->h_small[0];
   const int monotone = c->h_small[1] == 0;
+  // flow events of this batch's new part (the fit ran above); the halo is assumed to have the same density
+  const unsigned long long valid_total = *(const unsigned long long *)(c->h_small + 2);
+  const double flow_frac = n ? (double)(valid_total - c->valid_seen) / (double)n : 0.0;
+  c->valid_seen = valid_total;
   PoolGeom g{};
   g.W = c->W;
   g.H = c->H;
@@ -283,8 +289,8 @@ int run_batch(farms_ctx *c, const uint16_t *dx, const uint16_t *dy, const uint64
   CU(cudaMemsetAsync(c->done, 0, m, s));
   const int fast = monotone && !(c->cfg.flags & FARMS_FLAG_GENERIC_POOLING);
   *L += launch_pooling(c->rec, c->pay, (const uint32_t *)c->cell_start.p, c->slab_ids, c->done, m, (uint32_t)ncells,
-                       (int)h, (int)nslabs, g, fast, c->gr, c->gth, c->scale, c->d_work, c->d_counters + 1,
-                       c->num_sms, s);
+                       (int)h, (int)nslabs, g, fast, flow_frac * (double)m / (double)nslabs, c->gr, c->gth, c->scale,
+                       c->d_work, c->d_counters + 1, c->num_sms, s);
   CU(cudaEventRecord(c->ev[EV_POOL], s));
 
   // ---- results of the new events ----
@@ -355,6 +361,7 @@ int process(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *
   farms_timings &tm = c->tm;
   tm = farms_timings{};
   CU(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), s));
+  c->valid_seen = 0;
   float stage[8] = {0};
   float h2d_ms = 0, d2h_ms = 0;
   CU(cudaEventRecord(c->ev[EV_START], s));

@@ -95,6 +95,6 @@ void launch_build_records(const uint32_t *skeys, const uint32_t *sidx, size_t m,
 // returns the number of kernels launched.  work_counter: two zeroed words; done: m zeroed bytes.
 int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_start, const uint32_t *slab_ids,
                    uint8_t *done, size_t m, uint32_t ncells, int h, int nslabs, PoolGeom g, int fast,
-                   double *global_r, double *global_theta, uint8_t *scale, unsigned int *work_counter,
-                   unsigned long long *cand_count, int num_sms, cudaStream_t s);
+                   double flow_per_slab, double *global_r, double *global_theta, uint8_t *scale,
+                   unsigned int *work_counter, unsigned long long *cand_count, int num_sms, cudaStream_t s);
 int pool_tile_smem_bytes();

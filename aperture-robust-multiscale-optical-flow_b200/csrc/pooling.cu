@@ -108,16 +108,17 @@ struct PoolArgs {
 // ring sums of one event -> nested-square means -> arg-max scale -> outputs.  rl/rx/ry/rn hold ring k's
 // totals in lane k (k < 11).  All lanes must call.  The prefix over rings is sequential (an empty ring adds
 // exactly 0.0, so a scale whose outer ring is empty has bit-identical sums and loses the strict '>').
+template <int WIDTH>
 __device__ __forceinline__ void finish_event(const PoolArgs &A, int lane, double rl, double rx, double ry,
-                                             double rn, double own_cx, double own_cy, int out_index) {
+                                             double rn, double own_cx, double own_cy, int out_index, bool write) {
   double Sl = 0.0, Sx = 0.0, Sy = 0.0, Sn = 0.0;
   double myl = 0.0, myx = 0.0, myy = 0.0, myn = 0.0;
 #pragma unroll
   for (int k = 0; k < FARMS_NSCALES; k++) {
-    Sn += __shfl_sync(0xffffffffu, rn, k);
-    Sl += __shfl_sync(0xffffffffu, rl, k);
-    Sx += __shfl_sync(0xffffffffu, rx, k);
-    Sy += __shfl_sync(0xffffffffu, ry, k);
+    Sn += __shfl_sync(0xffffffffu, rn, k, WIDTH);
+    Sl += __shfl_sync(0xffffffffu, rl, k, WIDTH);
+    Sx += __shfl_sync(0xffffffffu, rx, k, WIDTH);
+    Sy += __shfl_sync(0xffffffffu, ry, k, WIDTH);
     if (lane == k) {
       myl = Sl; myx = Sx; myy = Sy; myn = Sn;
     }
@@ -129,16 +130,16 @@ __device__ __forceinline__ void finish_event(const PoolArgs &A, int lane, double
   int bk = -1;
 #pragma unroll
   for (int k = 0; k < FARMS_NSCALES; k++) {
-    const double mk = __shfl_sync(0xffffffffu, mean, k);
+    const double mk = __shfl_sync(0xffffffffu, mean, k, WIDTH);
     if (mk > best) {
       best = mk;
       bk = k;
     }
   }
   const int srcl = bk < 0 ? 0 : bk;
-  const double wx = __shfl_sync(0xffffffffu, myx, srcl), wy = __shfl_sync(0xffffffffu, myy, srcl),
-               wn = __shfl_sync(0xffffffffu, myn, srcl);
-  if (lane == 0) {
+  const double wx = __shfl_sync(0xffffffffu, myx, srcl, WIDTH), wy = __shfl_sync(0xffffffffu, myy, srcl, WIDTH),
+               wn = __shfl_sync(0xffffffffu, myn, srcl, WIDTH);
+  if (lane == 0 && write) {
     double bvx, bvy;
     if (bk < 0) {  // :1085-1094 fallback: the event's own flow
       bvx = own_cx;
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
         }
       }
       __syncwarp();
-      finish_event(A, lane, rl, rx, ry, rn, pay_cx[tpos], pay_cy[tpos], ii - A.h);
+      finish_event<32>(A, lane, rl, rx, ry, rn, pay_cx[tpos], pay_cy[tpos], ii - A.h, true);
     }
   }
   if (lane == 0 && ncand) atomicAdd(A.cand_count, ncand);
@@ -269,25 +270,23 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
 // ------------------------------------------------------------------------------------------------
 // fast path: owner tiles with shared-memory staging
 // ------------------------------------------------------------------------------------------------
-constexpr int OT_SHIFT = 5, OT = 1 << OT_SHIFT;  // owner tile edge (pixels)
-constexpr int TK_WARPS = 8;
-constexpr int TK_THREADS = TK_WARPS * 32;
 constexpr int TK_RING = 5;     // a 500-us window touches at most 5 slabs of 128 us
-constexpr int TK_CAP = 512;    // staged flow events per slab and region
-constexpr int TK_PAD = 128;    // the pooling loop reads 4 x 32 entries at a time without bounds checks
+constexpr int TK_PAD = 64;     // the pooling loop reads 4 x 16 records at a time without bounds checks
 constexpr int TK_SEG = 64;     // slabs per work item
 constexpr int TK_MAXT = 256;   // targets handled per round
 constexpr int TK_MAXRUN = 24;  // tile-column runs of a region: <= 10 for rows < H plus <= 10 aliased
 
+// OWS/OHS: log2 of the owner tile's width/height; WARPS per CTA; CAP staged flow events per slab and region
+template <int OWS, int OHS, int WARPS, int CAP>
 struct TileSmem {
-  double2 lx[TK_RING][TK_CAP + TK_PAD];     // len, lcx
-  double ly[TK_RING][TK_CAP + TK_PAD];      // lcy
-  uint4 rec[TK_RING][TK_CAP + TK_PAD];      // {x | y<<16 (logical window coordinates), idx, end - idx, 0}
-  double2 a1[TK_WARPS][FARMS_NSCALES][32];  // per-lane ring sums: len, lcx
-  double2 a2[TK_WARPS][FARMS_NSCALES][32];  //                     lcy, count
+  uint4 rec[TK_RING][CAP + TK_PAD];         // {x | y<<16 (logical window coordinates), idx, end - idx, 0}
+  double2 lx[TK_RING][CAP];                 // len, lcx
+  double ly[TK_RING][CAP];                  // lcy
+  double2 a1[WARPS][FARMS_NSCALES][32];     // per-lane ring sums: len, lcx
+  double2 a2[WARPS][FARMS_NSCALES][32];     //                     lcy, count
   uint32_t tlist[TK_MAXT];
   uint32_t run_s[TK_MAXRUN], run_o[TK_MAXRUN + 1];
-  uint32_t wcount[TK_WARPS];
+  uint32_t wcount[WARPS];
   int tag[TK_RING];
   int count[TK_RING];
   int overflow[TK_RING];
@@ -302,7 +301,8 @@ struct Region {  // pixels an owner tile can reach, as physical rectangles
 // Stage the flow events of dense slab `s` inside region R into ring slot `slot`, preserving index order
 // (ordered compaction => deterministic summation order).  Aliased events are stored with their LOGICAL
 // window coordinates (x - 1, y + H) so that the pooling loop needs no special case.
-__device__ void stage_slab(const PoolArgs &A, TileSmem &S, int s, int slot, const Region &R) {
+template <class SM, int WARPS, int CAP>
+__device__ void stage_slab(const PoolArgs &A, SM &S, int s, int slot, const Region &R) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ts = A.g.tile_shift, nty = A.g.nty, NT = A.g.ntx * A.g.nty, H = A.g.H;
   const int tx0 = R.rx0 >> ts, tx1 = R.rx1 >> ts, ty0 = R.ry0 >> ts, ty1 = R.ry1 >> ts;
@@ -311,30 +311,35 @@ __device__ void stage_slab(const PoolArgs &A, TileSmem &S, int s, int slot, cons
   const int nrun1 = R.ay1 >= 0 ? atx1 - atx0 + 1 : 0;
   const int nrun = nrun0 + nrun1;
   __syncthreads();  // previous users of run_s/run_o/wcount and of this slot are done
+  if (tid < nrun) {
+    const int c = tid;
+    uint32_t a, b;
+    if (c < nrun0) {
+      const size_t cb = (size_t)s * NT + (size_t)(tx0 + c) * nty;
+      a = A.cell_start[cb + ty0];
+      b = A.cell_start[cb + ty1 + 1];
+    } else {
+      const size_t cb = (size_t)s * NT + (size_t)(atx0 + c - nrun0) * nty;
+      a = A.cell_start[cb];
+      b = A.cell_start[cb + (R.ay1 >> ts) + 1];
+    }
+    S.run_s[c] = a;
+    S.run_o[c + 1] = b - a;  // lengths first, prefix below
+  }
+  __syncthreads();
   if (tid == 0) {
     uint32_t o = 0;
+    S.run_o[0] = 0;
     for (int c = 0; c < nrun; c++) {
-      uint32_t a, b;
-      if (c < nrun0) {
-        const size_t cb = (size_t)s * NT + (size_t)(tx0 + c) * nty;
-        a = A.cell_start[cb + ty0];
-        b = A.cell_start[cb + ty1 + 1];
-      } else {
-        const size_t cb = (size_t)s * NT + (size_t)(atx0 + c - nrun0) * nty;
-        a = A.cell_start[cb];
-        b = A.cell_start[cb + (R.ay1 >> ts) + 1];
-      }
-      S.run_s[c] = a;
-      S.run_o[c] = o;
-      o += b - a;
+      o += S.run_o[c + 1];
+      S.run_o[c + 1] = o;
     }
-    S.run_o[nrun] = o;
   }
   __syncthreads();
   const uint32_t total = S.run_o[nrun];
   const double *pay_len = A.pay, *pay_cx = A.pay + A.m, *pay_cy = A.pay + 2 * A.m;
   uint32_t out_base = 0;
-  for (uint32_t r0 = 0; r0 < total; r0 += TK_THREADS) {
+  for (uint32_t r0 = 0; r0 < total; r0 += WARPS * 32) {
     const uint32_t f = r0 + tid;
     bool pass = false;
     uint32_t pos = 0;
@@ -359,13 +364,13 @@ __device__ void stage_slab(const PoolArgs &A, TileSmem &S, int s, int slot, cons
     __syncthreads();
     uint32_t pre = 0, all = 0;
 #pragma unroll
-    for (int w = 0; w < TK_WARPS; w++) {
+    for (int w = 0; w < WARPS; w++) {
       const uint32_t cw = S.wcount[w];
       if (w < warp) pre += cw;
       all += cw;
     }
     const uint32_t o = out_base + pre + __popc(bal & ((1u << lane) - 1u));
-    if (pass && o < TK_CAP) {
+    if (pass && o < (uint32_t)CAP) {
       S.rec[slot][o] = make_uint4(rec.x, rec.z, rec.w - rec.z, 0u);
       S.lx[slot][o] = make_double2(pay_len[pos], pay_cx[pos]);
       S.ly[slot][o] = pay_cy[pos];
@@ -373,20 +378,24 @@ __device__ void stage_slab(const PoolArgs &A, TileSmem &S, int s, int slot, cons
     out_base += all;
     __syncthreads();
   }
-  const uint32_t cnt = min(out_base, (uint32_t)TK_CAP);
+  const uint32_t cnt = min(out_base, (uint32_t)CAP);
   // entries the unrolled loop may touch past the end: span 0 never passes
   if (tid < TK_PAD) S.rec[slot][cnt + tid] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
     S.tag[slot] = s;
     S.count[slot] = (int)cnt;
-    S.overflow[slot] = out_base > TK_CAP;
+    S.overflow[slot] = out_base > (uint32_t)CAP;
   }
 }
 
-__global__ void __launch_bounds__(TK_THREADS, 1) k_pool_tile(PoolArgs A, int otx_n, int oty_n, int nseg) {
+template <int OWS, int OHS, int WARPS, int CAP, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_pool_tile(PoolArgs A, int otx_n, int oty_n, int nseg) {
+  using SM = TileSmem<OWS, OHS, WARPS, CAP>;
+  constexpr int OW = 1 << OWS, OH = 1 << OHS, THREADS = WARPS * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem &S = *reinterpret_cast<TileSmem *>(smem_raw);
+  SM &S = *reinterpret_cast<SM *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = lane >> 4, sub = lane & 15;
   const int W = A.g.W, H = A.g.H, nty = A.g.nty, NT = A.g.ntx * A.g.nty;
   const double *pay_cx = A.pay + A.m, *pay_cy = A.pay + 2 * A.m;
   const unsigned int nitems = (unsigned int)otx_n * oty_n * nseg;
@@ -402,21 +411,21 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_pool_tile(PoolArgs A, int otx
     // items are ordered segment-major so that CTAs running together work on the same time span (L2 reuse)
     const int seg = item / (otx_n * oty_n), ot = item % (otx_n * oty_n);
     const int TX = ot / oty_n, TY = ot % oty_n;
-    const int X0 = TX << OT_SHIFT, Y0 = TY << OT_SHIFT;
+    const int X0 = TX << OWS, Y0 = TY << OHS;
     Region R;
     R.rx0 = max(X0 - FARMS_MAX_WINDOW, 0);
-    R.rx1 = min(X0 + OT - 1 + FARMS_MAX_WINDOW, W - 1);                       // src/vFlow.cpp:998
+    R.rx1 = min(X0 + OW - 1 + FARMS_MAX_WINDOW, W - 1);                       // src/vFlow.cpp:998
     R.ry0 = max(Y0 - FARMS_MAX_WINDOW, 0);
-    const int jmax = min(min(Y0 + OT - 1, H - 1) + FARMS_MAX_WINDOW, W - 1);  // :1000 (sic: width - 1)
+    const int jmax = min(min(Y0 + OH - 1, H - 1) + FARMS_MAX_WINDOW, W - 1);  // :1000 (sic: width - 1)
     R.ry1 = min(jmax, H - 1);
     // logical rows j in [H, 2H) alias pixel (i + 1, j - H); rows >= 2H are left to k_pool_any
     R.ay1 = min(jmax, 2 * H - 1) - H;
     R.ax0 = R.rx0 + 1;
     R.ax1 = min(R.rx1 + 1, W - 1);
     if (R.ax0 > R.ax1) R.ay1 = -1;
-    // index tiles (16x16) of the owner tile: 2 columns x 2 rows, clipped
-    const int itx0 = X0 >> 4, itx1 = min((X0 + OT - 1) >> 4, A.g.ntx - 1);
-    const int ity0 = Y0 >> 4, ity1 = min((Y0 + OT - 1) >> 4, nty - 1);
+    // index tiles (16x16) of the owner tile, clipped
+    const int itx0 = X0 >> 4, itx1 = min((X0 + OW - 1) >> 4, A.g.ntx - 1);
+    const int ity0 = Y0 >> 4, ity1 = min((Y0 + OH - 1) >> 4, nty - 1);
     const int d_begin = seg * TK_SEG, d_end = min(d_begin + TK_SEG, A.nslabs);
 
     for (int d = d_begin; d < d_end; d++) {
@@ -426,7 +435,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_pool_tile(PoolArgs A, int otx
 #pragma unroll
       for (int c = 0; c < 2; c++) {
         ta[c] = tb[c] = 0;
-        if (itx0 + c <= itx1) {
+        if (c < (OW >> 4) && itx0 + c <= itx1) {
           const size_t cb = (size_t)d * NT + (size_t)(itx0 + c) * nty;
           ta[c] = A.cell_start[cb + ity0];
           tb[c] = A.cell_start[cb + ity1 + 1];
@@ -444,7 +453,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_pool_tile(PoolArgs A, int otx
       while (dlo > 0 && d - dlo < TK_RING - 1 && A.slab_ids[dlo - 1] >= lo_id) dlo--;
       for (int s = dlo; s <= d; s++) {
         const int slot = s % TK_RING;
-        if (S.tag[slot] != s) stage_slab(A, S, s, slot, R);  // uniform: tag is read after a barrier
+        if (S.tag[slot] != s) stage_slab<SM, WARPS, CAP>(A, S, s, slot, R);  // uniform: tag is read after a barrier
         __syncthreads();
       }
       bool any_overflow = false;
@@ -457,7 +466,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_pool_tile(PoolArgs A, int otx
           S.tnext = 0;
         }
         __syncthreads();
-        for (uint32_t f = t0 + tid; f < min(nraw, t0 + TK_MAXT); f += TK_THREADS) {
+        for (uint32_t f = t0 + tid; f < min(nraw, t0 + TK_MAXT); f += THREADS) {
           const uint32_t n0 = tb[0] - ta[0];
           const uint32_t pos = f < n0 ? ta[0] + f : ta[1] + (f - n0);
           const uint4 r = A.rec[pos];
@@ -469,64 +478,67 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_pool_tile(PoolArgs A, int otx
         __syncthreads();
         const uint32_t ntg = S.ntg;
 
-        // ---- one warp per target ----
+        // ---- two targets per warp: lanes 0-15 pool one event, lanes 16-31 the next ----
         for (;;) {
           uint32_t k = 0;
-          if (lane == 0) k = atomicAdd(&S.tnext, 1u);
+          if (lane == 0) k = atomicAdd(&S.tnext, 2u);
           k = __shfl_sync(0xffffffffu, k, 0);
           if (k >= ntg) break;
-          const uint32_t tpos = S.tlist[k];
+          const bool have = k + half < ntg;
+          const uint32_t tpos = S.tlist[have ? k + half : k];
           const uint4 r = A.rec[tpos];
           const int xi = (int)(r.x & 0xffffu), yi = (int)(r.x >> 16);
           const uint32_t ii = r.z;
           const int jlo = max(0, yi - FARMS_MAX_WINDOW), jhi = min(yi + FARMS_MAX_WINDOW, W - 1);  // :1000 (sic)
-          const uint32_t jspan = (uint32_t)(jhi - jlo);  // jhi >= jlo is not guaranteed when W < H: wraps to "never"
-          const bool rows_ok = jhi >= jlo;
+          // jhi < jlo happens when W < H: then no cell qualifies (the uint32 span test below never passes
+          // because the record loop is skipped)
+          const bool rows_ok = have && jhi >= jlo;
+          const uint32_t jspan = rows_ok ? (uint32_t)(jhi - jlo) : 0u;
+          const int ylo = rows_ok ? jlo : 0x7fff0000;  // makes (cy - ylo) huge => fails
           const int xoff = FARMS_MAX_WINDOW - xi;
 #pragma unroll
           for (int q = 0; q < FARMS_NSCALES; q++) {
             S.a1[warp][q][lane] = make_double2(0.0, 0.0);
             S.a2[warp][q][lane] = make_double2(0.0, 0.0);
           }
-          if (rows_ok) {
-            for (int s = dlo; s <= d; s++) {
-              const int slot = s % TK_RING;
-              const int n = S.count[slot];
-              ncand += (lane == 0) ? n : 0;
-              for (int q0 = lane; q0 < n; q0 += 128) {
-                uint4 c[4];
+          for (int s = dlo; s <= d; s++) {
+            const int slot = s % TK_RING;
+            const int n = S.count[slot];
+            ncand += (sub == 0 && have) ? n : 0;
+            for (int q0 = sub; q0 < n; q0 += 64) {
+              uint4 c[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) c[u] = S.rec[slot][q0 + 32 * u];  // padded: no bounds check
+              for (int u = 0; u < 4; u++) c[u] = S.rec[slot][q0 + 16 * u];  // padded: no bounds check
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                  const int cx = (int)(c[u].x & 0xffffu), cy = (int)(c[u].x >> 16);
-                  // still the latest event of its pixel AND younger than 500 us  <=>  idx <= ii < end
-                  const bool ok = (ii - c[u].y) < c[u].z && (uint32_t)(cx + xoff) <= 2u * FARMS_MAX_WINDOW &&
-                                  (uint32_t)(cy - jlo) <= jspan;
-                  if (ok) {
-                    const int q = q0 + 32 * u;
-                    const int m = max(abs(cx - xi), abs(cy - yi));
-                    const int ring = ((m + FARMS_WINDOW_JUMP - 1) * 205) >> 10;  // /5 for values <= 54
-                    double2 v1 = S.a1[warp][ring][lane], v2 = S.a2[warp][ring][lane];
-                    const double2 l = S.lx[slot][q];
-                    v1.x += l.x;
-                    v1.y += l.y;
-                    v2.x += S.ly[slot][q];
-                    v2.y += 1.0;
-                    S.a1[warp][ring][lane] = v1;
-                    S.a2[warp][ring][lane] = v2;
-                  }
+              for (int u = 0; u < 4; u++) {
+                const int cx = (int)(c[u].x & 0xffffu), cy = (int)(c[u].x >> 16);
+                // still the latest event of its pixel AND younger than 500 us  <=>  idx <= ii < end
+                const bool ok = (ii - c[u].y) < c[u].z && (uint32_t)(cx + xoff) <= 2u * FARMS_MAX_WINDOW &&
+                                (uint32_t)(cy - ylo) <= jspan;
+                if (ok) {
+                  const int q = q0 + 16 * u;
+                  const int m = max(abs(cx - xi), abs(cy - yi));
+                  const int ring = ((m + FARMS_WINDOW_JUMP - 1) * 205) >> 10;  // /5 for values <= 54
+                  double2 v1 = S.a1[warp][ring][lane], v2 = S.a2[warp][ring][lane];
+                  const double2 l = S.lx[slot][q];
+                  v1.x += l.x;
+                  v1.y += l.y;
+                  v2.x += S.ly[slot][q];
+                  v2.y += 1.0;
+                  S.a1[warp][ring][lane] = v1;
+                  S.a2[warp][ring][lane] = v2;
                 }
               }
             }
           }
           __syncwarp();
+          // sub-lane k < 11 of each half reduces ring k over the half's 16 per-lane partials
           double rl = 0.0, rx = 0.0, ry = 0.0, rn = 0.0;
-          if (lane < FARMS_NSCALES) {
+          if (sub < FARMS_NSCALES) {
 #pragma unroll 8
-            for (int q = 0; q < 32; q++) {
-              const int qq = (q + lane) & 31;
-              const double2 v1 = S.a1[warp][lane][qq], v2 = S.a2[warp][lane][qq];
+            for (int q = 0; q < 16; q++) {
+              const int col = (half << 4) | ((q + sub) & 15);
+              const double2 v1 = S.a1[warp][sub][col], v2 = S.a2[warp][sub][col];
               rl += v1.x;
               rx += v1.y;
               ry += v2.x;
@@ -534,13 +546,30 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_pool_tile(PoolArgs A, int otx
             }
           }
           __syncwarp();
-          finish_event(A, lane, rl, rx, ry, rn, pay_cx[tpos], pay_cy[tpos], (int)ii - A.h);
-          if (lane == 0) A.done[tpos] = 1;
+          finish_event<16>(A, sub, rl, rx, ry, rn, pay_cx[tpos], pay_cy[tpos], (int)ii - A.h, have);
+          if (sub == 0 && have) A.done[tpos] = 1;
         }
       }
     }
   }
-  if (lane == 0 && ncand) atomicAdd(A.cand_count, ncand);
+  if ((lane & 15) == 0 && ncand) atomicAdd(A.cand_count, ncand);
+}
+
+template <int OWS, int OHS, int WARPS, int CAP, int MINB>
+void launch_tile(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
+  PoolArgs A = A0;
+  using SM = TileSmem<OWS, OHS, WARPS, CAP>;
+  auto kern = k_pool_tile<OWS, OHS, WARPS, CAP, MINB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
+    attr_set = true;
+  }
+  const int otx = (A.g.W + (1 << OWS) - 1) >> OWS, oty = (A.g.H + (1 << OHS) - 1) >> OHS;
+  const int nseg = (nslabs + TK_SEG - 1) / TK_SEG;
+  const long long items = (long long)otx * oty * nseg;
+  unsigned grid = (unsigned)std::min<long long>(items, (long long)num_sms * MINB);
+  kern<<<grid, WARPS * 32, sizeof(SM), s>>>(A, otx, oty, nseg);
 }
 
 inline unsigned nb(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -561,14 +590,15 @@ void launch_build_records(const uint32_t *skeys, const uint32_t *sidx, size_t m,
                                                    pay, cell_start, ncells);
 }
 
-int pool_tile_smem_bytes() { return (int)sizeof(TileSmem); }
+int pool_tile_smem_bytes() { return (int)sizeof(TileSmem<5, 4, 4, 288>); }
 
 // Launches the fast path (when `fast` is set) and then the general path for whatever is left.
-// work_counter: two zeroed words.  done: m zeroed bytes.
+// work_counter: two zeroed words.  done: m zeroed bytes.  flow_per_slab: average number of flow events per
+// time slab over the whole sensor (picks the staging capacity).
 int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_start, const uint32_t *slab_ids,
                    uint8_t *done, size_t m, uint32_t ncells, int h, int nslabs, PoolGeom g, int fast,
-                   double *global_r, double *global_theta, uint8_t *scale, unsigned int *work_counter,
-                   unsigned long long *cand_count, int num_sms, cudaStream_t s) {
+                   double flow_per_slab, double *global_r, double *global_theta, uint8_t *scale,
+                   unsigned int *work_counter, unsigned long long *cand_count, int num_sms, cudaStream_t s) {
   if (!m) return 0;
   int launches = 0;
   PoolArgs A;
@@ -577,17 +607,13 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
   A.global_r = global_r; A.global_theta = global_theta; A.scale = scale;
   A.cand_count = cand_count;
   if (fast && g.tile_shift == 4) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_pool_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
-      attr_set = true;
-    }
-    const int otx = (g.W + OT - 1) >> OT_SHIFT, oty = (g.H + OT - 1) >> OT_SHIFT;
-    const int nseg = (nslabs + TK_SEG - 1) / TK_SEG;
-    const long long items = (long long)otx * oty * nseg;
     A.work_counter = work_counter;
-    unsigned grid = (unsigned)std::min<long long>(items, num_sms);
-    k_pool_tile<<<grid, TK_THREADS, sizeof(TileSmem), s>>>(A, otx, oty, nseg);
+    // expected staged events per slab in a (32+100) x (16+100) region, with headroom for clustering
+    const double dens = flow_per_slab / ((double)g.W * g.H);
+    if (dens * 132.0 * 116.0 * 2.2 < 288.0)  // event scenes are clustered along edges: local density reaches ~2x the mean
+      launch_tile<5, 4, 4, 288, 2>(A, nslabs, num_sms, s);   // 2 CTAs per SM
+    else
+      launch_tile<5, 5, 8, 640, 1>(A, nslabs, num_sms, s);   // 1 CTA per SM, larger staging
     launches++;
   }
   A.work_counter = work_counter + 1;
