@@ -268,29 +268,33 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// fast path: owner tiles with shared-memory staging
+// fast path: owner tiles with shared-memory staging, FP32 ring partials, exact decisions
 // ------------------------------------------------------------------------------------------------
-constexpr int TK_RING = 5;     // a 500-us window touches at most 5 slabs of 128 us
+// Ring partial sums are kept in FP32 (half the shared memory of FP64 => twice the resident warps) and
+// combined in FP64.  That perturbs a scale's mean by < 1e-5 relative, so an event is only finished here when
+// its arg-max over scales is decided by a margin > 2e-5 and its mean vector is not a cancellation residue;
+// everything else (measured: well under 1 % of events) is left to k_pool_any, which is exact.  Scales whose
+// extra rings are empty have bit-identical sums in both arithmetics, so exact ties behave like the reference.
+constexpr int OT_SHIFT = 5, OT = 1 << OT_SHIFT;  // owner tile edge (pixels)
+constexpr int TK_RING = 6;     // two consecutive slabs are pooled per round: their windows span <= 6 slabs
 constexpr int TK_PAD = 64;     // the pooling loop reads 4 x 16 records at a time without bounds checks
 constexpr int TK_SEG = 64;     // slabs per work item
-constexpr int TK_MAXT = 256;   // targets handled per round
+constexpr int TK_MAXT = 256;   // targets handled per round and slab
 constexpr int TK_MAXRUN = 24;  // tile-column runs of a region: <= 10 for rows < H plus <= 10 aliased
+constexpr float TK_TIE_TOL = 2e-5f;
 
-// OWS/OHS: log2 of the owner tile's width/height; WARPS per CTA; CAP staged flow events per slab and region
-template <int OWS, int OHS, int WARPS, int CAP>
+template <int WARPS, int CAP>
 struct TileSmem {
-  uint4 rec[TK_RING][CAP + TK_PAD];         // {x | y<<16 (logical window coordinates), idx, end - idx, 0}
-  double2 lx[TK_RING][CAP];                 // len, lcx
-  double ly[TK_RING][CAP];                  // lcy
-  double2 a1[WARPS][FARMS_NSCALES][32];     // per-lane ring sums: len, lcx
-  double2 a2[WARPS][FARMS_NSCALES][32];     //                     lcy, count
-  uint32_t tlist[TK_MAXT];
+  uint4 ra[TK_RING][CAP + TK_PAD];        // {x | y<<16 (logical window coordinates), idx, end - idx, len as f32}
+  float2 rb[TK_RING][CAP];                // lcx, lcy
+  float4 acc[WARPS][FARMS_NSCALES][32];   // per-lane ring partials: len, lcx, lcy, count
+  uint32_t tlist[2][TK_MAXT];
   uint32_t run_s[TK_MAXRUN], run_o[TK_MAXRUN + 1];
   uint32_t wcount[WARPS];
   int tag[TK_RING];
   int count[TK_RING];
   int overflow[TK_RING];
-  unsigned int ntg, tnext, item;
+  unsigned int ntg[2], tnext, item;
 };
 
 struct Region {  // pixels an owner tile can reach, as physical rectangles
@@ -371,16 +375,15 @@ __device__ void stage_slab(const PoolArgs &A, SM &S, int s, int slot, const Regi
     }
     const uint32_t o = out_base + pre + __popc(bal & ((1u << lane) - 1u));
     if (pass && o < (uint32_t)CAP) {
-      S.rec[slot][o] = make_uint4(rec.x, rec.z, rec.w - rec.z, 0u);
-      S.lx[slot][o] = make_double2(pay_len[pos], pay_cx[pos]);
-      S.ly[slot][o] = pay_cy[pos];
+      S.ra[slot][o] = make_uint4(rec.x, rec.z, rec.w - rec.z, __float_as_uint(__double2float_rn(pay_len[pos])));
+      S.rb[slot][o] = make_float2(__double2float_rn(pay_cx[pos]), __double2float_rn(pay_cy[pos]));
     }
     out_base += all;
     __syncthreads();
   }
   const uint32_t cnt = min(out_base, (uint32_t)CAP);
   // entries the unrolled loop may touch past the end: span 0 never passes
-  if (tid < TK_PAD) S.rec[slot][cnt + tid] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < TK_PAD) S.ra[slot][cnt + tid] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
     S.tag[slot] = s;
     S.count[slot] = (int)cnt;
@@ -388,16 +391,68 @@ __device__ void stage_slab(const PoolArgs &A, SM &S, int s, int slot, const Regi
   }
 }
 
-template <int OWS, int OHS, int WARPS, int CAP, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) k_pool_tile(PoolArgs A, int otx_n, int oty_n, int nseg) {
-  using SM = TileSmem<OWS, OHS, WARPS, CAP>;
-  constexpr int OW = 1 << OWS, OH = 1 << OHS, THREADS = WARPS * 32;
+// Like finish_event, but from FP32 partial sums: writes only when the decision is safe; returns (in every lane
+// of the segment) whether the event was finished.
+__device__ __forceinline__ bool finish_event_checked(const PoolArgs &A, int sub, double rl, double rx, double ry,
+                                                     double rn, int out_index, bool have) {
+  double Sl = 0.0, Sx = 0.0, Sy = 0.0, Sn = 0.0;
+  double myl = 0.0, myx = 0.0, myy = 0.0, myn = 0.0;
+#pragma unroll
+  for (int k = 0; k < FARMS_NSCALES; k++) {
+    Sn += __shfl_sync(0xffffffffu, rn, k, 16);
+    Sl += __shfl_sync(0xffffffffu, rl, k, 16);
+    Sx += __shfl_sync(0xffffffffu, rx, k, 16);
+    Sy += __shfl_sync(0xffffffffu, ry, k, 16);
+    if (sub == k) {
+      myl = Sl; myx = Sx; myy = Sy; myn = Sn;
+    }
+  }
+  const double mean = (sub < FARMS_NSCALES && myn > 0.0) ? myl / myn : 0.0;
+  double best = 0.0, bn = 0.0;
+  int bk = -1;
+#pragma unroll
+  for (int k = 0; k < FARMS_NSCALES; k++) {
+    const double mk = __shfl_sync(0xffffffffu, mean, k, 16);
+    const double nk = __shfl_sync(0xffffffffu, myn, k, 16);
+    if (mk > best) {
+      best = mk;
+      bk = k;
+      bn = nk;
+    }
+  }
+  // is any other scale (with a different contributor set) within the FP32 noise of the winner?
+  const bool rival = sub < FARMS_NSCALES && myn != bn && fabs(mean - best) <= (double)TK_TIE_TOL * best;
+  const unsigned seg = 0xffffu << (threadIdx.x & 16);
+  const bool any_rival = (__ballot_sync(0xffffffffu, rival) & seg) != 0u;
+  const int srcl = bk < 0 ? 0 : bk;
+  const double wx = __shfl_sync(0xffffffffu, myx, srcl, 16), wy = __shfl_sync(0xffffffffu, myy, srcl, 16),
+               wn = __shfl_sync(0xffffffffu, myn, srcl, 16);
+  bool safe = have && bk >= 0 && !any_rival && best > 1e-30 && best < 1e30;
+  double bvx = 0.0, bvy = 0.0, r2 = 0.0;
+  if (safe) {
+    bvx = wx / wn;
+    bvy = wy / wn;
+    r2 = __dadd_rn(__dmul_rn(bvy, bvy), __dmul_rn(bvx, bvx));
+    // mean vector much shorter than the mean length: the FP32 sums cancelled, let the exact path do it
+    safe = r2 > 1e-4 * best * best;
+  }
+  if (sub == 0 && safe) {
+    A.global_r[out_index] = __dsqrt_rn(r2);        // src/vFlow.cpp:365
+    A.global_theta[out_index] = atan2(bvy, bvx);   // :366
+    A.scale[out_index] = (uint8_t)(bk * FARMS_WINDOW_JUMP);
+  }
+  return safe;
+}
+
+template <int WARPS, int CAP>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx_n, int oty_n, int nseg) {
+  using SM = TileSmem<WARPS, CAP>;
+  constexpr int THREADS = WARPS * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM &S = *reinterpret_cast<SM *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int half = lane >> 4, sub = lane & 15;
   const int W = A.g.W, H = A.g.H, nty = A.g.nty, NT = A.g.ntx * A.g.nty;
-  const double *pay_cx = A.pay + A.m, *pay_cy = A.pay + 2 * A.m;
   const unsigned int nitems = (unsigned int)otx_n * oty_n * nseg;
   unsigned long long ncand = 0;
 
@@ -411,104 +466,118 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_pool_tile(PoolArgs A, int 
     // items are ordered segment-major so that CTAs running together work on the same time span (L2 reuse)
     const int seg = item / (otx_n * oty_n), ot = item % (otx_n * oty_n);
     const int TX = ot / oty_n, TY = ot % oty_n;
-    const int X0 = TX << OWS, Y0 = TY << OHS;
+    const int X0 = TX << OT_SHIFT, Y0 = TY << OT_SHIFT;
     Region R;
     R.rx0 = max(X0 - FARMS_MAX_WINDOW, 0);
-    R.rx1 = min(X0 + OW - 1 + FARMS_MAX_WINDOW, W - 1);                       // src/vFlow.cpp:998
+    R.rx1 = min(X0 + OT - 1 + FARMS_MAX_WINDOW, W - 1);                       // src/vFlow.cpp:998
     R.ry0 = max(Y0 - FARMS_MAX_WINDOW, 0);
-    const int jmax = min(min(Y0 + OH - 1, H - 1) + FARMS_MAX_WINDOW, W - 1);  // :1000 (sic: width - 1)
+    const int jmax = min(min(Y0 + OT - 1, H - 1) + FARMS_MAX_WINDOW, W - 1);  // :1000 (sic: width - 1)
     R.ry1 = min(jmax, H - 1);
     // logical rows j in [H, 2H) alias pixel (i + 1, j - H); rows >= 2H are left to k_pool_any
     R.ay1 = min(jmax, 2 * H - 1) - H;
     R.ax0 = R.rx0 + 1;
     R.ax1 = min(R.rx1 + 1, W - 1);
     if (R.ax0 > R.ax1) R.ay1 = -1;
-    // index tiles (16x16) of the owner tile, clipped
-    const int itx0 = X0 >> 4, itx1 = min((X0 + OW - 1) >> 4, A.g.ntx - 1);
-    const int ity0 = Y0 >> 4, ity1 = min((Y0 + OH - 1) >> 4, nty - 1);
+    // index tiles (16x16) of the owner tile: 2 columns x 2 rows, clipped
+    const int itx0 = X0 >> 4, itx1 = min((X0 + OT - 1) >> 4, A.g.ntx - 1);
+    const int ity0 = Y0 >> 4, ity1 = min((Y0 + OT - 1) >> 4, nty - 1);
     const int d_begin = seg * TK_SEG, d_end = min(d_begin + TK_SEG, A.nslabs);
 
-    for (int d = d_begin; d < d_end; d++) {
-      // ---- targets of this step: flow events of the owner tile in slab d ----
-      uint32_t ta[2], tb[2];
-      uint32_t nraw = 0;
+    // two consecutive slabs per round
+    for (int d = d_begin; d < d_end; d += 2) {
+      const int nd = min(2, d_end - d);
+      // ---- targets of this round: flow events of the owner tile in slabs d, d+1 ----
+      uint32_t ta[2][2], tb[2][2], nraw[2] = {0u, 0u};
 #pragma unroll
-      for (int c = 0; c < 2; c++) {
-        ta[c] = tb[c] = 0;
-        if (c < (OW >> 4) && itx0 + c <= itx1) {
-          const size_t cb = (size_t)d * NT + (size_t)(itx0 + c) * nty;
-          ta[c] = A.cell_start[cb + ity0];
-          tb[c] = A.cell_start[cb + ity1 + 1];
+      for (int w = 0; w < 2; w++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          ta[w][c] = tb[w][c] = 0;
+          if (w < nd && itx0 + c <= itx1) {
+            const size_t cb = (size_t)(d + w) * NT + (size_t)(itx0 + c) * nty;
+            ta[w][c] = A.cell_start[cb + ity0];
+            tb[w][c] = A.cell_start[cb + ity1 + 1];
+          }
+          nraw[w] += tb[w][c] - ta[w][c];
         }
-        nraw += tb[c] - ta[c];
-      }
-      if (nraw == 0) continue;  // uniform across the CTA
+      if (nraw[0] + nraw[1] == 0) continue;  // uniform across the CTA
 
-      // ---- make sure the slabs of the 500-us window are staged ----
-      const uint32_t sid = A.slab_ids[d];
-      const uint32_t t_first = sid << FARMS_SLAB_SHIFT;
-      const uint32_t lo_id =
-          (t_first >= (uint32_t)(FARMS_KILL_OLD_FLOW_TIME - 1) ? t_first - (FARMS_KILL_OLD_FLOW_TIME - 1) : 0u) >> FARMS_SLAB_SHIFT;
-      int dlo = d;
-      while (dlo > 0 && d - dlo < TK_RING - 1 && A.slab_ids[dlo - 1] >= lo_id) dlo--;
-      for (int s = dlo; s <= d; s++) {
+      // ---- make sure the slabs of both 500-us windows are staged ----
+      int dlo[2], dhi[2];
+#pragma unroll
+      for (int w = 0; w < 2; w++) {
+        const int dd = min(d + w, d_end - 1);
+        const uint32_t t_first = A.slab_ids[dd] << FARMS_SLAB_SHIFT;
+        const uint32_t lo_id =
+            (t_first >= (uint32_t)(FARMS_KILL_OLD_FLOW_TIME - 1) ? t_first - (FARMS_KILL_OLD_FLOW_TIME - 1) : 0u) >> FARMS_SLAB_SHIFT;
+        int l = dd;
+        while (l > 0 && dd - l < TK_RING - 2 && A.slab_ids[l - 1] >= lo_id) l--;
+        dlo[w] = l;
+        dhi[w] = dd;
+      }
+      const int s_first = nraw[0] ? dlo[0] : dlo[1], s_last = nraw[1] ? dhi[1] : dhi[0];
+      for (int s = s_first; s <= s_last; s++) {
         const int slot = s % TK_RING;
         if (S.tag[slot] != s) stage_slab<SM, WARPS, CAP>(A, S, s, slot, R);  // uniform: tag is read after a barrier
         __syncthreads();
       }
-      bool any_overflow = false;
-      for (int s = dlo; s <= d; s++) any_overflow |= S.overflow[s % TK_RING] != 0;
+      bool ovf[2] = {false, false};
+#pragma unroll
+      for (int w = 0; w < 2; w++)
+        for (int s = dlo[w]; s <= dhi[w]; s++) ovf[w] |= S.overflow[s % TK_RING] != 0;
 
-      for (uint32_t t0 = 0; t0 < nraw; t0 += TK_MAXT) {
+      const uint32_t nmax = max(nraw[0], nraw[1]);
+      for (uint32_t t0 = 0; t0 < nmax; t0 += TK_MAXT) {
         __syncthreads();
         if (tid == 0) {
-          S.ntg = 0;
+          S.ntg[0] = S.ntg[1] = 0;
           S.tnext = 0;
         }
         __syncthreads();
-        for (uint32_t f = t0 + tid; f < min(nraw, t0 + TK_MAXT); f += THREADS) {
-          const uint32_t n0 = tb[0] - ta[0];
-          const uint32_t pos = f < n0 ? ta[0] + f : ta[1] + (f - n0);
-          const uint4 r = A.rec[pos];
-          const int yi = (int)(r.x >> 16);
-          // fast-path conditions: not a halo event, window rows stay below 2H, staging complete
-          const bool ok = (int)r.z >= A.h && min(yi + FARMS_MAX_WINDOW, W - 1) <= 2 * H - 1 && !any_overflow;
-          if (ok) S.tlist[atomicAdd(&S.ntg, 1u)] = pos;
-        }
+#pragma unroll
+        for (int w = 0; w < 2; w++)
+          for (uint32_t f = t0 + tid; f < min(nraw[w], t0 + TK_MAXT); f += THREADS) {
+            const uint32_t n0 = tb[w][0] - ta[w][0];
+            const uint32_t pos = f < n0 ? ta[w][0] + f : ta[w][1] + (f - n0);
+            const uint4 r = A.rec[pos];
+            const int yi = (int)(r.x >> 16);
+            // fast-path conditions: not a halo event, window rows stay below 2H, staging complete
+            const bool ok = (int)r.z >= A.h && min(yi + FARMS_MAX_WINDOW, W - 1) <= 2 * H - 1 && !ovf[w];
+            if (ok) S.tlist[w][atomicAdd(&S.ntg[w], 1u)] = pos;
+          }
         __syncthreads();
-        const uint32_t ntg = S.ntg;
+        const uint32_t ntg0 = S.ntg[0], ntg1 = S.ntg[1];
+        const uint32_t tasks0 = (ntg0 + 1) >> 1, tasks = tasks0 + ((ntg1 + 1) >> 1);
 
-        // ---- two targets per warp: lanes 0-15 pool one event, lanes 16-31 the next ----
+        // ---- two targets (of the same slab) per warp: lanes 0-15 pool one event, lanes 16-31 the next ----
         for (;;) {
           uint32_t k = 0;
-          if (lane == 0) k = atomicAdd(&S.tnext, 2u);
+          if (lane == 0) k = atomicAdd(&S.tnext, 1u);
           k = __shfl_sync(0xffffffffu, k, 0);
-          if (k >= ntg) break;
-          const bool have = k + half < ntg;
-          const uint32_t tpos = S.tlist[have ? k + half : k];
+          if (k >= tasks) break;
+          const int w = k >= tasks0;
+          const uint32_t kk = (w ? k - tasks0 : k) * 2 + half, nt = w ? ntg1 : ntg0;
+          const bool have = kk < nt;
+          const uint32_t tpos = S.tlist[w][have ? kk : nt - 1];
           const uint4 r = A.rec[tpos];
           const int xi = (int)(r.x & 0xffffu), yi = (int)(r.x >> 16);
           const uint32_t ii = r.z;
           const int jlo = max(0, yi - FARMS_MAX_WINDOW), jhi = min(yi + FARMS_MAX_WINDOW, W - 1);  // :1000 (sic)
-          // jhi < jlo happens when W < H: then no cell qualifies (the uint32 span test below never passes
-          // because the record loop is skipped)
-          const bool rows_ok = have && jhi >= jlo;
+          const bool rows_ok = have && jhi >= jlo;  // jhi < jlo when W < H: no cell qualifies
           const uint32_t jspan = rows_ok ? (uint32_t)(jhi - jlo) : 0u;
           const int ylo = rows_ok ? jlo : 0x7fff0000;  // makes (cy - ylo) huge => fails
           const int xoff = FARMS_MAX_WINDOW - xi;
 #pragma unroll
-          for (int q = 0; q < FARMS_NSCALES; q++) {
-            S.a1[warp][q][lane] = make_double2(0.0, 0.0);
-            S.a2[warp][q][lane] = make_double2(0.0, 0.0);
-          }
-          for (int s = dlo; s <= d; s++) {
+          for (int q = 0; q < FARMS_NSCALES; q++) S.acc[warp][q][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int sl = w ? dlo[1] : dlo[0], sh = w ? dhi[1] : dhi[0];
+          for (int s = sl; s <= sh; s++) {
             const int slot = s % TK_RING;
             const int n = S.count[slot];
             ncand += (sub == 0 && have) ? n : 0;
             for (int q0 = sub; q0 < n; q0 += 64) {
               uint4 c[4];
 #pragma unroll
-              for (int u = 0; u < 4; u++) c[u] = S.rec[slot][q0 + 16 * u];  // padded: no bounds check
+              for (int u = 0; u < 4; u++) c[u] = S.ra[slot][q0 + 16 * u];  // padded: no bounds check
 #pragma unroll
               for (int u = 0; u < 4; u++) {
                 const int cx = (int)(c[u].x & 0xffffu), cy = (int)(c[u].x >> 16);
@@ -516,38 +585,35 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_pool_tile(PoolArgs A, int 
                 const bool ok = (ii - c[u].y) < c[u].z && (uint32_t)(cx + xoff) <= 2u * FARMS_MAX_WINDOW &&
                                 (uint32_t)(cy - ylo) <= jspan;
                 if (ok) {
-                  const int q = q0 + 16 * u;
                   const int m = max(abs(cx - xi), abs(cy - yi));
                   const int ring = ((m + FARMS_WINDOW_JUMP - 1) * 205) >> 10;  // /5 for values <= 54
-                  double2 v1 = S.a1[warp][ring][lane], v2 = S.a2[warp][ring][lane];
-                  const double2 l = S.lx[slot][q];
-                  v1.x += l.x;
-                  v1.y += l.y;
-                  v2.x += S.ly[slot][q];
-                  v2.y += 1.0;
-                  S.a1[warp][ring][lane] = v1;
-                  S.a2[warp][ring][lane] = v2;
+                  const float2 l = S.rb[slot][q0 + 16 * u];
+                  float4 v = S.acc[warp][ring][lane];
+                  v.x += __uint_as_float(c[u].w);
+                  v.y += l.x;
+                  v.z += l.y;
+                  v.w += 1.f;
+                  S.acc[warp][ring][lane] = v;
                 }
               }
             }
           }
           __syncwarp();
-          // sub-lane k < 11 of each half reduces ring k over the half's 16 per-lane partials
+          // sub-lane k < 11 of each half combines ring k's 16 per-lane partials in FP64
           double rl = 0.0, rx = 0.0, ry = 0.0, rn = 0.0;
           if (sub < FARMS_NSCALES) {
 #pragma unroll 8
             for (int q = 0; q < 16; q++) {
-              const int col = (half << 4) | ((q + sub) & 15);
-              const double2 v1 = S.a1[warp][sub][col], v2 = S.a2[warp][sub][col];
-              rl += v1.x;
-              rx += v1.y;
-              ry += v2.x;
-              rn += v2.y;
+              const float4 v = S.acc[warp][sub][(half << 4) | ((q + sub) & 15)];
+              rl += (double)v.x;
+              rx += (double)v.y;
+              ry += (double)v.z;
+              rn += (double)v.w;
             }
           }
           __syncwarp();
-          finish_event<16>(A, sub, rl, rx, ry, rn, pay_cx[tpos], pay_cy[tpos], (int)ii - A.h, have);
-          if (sub == 0 && have) A.done[tpos] = 1;
+          const bool fin = finish_event_checked(A, sub, rl, rx, ry, rn, (int)ii - A.h, have);
+          if (sub == 0 && fin) A.done[tpos] = 1;
         }
       }
     }
@@ -555,20 +621,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_pool_tile(PoolArgs A, int 
   if ((lane & 15) == 0 && ncand) atomicAdd(A.cand_count, ncand);
 }
 
-template <int OWS, int OHS, int WARPS, int CAP, int MINB>
+template <int WARPS, int CAP>
 void launch_tile(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
   PoolArgs A = A0;
-  using SM = TileSmem<OWS, OHS, WARPS, CAP>;
-  auto kern = k_pool_tile<OWS, OHS, WARPS, CAP, MINB>;
+  using SM = TileSmem<WARPS, CAP>;
+  auto kern = k_pool_tile<WARPS, CAP>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
     attr_set = true;
   }
-  const int otx = (A.g.W + (1 << OWS) - 1) >> OWS, oty = (A.g.H + (1 << OHS) - 1) >> OHS;
+  const int otx = (A.g.W + OT - 1) >> OT_SHIFT, oty = (A.g.H + OT - 1) >> OT_SHIFT;
   const int nseg = (nslabs + TK_SEG - 1) / TK_SEG;
   const long long items = (long long)otx * oty * nseg;
-  unsigned grid = (unsigned)std::min<long long>(items, (long long)num_sms * MINB);
+  unsigned grid = (unsigned)std::min<long long>(items, (long long)num_sms);
   kern<<<grid, WARPS * 32, sizeof(SM), s>>>(A, otx, oty, nseg);
 }
 
@@ -590,16 +656,16 @@ void launch_build_records(const uint32_t *skeys, const uint32_t *sidx, size_t m,
                                                    pay, cell_start, ncells);
 }
 
-int pool_tile_smem_bytes() { return (int)sizeof(TileSmem<5, 4, 4, 288>); }
+int pool_tile_smem_bytes() { return (int)sizeof(TileSmem<16, 768>); }
 
-// Launches the fast path (when `fast` is set) and then the general path for whatever is left.
-// work_counter: two zeroed words.  done: m zeroed bytes.  flow_per_slab: average number of flow events per
-// time slab over the whole sensor (picks the staging capacity).
+// Launches the fast path (when `fast` is set) and then the general, exact path for whatever is left.
+// work_counter: two zeroed words.  done: m zeroed bytes.
 int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_start, const uint32_t *slab_ids,
                    uint8_t *done, size_t m, uint32_t ncells, int h, int nslabs, PoolGeom g, int fast,
                    double flow_per_slab, double *global_r, double *global_theta, uint8_t *scale,
                    unsigned int *work_counter, unsigned long long *cand_count, int num_sms, cudaStream_t s) {
   if (!m) return 0;
+  (void)flow_per_slab;
   int launches = 0;
   PoolArgs A;
   A.rec = rec; A.pay = pay; A.cell_start = cell_start; A.slab_ids = slab_ids; A.done = done;
@@ -608,12 +674,7 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
   A.cand_count = cand_count;
   if (fast && g.tile_shift == 4) {
     A.work_counter = work_counter;
-    // expected staged events per slab in a (32+100) x (16+100) region, with headroom for clustering
-    const double dens = flow_per_slab / ((double)g.W * g.H);
-    if (dens * 132.0 * 116.0 * 2.2 < 288.0)  // event scenes are clustered along edges: local density reaches ~2x the mean
-      launch_tile<5, 4, 4, 288, 2>(A, nslabs, num_sms, s);   // 2 CTAs per SM
-    else
-      launch_tile<5, 5, 8, 640, 1>(A, nslabs, num_sms, s);   // 1 CTA per SM, larger staging
+    launch_tile<16, 768>(A, nslabs, num_sms, s);  // 16 warps, 1 CTA per SM, ~206 KB of shared memory
     launches++;
   }
   A.work_counter = work_counter + 1;

@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libfarms_b200.so")
 
 OK, ERR_ARG, ERR_RANGE, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4, -5
 FLAG_DEBUG_DET = 1
-FLAG_GENERIC_POOLING = 2
+FLAG_EXACT_POOLING = 2
+FLAG_GENERIC_POOLING = FLAG_EXACT_POOLING
 
 EXPORTS = [
     "farms_abi_version", "farms_create", "farms_destroy", "farms_reset", "farms_last_error", "farms_normalize_filtersize", "farms_get_params",

@@ -53,7 +53,11 @@ typedef struct {
 } farms_config;
 
 #define FARMS_FLAG_DEBUG_DET 1u       /* also produce the determinant column (farms_out.det)       */
-#define FARMS_FLAG_GENERIC_POOLING 2u /* pool every event with the general kernel (testing aid)    */
+#define FARMS_FLAG_EXACT_POOLING 2u   /* pool every event with the general FP64 kernel: slower, sums
+                                         accurate to ~1e-15 instead of ~1e-7 relative (the default fast
+                                         path keeps FP32 ring partials; its scale decisions are exact
+                                         either way, see csrc/pooling.cu)                           */
+#define FARMS_FLAG_GENERIC_POOLING FARMS_FLAG_EXACT_POOLING
 
 /* Per-event results, structure of arrays, n entries each, caller-allocated.  Any pointer may be
  * NULL (that column is skipped).  Columns follow the reference's batch output row
