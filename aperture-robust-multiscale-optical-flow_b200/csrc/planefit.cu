@@ -232,6 +232,183 @@ __global__ void __launch_bounds__(128) k_plane_fit(const uint2 *__restrict__ sae
   if ((threadIdx.x & 31) == 0 && bal) atomicAdd(valid_count, (unsigned long long)__popc(bal));
 }
 
+// Specialisation for the usual radii: the (4R+1)^2 footprint is gathered ONCE (column by column, all loads of
+// a column in flight together) into shared memory laid out [cell][thread]; window selection, AtA, the solve
+// and the inlier loop then read shared memory.  Same arithmetic, operation for operation, as k_plane_fit.
+template <int R, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_plane_fit_r(const uint2 *__restrict__ sae, const int2 *__restrict__ prevp,
+                                                         const uint16_t *__restrict__ ex,
+                                                         const uint16_t *__restrict__ ey,
+                                                         const uint32_t *__restrict__ et, int i0, int i1,
+                                                         FitParams fp, FitOut fo,
+                                                         unsigned long long *__restrict__ valid_count) {
+  constexpr int N = 4 * R + 1, N1 = 2 * R + 1;
+  extern __shared__ uint32_t s_tc[];  // times [N*N][THREADS], then hit flags (bytes) [N*N][THREADS]
+  uint32_t *my = s_tc + threadIdx.x;
+  uint8_t *myh = reinterpret_cast<uint8_t *>(s_tc + N * N * THREADS) + threadIdx.x;
+  const int i = i0 + blockIdx.x * THREADS + threadIdx.x;
+  bool valid = false;
+  if (i < i1) {
+    const int W = fp.W, H = fp.H;
+    const int x = ex[i], y = ey[i];
+    const uint32_t t = et[i];
+    unsigned long long sums[9];
+#pragma unroll
+    for (int w = 0; w < 9; w++) sums[w] = 0ull;
+#pragma unroll 1
+    for (int a = 0; a < N; a++) {
+      const int cx = x + a - 2 * R;
+      unsigned long long c0 = 0, c1 = 0, c2 = 0;
+      if (cx >= 0 && cx < W) {
+        uint2 cell[N];
+#pragma unroll
+        for (int b = 0; b < N; b++) {
+          const int cy = y + b - 2 * R;
+          cell[b] = (cy >= 0 && cy < H) ? sae[cx * H + cy] : make_uint2(0u, (uint32_t)SAE_NEVER);
+        }
+#pragma unroll
+        for (int b = 0; b < N; b++) {
+          const int cy = y + b - 2 * R;
+          int j = (int)cell[b].y;
+          uint32_t tc = cell[b].x;
+          while (j > i) {  // later events of this chunk: step back along the pixel's history
+            const int2 pp = prevp[j];
+            j = pp.x;
+            tc = (uint32_t)pp.y;
+          }
+          my[(a * N + b) * THREADS] = tc;
+          myh[(a * N + b) * THREADS] = j != SAE_NEVER;
+          if (cy >= 0 && cy < H) {
+            const unsigned long long age = (uint32_t)(t - tc);
+            if (b <= 2 * R) c0 += age;
+            if (b >= R && b <= 3 * R) c1 += age;
+            if (b >= 2 * R) c2 += age;
+          }
+        }
+      }
+      if (a <= 2 * R) { sums[0] += c0; sums[1] += c1; sums[2] += c2; }
+      if (a >= R && a <= 3 * R) { sums[3] += c0; sums[4] += c1; sums[5] += c2; }
+      if (a >= 2 * R) { sums[6] += c0; sums[7] += c1; sums[8] += c2; }
+    }
+    int best = -1;
+    unsigned long long bestsum = ~0ull;
+#pragma unroll
+    for (int w = 0; w < 9; w++) {
+      const int di = w / 3 - 1, dj = w % 3 - 1;
+      const int wx = x + di * R, wy = y + dj * R;
+      const bool inb = wx - R >= 0 && wx + R <= W - 1 && wy - R >= 0 && wy + R <= H - 1;  // src/vFlow.cpp:889
+      if (inb && sums[w] < bestsum) {  // strict '<' keeps the first minimum (:906)
+        bestsum = sums[w];
+        best = w;
+      }
+    }
+
+    double vx = 0.0, vy = 0.0, det = __longlong_as_double(0x7ff8000000000000ll);
+    int inliers = 0;
+    if (best >= 0) {
+      const int oa = (best / 3) * R, ob = (best % 3) * R;  // window origin inside the footprint
+      const int bx0 = x - 2 * R + oa, by0 = y - 2 * R + ob;
+      long long Sxx = 0, Sxy = 0, Sx = 0, Syy = 0, Sy = 0;
+#pragma unroll 1
+      for (int a = 0; a < N1; a++)
+#pragma unroll
+        for (int b = 0; b < N1; b++) {
+          const int cidx = (oa + a) * N + ob + b;
+          const bool hit = myh[cidx * THREADS] != 0;
+          const long long sx = hit ? bx0 + a : 0, sy = hit ? by0 + b : 0;
+          Sxx += sx * sx; Sxy += sx * sy; Sx += sx; Syy += sy * sy; Sy += sy;
+        }
+      const double m00 = (double)Sxx, m01 = (double)Sxy, m02 = (double)Sx, m11 = (double)Syy, m12 = (double)Sy,
+                   m22 = (double)(N1 * N1);
+      double DET = lu_det3(m00, m01, m02, m01, m11, m12, m02, m12, m22);  // :1316
+      det = DET;
+      if (!(DET < 1)) {  // :1323
+        const double d0 = m00, d1 = m01, d2 = m02, d3 = m01, d4 = m11, d5 = m12, d6 = m02, d7 = m12, d8 = m22;
+        DET = ddiv(1.0, DET);  // :1327-1336
+        const double A0 = dmul(DET, dsub(dmul(d8, d4), dmul(d7, d5)));
+        const double A1 = dmul(DET, dsub(dmul(d7, d2), dmul(d8, d1)));
+        const double A3 = dmul(DET, dsub(dmul(d6, d5), dmul(d8, d3)));
+        const double A4 = dmul(DET, dsub(dmul(d8, d0), dmul(d6, d2)));
+        const double A6 = dmul(DET, dsub(dmul(d7, d3), dmul(d6, d4)));
+        const double A7 = dmul(DET, dsub(dmul(d6, d1), dmul(d7, d0)));
+        double abc0 = 0.0, abc1 = 0.0;
+#pragma unroll 1
+        for (int a = 0; a < N1; a++)
+#pragma unroll
+          for (int b = 0; b < N1; b++) {
+            const int cidx = (oa + a) * N + ob + b;
+            const bool hit = myh[cidx * THREADS] != 0;
+            const uint32_t tc = my[cidx * THREADS];
+            const double sx = hit ? (double)(bx0 + a) : 0.0, sy = hit ? (double)(by0 + b) : 0.0;
+            const double Y = tc > t ? dmul(dsub((double)tc, MAXSTAMP_D), TSTOSEC_D) : dmul((double)tc, TSTOSEC_D);
+            const double mk0 = dadd(dadd(dadd(0.0, dmul(A0, sx)), dmul(A3, sy)), A6);
+            const double mk1 = dadd(dadd(dadd(0.0, dmul(A1, sx)), dmul(A4, sy)), A7);
+            abc0 = dadd(abc0, dmul(mk0, Y));
+            abc1 = dadd(abc1, dmul(mk1, Y));
+          }
+        const double dtdp = __dsqrt_rn(dadd(dmul(abc0, abc0), dmul(abc1, abc1)));  // :1349
+        const double half = dmul(dtdp, 0.5);
+        const double cxd = (double)x, cyd = (double)y, cz = dmul((double)t, TSTOSEC_D);  // :1236-1237
+#pragma unroll 1
+        for (int a = 0; a < N1; a++)
+#pragma unroll
+          for (int b = 0; b < N1; b++) {  // :1352-1369
+            const int cidx = (oa + a) * N + ob + b;
+            const bool hit = myh[cidx * THREADS] != 0;
+            const uint32_t tc = my[cidx * THREADS];
+            const double sx = hit ? (double)(bx0 + a) : 0.0, sy = hit ? (double)(by0 + b) : 0.0;
+            const double Y = tc > t ? dmul(dsub((double)tc, MAXSTAMP_D), TSTOSEC_D) : dmul((double)tc, TSTOSEC_D);
+            const double planedt = dadd(dmul(abc0, dsub(sx, cxd)), dmul(abc1, dsub(sy, cyd)));
+            const double actualdt = dsub(Y, cz);
+            if (fabs(dsub(planedt, actualdt)) < half && Y > 0) inliers++;
+          }
+        if (inliers >= fp.min_inl) {  // :934-939
+          const double speed = ddiv(1.0, dtdp);  // :1373-1377
+          const double angle = atan2(abc0, abc1);
+          vx = dmul(speed, cos(angle));
+          vy = dmul(speed, sin(angle));
+        }
+      }
+    }
+
+    valid = !isnan(vx) && !isnan(vy) && vx != 0.0 && vy != 0.0;  // src/vFlow.cpp:315
+    double len = 0.0, theta = 0.0, lcx = 0.0, lcy = 0.0;
+    if (valid) {
+      len = __dsqrt_rn(dadd(dmul(vx, vx), dmul(vy, vy)));  // :324
+      theta = atan2(vy, vx);                                 // :325
+      lcx = dmul(len, cos(theta));                           // :1007
+      lcy = dmul(len, sin(theta));                           // :1008
+    }
+    fo.vx[i] = vx;
+    fo.vy[i] = vy;
+    fo.len[i] = len;
+    fo.theta[i] = theta;
+    fo.lcx[i] = lcx;
+    fo.lcy[i] = lcy;
+    fo.valid[i] = valid ? 1 : 0;
+    fo.best_window[i] = (int8_t)best;
+    fo.inliers[i] = (uint16_t)inliers;
+    if (fo.det) fo.det[i] = det;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, valid);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(valid_count, (unsigned long long)__popc(bal));
+}
+
+template <int R, int THREADS>
+void launch_fit_r(const uint2 *sae, const int2 *prevp, const uint16_t *ex, const uint16_t *ey, const uint32_t *et,
+                  int i0, int i1, FitParams fp, FitOut fo, unsigned long long *valid_count, cudaStream_t s) {
+  constexpr int N = 4 * R + 1;
+  constexpr size_t smem = (size_t)N * N * THREADS * (sizeof(uint32_t) + 1);
+  auto kern = k_plane_fit_r<R, THREADS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)((i1 - i0 + THREADS - 1) / THREADS);
+  kern<<<grid, THREADS, smem, s>>>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count);
+}
+
 __global__ void k_sae_init(uint2 *sae, size_t npx) {
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q < npx) sae[q] = make_uint2(0u, (uint32_t)SAE_NEVER);
@@ -285,7 +462,11 @@ void launch_sae_finalize(uint2 *sae, const uint32_t *pix, const int32_t *nextp, 
 void launch_plane_fit(const uint2 *sae, const int2 *prevp, const uint16_t *ex, const uint16_t *ey,
                       const uint32_t *et, int i0, int i1, FitParams fp, FitOut fo, unsigned long long *valid_count,
                       cudaStream_t s) {
-  if (i1 > i0) k_plane_fit<<<nb((size_t)(i1 - i0), 128), 128, 0, s>>>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count);
+  if (i1 <= i0) return;
+  if (fp.r == 1) launch_fit_r<1, 128>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count, s);
+  else if (fp.r == 2) launch_fit_r<2, 128>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count, s);
+  else if (fp.r == 3) launch_fit_r<3, 64>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count, s);
+  else k_plane_fit<<<nb((size_t)(i1 - i0), 128), 128, 0, s>>>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count);
 }
 
 void launch_sae_export(const uint2 *sae, size_t npx, uint32_t *last_t, uint8_t *hit, cudaStream_t s) {
