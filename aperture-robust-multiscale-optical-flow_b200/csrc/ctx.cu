@@ -588,4 +588,13 @@ int farms_slice_surface(farms_ctx *c, const uint16_t *d_x, const uint16_t *d_y, 
   return FARMS_OK;
 }
 
+int farms_pack4_f32(farms_ctx *c, const double *d_a, const double *d_b, const double *d_c, const double *d_d,
+                    uint64_t n, float *d_out4) {
+  if (!c || (n && (!d_a || !d_b || !d_c || !d_d || !d_out4))) return FARMS_ERR_ARG;
+  CU(cudaSetDevice(c->cfg.device));
+  launch_pack4(d_a, d_b, d_c, d_d, (size_t)n, (float4 *)d_out4, c->stream);
+  CU(cudaStreamSynchronize(c->stream));
+  return FARMS_OK;
+}
+
 }  // extern "C"

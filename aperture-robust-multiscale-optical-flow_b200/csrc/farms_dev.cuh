@@ -73,6 +73,9 @@ void launch_slice_surface(const uint16_t *x, const uint16_t *y, const uint64_t *
 void launch_unpack_surface(const unsigned long long *packed, size_t npx, uint32_t *last_t, uint8_t *hit,
                            cudaStream_t s);
 
+void launch_pack4(const double *a, const double *b, const double *c, const double *d, size_t n, float4 *out,
+                  cudaStream_t s);
+
 // ---- planefit.cu ----
 void launch_sae_init(uint2 *sae, size_t npx, cudaStream_t s);
 void launch_sae_advance(uint2 *sae, const uint32_t *pix, const uint32_t *et, const int32_t *nextp, int c0, int c1,

@@ -90,9 +90,20 @@ __global__ void k_unpack_surface(const unsigned long long *__restrict__ packed, 
   hit[q] = v != 0ull;
 }
 
+__global__ void k_pack4(const double *__restrict__ a, const double *__restrict__ b, const double *__restrict__ c,
+                        const double *__restrict__ d, size_t n, float4 *__restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float4((float)a[i], (float)b[i], (float)c[i], (float)d[i]);
+}
+
 inline unsigned nb(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
+
+void launch_pack4(const double *a, const double *b, const double *c, const double *d, size_t n, float4 *out,
+                  cudaStream_t s) {
+  if (n) k_pack4<<<nb(n, 256), 256, 0, s>>>(a, b, c, d, n, out);
+}
 
 void launch_ingest(const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t t0, size_t n, int W, int H,
                    uint16_t *ex, uint16_t *ey, uint32_t *et, uint32_t *pix, uint32_t *idx, uint32_t idx_base,

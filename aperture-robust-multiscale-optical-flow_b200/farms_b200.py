@@ -20,7 +20,7 @@ FLAG_GENERIC_POOLING = FLAG_EXACT_POOLING
 EXPORTS = [
     "farms_abi_version", "farms_create", "farms_destroy", "farms_reset", "farms_last_error", "farms_normalize_filtersize", "farms_get_params",
     "farms_process_host", "farms_process_device", "farms_num_events", "farms_get_timings", "farms_set_t0",
-    "farms_state_export", "farms_state_fold", "farms_slice_surface",
+    "farms_state_export", "farms_state_fold", "farms_slice_surface", "farms_pack4_f32",
 ]
 
 
@@ -79,6 +79,7 @@ def lib():
         L.farms_state_fold.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.farms_slice_surface.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                                           C.c_void_p, C.c_void_p]
+        L.farms_pack4_f32.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_void_p]
         _lib = L
     return _lib
 
@@ -180,3 +181,8 @@ class Farms:
     def slice_surface(self, x, y, t, t0, d_last_t, d_hit):
         self._check(lib().farms_slice_surface(self._h, x.data_ptr(), y.data_ptr(), t.data_ptr(), x.numel(), int(t0),
                                               d_last_t.data_ptr(), d_hit.data_ptr()))
+
+    def pack4_f32(self, a, b, c, d, out4):
+        """a..d: f64 CUDA tensors of n entries; out4: float32 CUDA tensor of shape (>= n, 4)."""
+        self._check(lib().farms_pack4_f32(self._h, a.data_ptr(), b.data_ptr(), c.data_ptr(), d.data_ptr(), a.numel(),
+                                          out4.data_ptr()))

@@ -206,8 +206,6 @@ def main():
     tdt = {np.uint32: torch.int32, np.float64: torch.float64, np.uint8: torch.uint8}
     dev_out = {k: torch.empty(n_all, dtype=tdt[farms_b200.OUT_DTYPES[k]], device=dev) for k in E2E_COLUMNS}
     host_out = None
-    packed = torch.empty((n_owned, 4), dtype=torch.float32, device=dev) if dist else None
-    gathered = None
 
     def exchange_state():
         """SAE at this rank's halo start = fold of earlier ranks' 'last event per pixel' surfaces."""
@@ -220,21 +218,22 @@ def main():
         for r in range(rank):
             f.state_fold(all_t[r * npx:(r + 1) * npx], all_hit[r * npx:(r + 1) * npx])
 
+    # final NCCL gather of the owned events' outputs to rank 0 (float4 per event); slices differ by a few
+    # events, so every rank sends n_max rows and rank 0 keeps the first sizes[r]
+    if dist:
+        sz = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(sz, torch.tensor([n_owned], dtype=torch.int64, device=dev))
+        sizes = [int(q.item()) for q in sz]
+        n_max = max(sizes)
+        packed = torch.zeros((n_max, 4), dtype=torch.float32, device=dev)
+        gathered = [torch.empty((n_max, 4), dtype=torch.float32, device=dev) for _ in range(world)] if rank == 0 else None
+
     def gather_outputs(cols):
-        """final NCCL gather of the per-event outputs of the owned events to rank 0 (f32 columns)."""
         if not dist:
             return
-        nonlocal gathered
-        for j, k in enumerate(("global_r", "global_theta", "local_r", "local_theta")):
-            packed[:, j] = cols[k][n_halo:]
-        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([n_owned], dtype=torch.int64, device=dev))
-        if rank == 0:
-            if gathered is None:
-                gathered = [torch.empty((int(s.item()), 4), dtype=torch.float32, device=dev) for s in sizes]
-            dist.gather(packed, gathered, dst=0)
-        else:
-            dist.gather(packed, None, dst=0)
+        f.pack4_f32(cols["global_r"][n_halo:], cols["global_theta"][n_halo:], cols["local_r"][n_halo:],
+                    cols["local_theta"][n_halo:], packed)
+        dist.gather(packed, gathered, dst=0)
 
     launches = [0]
     stage = {}
@@ -244,7 +243,7 @@ def main():
         exchange_state()
         f.process_device(dx, dy, dt, columns=E2E_COLUMNS, out=dev_out)
         tm = f.timings()
-        launches[0] += tm["kernel_launches"] + (3 if dist else 0)
+        launches[0] += tm["kernel_launches"] + (3 + rank if dist else 0)
         for k, v in tm.items():
             stage[k] = stage.get(k, 0) + v
         gather_outputs(dev_out)

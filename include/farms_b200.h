@@ -146,6 +146,12 @@ int farms_state_fold(farms_ctx *ctx, const uint32_t *d_last_t, const uint8_t *d_
 int farms_slice_surface(farms_ctx *ctx, const uint16_t *d_x, const uint16_t *d_y, const uint64_t *d_t,
                         uint64_t n, uint64_t t0, uint32_t *d_last_t, uint8_t *d_hit);
 
+/* K5 helper for the final gather of a time-sliced run: interleave four f64 device columns (normally globalR,
+ * globalTheta, localR, localTheta -- the README's 8-column contract minus the echoed x y t p) into one
+ * float4-per-event device buffer that goes over NVLink in a single NCCL gather. */
+int farms_pack4_f32(farms_ctx *ctx, const double *d_a, const double *d_b, const double *d_c, const double *d_d,
+                    uint64_t n, float *d_out4);
+
 #ifdef __cplusplus
 }
 #endif
