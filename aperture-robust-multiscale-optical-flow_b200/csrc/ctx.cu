@@ -36,6 +36,24 @@ struct DevBuf {
 
 }  // namespace
 
+// The per-event working arrays of one internal batch.  The host path keeps two sets so that the result
+// copies of batch k (device->host) overlap the kernels of batch k+1.
+struct WorkSet {
+  size_t cap = 0;  // capacity in events
+  uint16_t *ex = nullptr, *ey = nullptr;
+  uint32_t *et = nullptr, *em = nullptr, *keyA = nullptr, *valA = nullptr, *keyB = nullptr, *valB = nullptr,
+           *pixkeep = nullptr, *flags = nullptr, *slab_ids = nullptr;
+  int2 *prevp = nullptr;
+  int32_t *nextp = nullptr;
+  double *vx = nullptr, *vy = nullptr, *len = nullptr, *theta = nullptr, *lcx = nullptr, *lcy = nullptr,
+         *det = nullptr, *gr = nullptr, *gth = nullptr, *pay = nullptr;
+  uint8_t *valid = nullptr, *scale = nullptr, *done = nullptr;
+  int8_t *bw = nullptr;
+  uint16_t *inl = nullptr;
+  uint4 *rec = nullptr;
+  std::vector<void *> owned;
+};
+
 struct farms_ctx {
   farms_config cfg{};
   int W = 0, H = 0, fs = 0, r = 0, P = 0, min_inl = 0;
@@ -50,30 +68,21 @@ struct farms_ctx {
   uint32_t last_M = 0;
   unsigned long long valid_seen = 0;  // flow events counted so far in the current process call
   size_t halo = 0;  // events in the halo store
-  size_t cap = 0;   // capacity (events) of the per-event working arrays
   size_t cap_in = 0;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_h2d[2]{}, ev_ingest[2]{}, ev_pool[2]{}, ev_d2h[2]{}, ev_c0 = nullptr, ev_c1 = nullptr;
+  bool d2h_pending[2] = {false, false};
   farms_timings tm{};
 
   uint2 *sae = nullptr;
-  // per-event working arrays (capacity cap)
-  uint16_t *ex = nullptr, *ey = nullptr;
-  uint32_t *et = nullptr, *em = nullptr, *keyA = nullptr, *valA = nullptr, *keyB = nullptr, *valB = nullptr,
-           *pixkeep = nullptr, *flags = nullptr, *slab_ids = nullptr;
-  int2 *prevp = nullptr;
-  int32_t *nextp = nullptr;
-  double *vx = nullptr, *vy = nullptr, *len = nullptr, *theta = nullptr, *lcx = nullptr, *lcy = nullptr,
-         *det = nullptr, *gr = nullptr, *gth = nullptr, *pay = nullptr;
-  uint8_t *valid = nullptr, *scale = nullptr, *done = nullptr;
-  int8_t *bw = nullptr;
-  uint16_t *inl = nullptr;
-  uint4 *rec = nullptr;
+  WorkSet ws[2];
   // halo store
   uint16_t *hx = nullptr, *hy = nullptr;
   uint32_t *ht = nullptr, *hm = nullptr;
   double *hlen = nullptr, *hlcx = nullptr, *hlcy = nullptr;
   // staging for the host path
-  uint16_t *in_x = nullptr, *in_y = nullptr;
-  uint64_t *in_t = nullptr;
+  uint16_t *in_x[2] = {nullptr, nullptr}, *in_y[2] = {nullptr, nullptr};
+  uint64_t *in_t[2] = {nullptr, nullptr};
   // misc
   DevBuf sort_temp, scan_temp, cell_start;
   int *d_err = nullptr;
@@ -81,7 +90,6 @@ struct farms_ctx {
   unsigned int *d_work = nullptr;
   uint32_t *d_small = nullptr;  // device scratch words
   uint32_t *h_small = nullptr;  // pinned host scratch words
-  std::vector<void *> owned;
 };
 
 namespace {
@@ -105,17 +113,18 @@ int fail(farms_ctx *c, int code, const char *fmt, ...) {
   } while (0)
 
 template <class T>
-int dalloc(farms_ctx *c, T **p, size_t count) {
+int dalloc(farms_ctx *c, WorkSet &w, T **p, size_t count) {
   void *q = nullptr;
   CU(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
   *p = (T *)q;
-  c->owned.push_back(q);
+  w.owned.push_back(q);
   return 0;
 }
 
-void free_owned(farms_ctx *c) {
-  for (void *p : c->owned) cudaFree(p);
-  c->owned.clear();
+void free_owned(WorkSet &w) {
+  for (void *p : w.owned) cudaFree(p);
+  w.owned.clear();
+  w.cap = 0;
 }
 
 int ensure(farms_ctx *c, DevBuf &b, size_t bytes) {
@@ -129,24 +138,22 @@ int ensure(farms_ctx *c, DevBuf &b, size_t bytes) {
   return 0;
 }
 
-// (re)allocate the per-event working arrays for `cap` events
-int alloc_working(farms_ctx *c, size_t cap) {
-  if (cap <= c->cap) return 0;
-  CU(cudaStreamSynchronize(c->stream));
-  // keep the persistent pieces (sae, halo store, staging, counters) -- they are not in `owned`
-  free_owned(c);
-  c->cap = 0;
+// (re)allocate the per-event working arrays of one set for `cap` events
+int alloc_working(farms_ctx *c, WorkSet &w, size_t cap) {
+  if (cap <= w.cap) return 0;
+  CU(cudaDeviceSynchronize());
+  free_owned(w);
   int rc = 0;
-#define A(ptr, n) if ((rc = dalloc(c, &c->ptr, (n)))) return rc;
+#define A(ptr, n) if ((rc = dalloc(c, w, &w.ptr, (n)))) return rc;
   A(ex, cap) A(ey, cap) A(et, cap) A(em, cap) A(keyA, cap) A(valA, cap) A(keyB, cap) A(valB, cap)
   A(pixkeep, cap) A(flags, cap) A(slab_ids, cap + 1) A(prevp, cap) A(nextp, cap)
   A(vx, cap) A(vy, cap) A(len, cap) A(theta, cap) A(lcx, cap) A(lcy, cap) A(gr, cap) A(gth, cap)
   A(pay, 3 * cap) A(done, cap) A(valid, cap) A(scale, cap) A(bw, cap) A(inl, cap) A(rec, cap)
-  if (c->cfg.flags & FARMS_FLAG_DEBUG_DET) { A(det, cap) } else c->det = nullptr;
+  if (c->cfg.flags & FARMS_FLAG_DEBUG_DET) { A(det, cap) } else w.det = nullptr;
 #undef A
   if ((rc = ensure(c, c->sort_temp, radix_sort_temp_bytes(cap)))) return rc;
   if ((rc = ensure(c, c->scan_temp, scan_temp_bytes(cap)))) return rc;
-  c->cap = cap;
+  w.cap = cap;
   return 0;
 }
 
@@ -173,53 +180,65 @@ __global__ void k_nslabs(const uint32_t *__restrict__ em, const uint32_t *__rest
   out[0] = excl[m - 1] + ((m > 1 && first) ? 1u : 0u) + 1u;
 }
 
-struct Loc {  // where the caller's buffers live
-  bool device;
-};
+// Small device->host read-backs (error flag, slab count, tail position) are written straight into pinned host
+// memory by a kernel: a cudaMemcpy on the compute stream would queue behind the large result copies of the
+// previous batch on the device->host copy engine and stall the kernels.
+__global__ void k_publish(uint32_t *__restrict__ host_dst, const uint32_t *__restrict__ src, int nwords) {
+  if ((int)threadIdx.x < nwords) host_dst[threadIdx.x] = src[threadIdx.x];
+  __threadfence_system();
+}
 
 template <class T>
-int copy_out(farms_ctx *c, T *dst, const T *src, size_t n, bool to_device) {
+int copy_out(farms_ctx *c, T *dst, const T *src, size_t n, bool to_device, cudaStream_t st) {
   if (!dst || !n) return 0;
-  CU(cudaMemcpyAsync(dst, src, n * sizeof(T), to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(dst, src, n * sizeof(T), to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   return 0;
 }
 
 // One internal batch: n new events already on the device at (dx, dy, dt).
-int run_batch(farms_ctx *c, const uint16_t *dx, const uint16_t *dy, const uint64_t *dt, size_t n, const farms_out *out,
-              size_t out_off, bool out_device, float *stage_ms) {
+// Results go out on `out_stream` (the compute stream itself, or the device->host stream of the host path).
+int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, const uint64_t *dt, size_t n,
+              const farms_out *out, size_t out_off, bool out_device, cudaStream_t out_stream, float *stage_ms) {
   cudaStream_t s = c->stream;
+  WorkSet &w = c->ws[set];
   const size_t h = c->halo, m = h + n;
   int rc;
-  if (m > c->cap && (rc = alloc_working(c, m + m / 8 + 1024))) return rc;
+  if (m > w.cap && (rc = alloc_working(c, w, m + m / 8 + 1024))) return rc;
+  // this set's previous results must have left the device before it is overwritten
+  if (c->d2h_pending[set]) {
+    CU(cudaStreamWaitEvent(s, c->ev_d2h[set], 0));
+    c->d2h_pending[set] = false;
+  }
   uint64_t *L = &c->tm.kernel_launches;
 
   // ---- halo to the front of the working arrays ----
   if (h) {
-    CU(cudaMemcpyAsync(c->ex, c->hx, h * 2, cudaMemcpyDeviceToDevice, s));
-    CU(cudaMemcpyAsync(c->ey, c->hy, h * 2, cudaMemcpyDeviceToDevice, s));
-    CU(cudaMemcpyAsync(c->et, c->ht, h * 4, cudaMemcpyDeviceToDevice, s));
-    CU(cudaMemcpyAsync(c->em, c->hm, h * 4, cudaMemcpyDeviceToDevice, s));
-    CU(cudaMemcpyAsync(c->len, c->hlen, h * 8, cudaMemcpyDeviceToDevice, s));
-    CU(cudaMemcpyAsync(c->lcx, c->hlcx, h * 8, cudaMemcpyDeviceToDevice, s));
-    CU(cudaMemcpyAsync(c->lcy, c->hlcy, h * 8, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(w.ex, c->hx, h * 2, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(w.ey, c->hy, h * 2, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(w.et, c->ht, h * 4, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(w.em, c->hm, h * 4, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(w.len, c->hlen, h * 8, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(w.lcx, c->hlcx, h * 8, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(w.lcy, c->hlcy, h * 8, cudaMemcpyDeviceToDevice, s));
   }
   CU(cudaEventRecord(c->ev[EV_H2D], s));
 
   // ---- K1 ingest ----
   CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), s));
-  launch_ingest(dx, dy, dt, c->t0, n, c->W, c->H, c->ex + h, c->ey + h, c->et + h, c->keyA + h, c->valA + h,
+  launch_ingest(dx, dy, dt, c->t0, n, c->W, c->H, w.ex + h, w.ey + h, w.et + h, w.keyA + h, w.valA + h,
                 (uint32_t)h, c->d_err, s);
-  launch_halo_keys(c->ex, c->ey, h, c->H, c->keyA, c->valA, s);
-  inclusive_max_scan_u32(c->et + h, c->em + h, n, c->last_M, c->scan_temp.p, s, L);
-  CU(cudaMemcpyAsync(c->pixkeep, c->keyA, m * 4, cudaMemcpyDeviceToDevice, s));
+  launch_halo_keys(w.ex, w.ey, h, c->H, w.keyA, w.valA, s);
+  inclusive_max_scan_u32(w.et + h, w.em + h, n, c->last_M, c->scan_temp.p, s, L);
+  CU(cudaMemcpyAsync(w.pixkeep, w.keyA, m * 4, cudaMemcpyDeviceToDevice, s));
   *L += 2;
-  CU(cudaMemcpyAsync(c->h_small, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  k_publish<<<1, 32, 0, s>>>(c->h_small, (const uint32_t *)c->d_err, 1);
   CU(cudaEventRecord(c->ev[EV_INGEST], s));
+  CU(cudaEventRecord(c->ev_ingest[set], s));  // the input staging buffers of this set are free again
 
   // ---- K2 history index: stable sort by pixel, prev/next links ----
-  int which = radix_sort_pairs(c->keyA, c->valA, c->keyB, c->valB, m, bits_for(c->npx), c->sort_temp.p, s, L);
-  const uint32_t *skeys = which ? c->keyB : c->keyA, *svals = which ? c->valB : c->valA;
-  launch_links(skeys, svals, c->et, c->sae, m, c->prevp, c->nextp, s);
+  int which = radix_sort_pairs(w.keyA, w.valA, w.keyB, w.valB, m, bits_for(c->npx), c->sort_temp.p, s, L);
+  const uint32_t *skeys = which ? w.keyB : w.keyA, *svals = which ? w.valB : w.valA;
+  launch_links(skeys, svals, w.et, c->sae, m, w.prevp, w.nextp, s);
   *L += 1;
   CU(cudaEventRecord(c->ev[EV_INDEX], s));
 
@@ -229,28 +248,28 @@ int run_batch(farms_ctx *c, const uint16_t *dx, const uint16_t *dy, const uint64
 
   // ---- K3 plane fit, chunk by chunk against the chunk-end SAE snapshot ----
   FitParams fp{c->W, c->H, c->r, c->P, c->min_inl};
-  FitOut fo{c->vx, c->vy, c->len, c->theta, c->lcx, c->lcy, c->valid, c->bw, c->inl, c->det};
+  FitOut fo{w.vx, w.vy, w.len, w.theta, w.lcx, w.lcy, w.valid, w.bw, w.inl, w.det};
   for (size_t c0 = 0; c0 < m; c0 += FIT_CHUNK) {
     const size_t c1 = std::min(m, c0 + (size_t)FIT_CHUNK);
-    launch_sae_advance(c->sae, c->pixkeep, c->et, c->nextp, (int)c0, (int)c1, s);
+    launch_sae_advance(c->sae, w.pixkeep, w.et, w.nextp, (int)c0, (int)c1, s);
     *L += 1;
     if (c1 > h) {
-      launch_plane_fit(c->sae, c->prevp, c->ex, c->ey, c->et, (int)std::max(c0, h), (int)c1, fp, fo, c->d_counters, s);
+      launch_plane_fit(c->sae, w.prevp, w.ex, w.ey, w.et, (int)std::max(c0, h), (int)c1, fp, fo, c->d_counters, s);
       *L += 1;
     }
   }
-  launch_sae_finalize(c->sae, c->pixkeep, c->nextp, (int)m, s);
+  launch_sae_finalize(c->sae, w.pixkeep, w.nextp, (int)m, s);
   *L += 1;
   CU(cudaEventRecord(c->ev[EV_FIT], s));
 
   // ---- K4a pooling index: dense time slabs x tiles ----
   CU(cudaMemsetAsync(c->d_small, 0, 16, s));
-  launch_slab_flags(c->em, c->et, m, c->flags, c->d_small + 1, s);
-  exclusive_scan_u32(c->flags, c->flags, m, c->scan_temp.p, s, L);
-  k_nslabs<<<1, 1, 0, s>>>(c->em, c->flags, (uint32_t)m, c->d_small);
+  launch_slab_flags(w.em, w.et, m, w.flags, c->d_small + 1, s);
+  exclusive_scan_u32(w.flags, w.flags, m, c->scan_temp.p, s, L);
+  k_nslabs<<<1, 1, 0, s>>>(w.em, w.flags, (uint32_t)m, c->d_small);
   *L += 2;
-  CU(cudaMemcpyAsync(c->h_small, c->d_small, 8, cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(c->h_small + 2, c->d_counters, 8, cudaMemcpyDeviceToHost, s));
+  k_publish<<<1, 32, 0, s>>>(c->h_small, c->d_small, 2);
+  k_publish<<<1, 32, 0, s>>>(c->h_small + 2, (const uint32_t *)c->d_counters, 2);
   CU(cudaStreamSynchronize(s));
   const size_t nslabs = c->h_small[0];
   const int monotone = c->h_small[1] == 0;
@@ -272,62 +291,70 @@ int run_batch(farms_ctx *c, const uint16_t *dx, const uint16_t *dy, const uint64
   if (ncells >= (1ull << 31)) return fail(c, FARMS_ERR_NOMEM, "pooling index too large (%zu cells)", ncells);
   if ((rc = ensure(c, c->cell_start, (ncells + 1) * sizeof(uint32_t)))) return rc;
   CU(cudaMemsetAsync(c->cell_start.p, 0, (ncells + 1) * sizeof(uint32_t), s));
-  launch_cell_keys(c->ex, c->ey, c->em, c->flags, c->len, m, g, (uint32_t)ncells, c->keyA, c->valA, c->slab_ids, s);
-  which = radix_sort_pairs(c->keyA, c->valA, c->keyB, c->valB, m, bits_for(ncells + 1), c->sort_temp.p, s, L);
-  skeys = which ? c->keyB : c->keyA;
-  svals = which ? c->valB : c->valA;
-  launch_build_records(skeys, svals, m, c->ex, c->ey, c->et, c->nextp, c->len, c->lcx, c->lcy, monotone, c->rec,
-                       c->pay, (uint32_t *)c->cell_start.p, (uint32_t)ncells, s);
+  launch_cell_keys(w.ex, w.ey, w.em, w.flags, w.len, m, g, (uint32_t)ncells, w.keyA, w.valA, w.slab_ids, s);
+  which = radix_sort_pairs(w.keyA, w.valA, w.keyB, w.valB, m, bits_for(ncells + 1), c->sort_temp.p, s, L);
+  skeys = which ? w.keyB : w.keyA;
+  svals = which ? w.valB : w.valA;
+  launch_build_records(skeys, svals, m, w.ex, w.ey, w.et, w.nextp, w.len, w.lcx, w.lcy, monotone, w.rec,
+                       w.pay, (uint32_t *)c->cell_start.p, (uint32_t)ncells, s);
   *L += 2;
   CU(cudaEventRecord(c->ev[EV_BIN], s));
 
   // ---- K4b pooling ----
-  CU(cudaMemsetAsync(c->gr, 0, n * 8, s));
-  CU(cudaMemsetAsync(c->gth, 0, n * 8, s));
-  CU(cudaMemsetAsync(c->scale, 0, n, s));
+  CU(cudaMemsetAsync(w.gr, 0, n * 8, s));
+  CU(cudaMemsetAsync(w.gth, 0, n * 8, s));
+  CU(cudaMemsetAsync(w.scale, 0, n, s));
   CU(cudaMemsetAsync(c->d_work, 0, 2 * sizeof(unsigned int), s));
-  CU(cudaMemsetAsync(c->done, 0, m, s));
+  CU(cudaMemsetAsync(w.done, 0, m, s));
   const int fast = monotone && !(c->cfg.flags & FARMS_FLAG_GENERIC_POOLING);
-  *L += launch_pooling(c->rec, c->pay, (const uint32_t *)c->cell_start.p, c->slab_ids, c->done, m, (uint32_t)ncells,
-                       (int)h, (int)nslabs, g, fast, flow_frac * (double)m / (double)nslabs, c->gr, c->gth, c->scale,
+  *L += launch_pooling(w.rec, w.pay, (const uint32_t *)c->cell_start.p, w.slab_ids, w.done, m, (uint32_t)ncells,
+                       (int)h, (int)nslabs, g, fast, flow_frac * (double)m / (double)nslabs, w.gr, w.gth, w.scale,
                        c->d_work, c->d_counters + 1, c->num_sms, s);
   CU(cudaEventRecord(c->ev[EV_POOL], s));
 
   // ---- results of the new events ----
   if (out) {
-    if ((rc = copy_out(c, out->t_rel ? out->t_rel + out_off : nullptr, c->et + h, n, out_device))) return rc;
-    if ((rc = copy_out(c, out->global_r ? out->global_r + out_off : nullptr, c->gr, n, out_device))) return rc;
-    if ((rc = copy_out(c, out->global_theta ? out->global_theta + out_off : nullptr, c->gth, n, out_device))) return rc;
-    if ((rc = copy_out(c, out->vx ? out->vx + out_off : nullptr, c->vx + h, n, out_device))) return rc;
-    if ((rc = copy_out(c, out->vy ? out->vy + out_off : nullptr, c->vy + h, n, out_device))) return rc;
-    if ((rc = copy_out(c, out->local_r ? out->local_r + out_off : nullptr, c->len + h, n, out_device))) return rc;
-    if ((rc = copy_out(c, out->local_theta ? out->local_theta + out_off : nullptr, c->theta + h, n, out_device))) return rc;
-    if ((rc = copy_out(c, out->scale ? out->scale + out_off : nullptr, c->scale, n, out_device))) return rc;
-    if ((rc = copy_out(c, out->valid ? out->valid + out_off : nullptr, c->valid + h, n, out_device))) return rc;
-    if ((rc = copy_out(c, out->best_window ? out->best_window + out_off : nullptr, c->bw + h, n, out_device))) return rc;
-    if ((rc = copy_out(c, out->inliers ? out->inliers + out_off : nullptr, c->inl + h, n, out_device))) return rc;
-    if (out->det && c->det)
-      if ((rc = copy_out(c, out->det + out_off, c->det + h, n, out_device))) return rc;
+    if (out_stream != s) {
+      CU(cudaEventRecord(c->ev_pool[set], s));
+      CU(cudaStreamWaitEvent(out_stream, c->ev_pool[set], 0));
+    }
+    if ((rc = copy_out(c, out->t_rel ? out->t_rel + out_off : nullptr, w.et + h, n, out_device, out_stream))) return rc;
+    if ((rc = copy_out(c, out->global_r ? out->global_r + out_off : nullptr, w.gr, n, out_device, out_stream))) return rc;
+    if ((rc = copy_out(c, out->global_theta ? out->global_theta + out_off : nullptr, w.gth, n, out_device, out_stream))) return rc;
+    if ((rc = copy_out(c, out->vx ? out->vx + out_off : nullptr, w.vx + h, n, out_device, out_stream))) return rc;
+    if ((rc = copy_out(c, out->vy ? out->vy + out_off : nullptr, w.vy + h, n, out_device, out_stream))) return rc;
+    if ((rc = copy_out(c, out->local_r ? out->local_r + out_off : nullptr, w.len + h, n, out_device, out_stream))) return rc;
+    if ((rc = copy_out(c, out->local_theta ? out->local_theta + out_off : nullptr, w.theta + h, n, out_device, out_stream))) return rc;
+    if ((rc = copy_out(c, out->scale ? out->scale + out_off : nullptr, w.scale, n, out_device, out_stream))) return rc;
+    if ((rc = copy_out(c, out->valid ? out->valid + out_off : nullptr, w.valid + h, n, out_device, out_stream))) return rc;
+    if ((rc = copy_out(c, out->best_window ? out->best_window + out_off : nullptr, w.bw + h, n, out_device, out_stream))) return rc;
+    if ((rc = copy_out(c, out->inliers ? out->inliers + out_off : nullptr, w.inl + h, n, out_device, out_stream))) return rc;
+    if (out->det && w.det)
+      if ((rc = copy_out(c, out->det + out_off, w.det + h, n, out_device, out_stream))) return rc;
+    if (out_stream != s) {
+      CU(cudaEventRecord(c->ev_d2h[set], out_stream));
+      c->d2h_pending[set] = true;
+    }
   }
 
   // ---- new tail -> halo store ----
   const uint32_t window = FARMS_KILL_OLD_FLOW_TIME + (c->cfg.reorder_slack_us ? c->cfg.reorder_slack_us : DEFAULT_SLACK_US);
-  k_tail_start<<<1, 1, 0, s>>>(c->em, (uint32_t)m, window, c->d_small);
+  k_tail_start<<<1, 1, 0, s>>>(w.em, (uint32_t)m, window, c->d_small);
   *L += 1;
-  CU(cudaMemcpyAsync(c->h_small, c->d_small, 8, cudaMemcpyDeviceToHost, s));
+  k_publish<<<1, 32, 0, s>>>(c->h_small, c->d_small, 2);
   CU(cudaEventRecord(c->ev[EV_END], s));
   CU(cudaStreamSynchronize(s));
   size_t ts = c->h_small[0];
   c->last_M = c->h_small[1];
   if (m - ts > HALO_CAP) ts = m - HALO_CAP;
   const size_t nh = m - ts;
-  CU(cudaMemcpyAsync(c->hx, c->ex + ts, nh * 2, cudaMemcpyDeviceToDevice, s));
-  CU(cudaMemcpyAsync(c->hy, c->ey + ts, nh * 2, cudaMemcpyDeviceToDevice, s));
-  CU(cudaMemcpyAsync(c->ht, c->et + ts, nh * 4, cudaMemcpyDeviceToDevice, s));
-  CU(cudaMemcpyAsync(c->hm, c->em + ts, nh * 4, cudaMemcpyDeviceToDevice, s));
-  CU(cudaMemcpyAsync(c->hlen, c->len + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
-  CU(cudaMemcpyAsync(c->hlcx, c->lcx + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
-  CU(cudaMemcpyAsync(c->hlcy, c->lcy + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(c->hx, w.ex + ts, nh * 2, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(c->hy, w.ey + ts, nh * 2, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(c->ht, w.et + ts, nh * 4, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(c->hm, w.em + ts, nh * 4, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(c->hlen, w.len + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(c->hlcx, w.lcx + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(c->hlcy, w.lcy + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
   c->halo = nh;
   CU(cudaStreamSynchronize(s));
 
@@ -365,36 +392,67 @@ int process(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *
   float stage[8] = {0};
   float h2d_ms = 0, d2h_ms = 0;
   CU(cudaEventRecord(c->ev[EV_START], s));
+  const uint64_t nbatch = (n + maxb - 1) / maxb;
   if (!device && c->cap_in < std::min<uint64_t>(n, maxb)) {
-    size_t want = (size_t)std::min<uint64_t>(n, maxb);
-    if (c->in_x) { cudaFree(c->in_x); cudaFree(c->in_y); cudaFree(c->in_t); c->in_x = nullptr; }
-    CU(cudaMalloc((void **)&c->in_x, want * 2));
-    CU(cudaMalloc((void **)&c->in_y, want * 2));
-    CU(cudaMalloc((void **)&c->in_t, want * 8));
+    const size_t want = (size_t)std::min<uint64_t>(n, maxb);
+    CU(cudaDeviceSynchronize());
+    for (int k = 0; k < 2; k++) {
+      if (c->in_x[k]) { cudaFree(c->in_x[k]); cudaFree(c->in_y[k]); cudaFree(c->in_t[k]); }
+      c->in_x[k] = nullptr; c->in_y[k] = nullptr; c->in_t[k] = nullptr;
+    }
+    c->cap_in = 0;
+    for (int k = 0; k < 2; k++) {
+      CU(cudaMalloc((void **)&c->in_x[k], want * 2));
+      CU(cudaMalloc((void **)&c->in_y[k], want * 2));
+      CU(cudaMalloc((void **)&c->in_t[k], want * 8));
+    }
     c->cap_in = want;
   }
-  for (uint64_t off = 0; off < n; off += maxb) {
+  // host path: batch k+1 is uploaded while batch k computes, and the results of batch k go down while batch
+  // k+1 computes (three streams, two working sets)
+  auto upload = [&](uint64_t k) -> int {
+    const int set = (int)(k & 1);
+    const uint64_t off = k * maxb;
     const size_t nb = (size_t)std::min<uint64_t>(maxb, n - off);
+    if (k >= 2) CU(cudaStreamWaitEvent(c->h2d_stream, c->ev_ingest[set], 0));
+    CU(cudaMemcpyAsync(c->in_x[set], x + off, nb * 2, cudaMemcpyHostToDevice, c->h2d_stream));
+    CU(cudaMemcpyAsync(c->in_y[set], y + off, nb * 2, cudaMemcpyHostToDevice, c->h2d_stream));
+    CU(cudaMemcpyAsync(c->in_t[set], t + off, nb * 8, cudaMemcpyHostToDevice, c->h2d_stream));
+    CU(cudaEventRecord(c->ev_h2d[set], c->h2d_stream));
+    return 0;
+  };
+  if (!device) {
+    int rc = upload(0);
+    if (rc) return rc;
+  }
+  for (uint64_t k = 0; k < nbatch; k++) {
+    const uint64_t off = k * maxb;
+    const size_t nb = (size_t)std::min<uint64_t>(maxb, n - off);
+    const int set = device ? 0 : (int)(k & 1);
     const uint16_t *dx = x + off, *dy = y + off;
     const uint64_t *dt = t + off;
     if (!device) {
-      cudaEvent_t a = c->ev[EV_H2D];
-      CU(cudaEventRecord(c->ev[EV_INGEST], s));
-      CU(cudaMemcpyAsync(c->in_x, x + off, nb * 2, cudaMemcpyHostToDevice, s));
-      CU(cudaMemcpyAsync(c->in_y, y + off, nb * 2, cudaMemcpyHostToDevice, s));
-      CU(cudaMemcpyAsync(c->in_t, t + off, nb * 8, cudaMemcpyHostToDevice, s));
-      CU(cudaEventRecord(a, s));
-      CU(cudaEventSynchronize(a));
-      float ms = 0;
-      CU(cudaEventElapsedTime(&ms, c->ev[EV_INGEST], a));
-      h2d_ms += ms;
-      dx = c->in_x;
-      dy = c->in_y;
-      dt = c->in_t;
+      if (k + 1 < nbatch) {
+        int rc = upload(k + 1);
+        if (rc) return rc;
+      }
+      CU(cudaStreamWaitEvent(s, c->ev_h2d[set], 0));
+      dx = c->in_x[set];
+      dy = c->in_y[set];
+      dt = c->in_t[set];
     }
-    int rc = run_batch(c, dx, dy, dt, nb, out, (size_t)off, device, stage);
-    if (rc) return rc;
+    int rc = run_batch(c, set, dx, dy, dt, nb, out, (size_t)off, device, device ? s : c->d2h_stream, stage);
+    if (rc) {
+      cudaDeviceSynchronize();
+      c->d2h_pending[0] = c->d2h_pending[1] = false;
+      return rc;
+    }
     c->total_events += nb;
+  }
+  if (!device) {
+    CU(cudaStreamSynchronize(c->d2h_stream));
+    CU(cudaStreamSynchronize(c->h2d_stream));
+    c->d2h_pending[0] = c->d2h_pending[1] = false;
   }
   CU(cudaEventRecord(c->ev[EV_END], s));
   CU(cudaStreamSynchronize(s));
@@ -409,8 +467,7 @@ int process(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *
   tm.fit_ms = stage[3];
   tm.bin_ms = stage[4];
   tm.pool_ms = stage[5];
-  tm.d2h_ms = device ? 0.f : stage[6];
-  (void)d2h_ms;
+  tm.d2h_ms = d2h_ms;
   tm.events = n;
   tm.valid_events = counters[0];
   tm.pool_candidates = counters[1];
@@ -462,8 +519,16 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   if (prop.major < 10) return bail(FARMS_ERR_CUDA);  // built for sm_100a only
   c->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   for (int i = 0; i < EV_COUNT; i++)
     if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+  {
+    cudaEvent_t *evs[] = {&c->ev_h2d[0], &c->ev_h2d[1], &c->ev_ingest[0], &c->ev_ingest[1], &c->ev_pool[0],
+                          &c->ev_pool[1], &c->ev_d2h[0], &c->ev_d2h[1], &c->ev_c0, &c->ev_c1};
+    for (cudaEvent_t *e : evs)
+      if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+  }
   bool ok = true;
   ok &= cudaMalloc((void **)&c->sae, c->npx * sizeof(uint2)) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->hx, HALO_CAP * 2) == cudaSuccess;
@@ -489,14 +554,23 @@ void farms_destroy(farms_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  free_owned(c);
+  cudaDeviceSynchronize();
+  free_owned(c->ws[0]);
+  free_owned(c->ws[1]);
   void *ps[] = {c->sae, c->hx, c->hy, c->ht, c->hm, c->hlen, c->hlcx, c->hlcy, c->d_err, c->d_counters, c->d_work,
-                c->d_small, c->in_x, c->in_y, c->in_t, c->sort_temp.p, c->scan_temp.p, c->cell_start.p};
+                c->d_small, c->in_x[0], c->in_y[0], c->in_t[0], c->in_x[1], c->in_y[1], c->in_t[1], c->sort_temp.p,
+                c->scan_temp.p, c->cell_start.p};
   for (void *p : ps)
     if (p) cudaFree(p);
   if (c->h_small) cudaFreeHost(c->h_small);
   for (int i = 0; i < EV_COUNT; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  cudaEvent_t evs[] = {c->ev_h2d[0], c->ev_h2d[1], c->ev_ingest[0], c->ev_ingest[1], c->ev_pool[0], c->ev_pool[1],
+                       c->ev_d2h[0], c->ev_d2h[1], c->ev_c0, c->ev_c1};
+  for (cudaEvent_t e : evs)
+    if (e) cudaEventDestroy(e);
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -534,6 +608,8 @@ int farms_get_timings(const farms_ctx *c, farms_timings *out) {
 int farms_reset(farms_ctx *c) {
   if (!c) return FARMS_ERR_ARG;
   CU(cudaSetDevice(c->cfg.device));
+  CU(cudaDeviceSynchronize());
+  c->d2h_pending[0] = c->d2h_pending[1] = false;
   launch_sae_init(c->sae, c->npx, c->stream);
   CU(cudaStreamSynchronize(c->stream));
   c->have_t0 = false;
