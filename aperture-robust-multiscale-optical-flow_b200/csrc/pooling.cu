@@ -276,10 +276,11 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
 // everything else (measured: well under 1 % of events) is left to k_pool_any, which is exact.  Scales whose
 // extra rings are empty have bit-identical sums in both arithmetics, so exact ties behave like the reference.
 constexpr int OT_SHIFT = 5, OT = 1 << OT_SHIFT;  // owner tile edge (pixels)
-constexpr int TK_RING = 6;     // two consecutive slabs are pooled per round: their windows span <= 6 slabs
+constexpr int TK_NSL = 4;      // consecutive slabs pooled per round (more events per round => fewer, fuller waves)
+constexpr int TK_RING = 4 + TK_NSL;  // a 500-us window touches <= 5 slabs, so a round's windows span <= 4 + NSL
 constexpr int TK_PAD = 64;     // the pooling loop reads 4 x 16 records at a time without bounds checks
 constexpr int TK_SEG = 64;     // slabs per work item
-constexpr int TK_MAXT = 256;   // targets handled per round and slab
+constexpr int TK_MAXT = 128;   // targets handled per round and slab
 constexpr int TK_MAXRUN = 24;  // tile-column runs of a region: <= 10 for rows < H plus <= 10 aliased
 constexpr float TK_TIE_TOL = 2e-5f;
 
@@ -288,13 +289,13 @@ struct TileSmem {
   uint4 ra[TK_RING][CAP + TK_PAD];        // {x | y<<16 (logical window coordinates), idx, end - idx, len as f32}
   float2 rb[TK_RING][CAP];                // lcx, lcy
   float4 acc[WARPS][FARMS_NSCALES][32];   // per-lane ring partials: len, lcx, lcy, count
-  uint32_t tlist[2][TK_MAXT];
+  uint32_t tlist[TK_NSL][TK_MAXT];
   uint32_t run_s[TK_MAXRUN], run_o[TK_MAXRUN + 1];
   uint32_t wcount[WARPS];
   int tag[TK_RING];
   int count[TK_RING];
   int overflow[TK_RING];
-  unsigned int ntg[2], tnext, item;
+  unsigned int ntg[TK_NSL], tnext, item;
 };
 
 struct Region {  // pixels an owner tile can reach, as physical rectangles
@@ -483,13 +484,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
     const int ity0 = Y0 >> 4, ity1 = min((Y0 + OT - 1) >> 4, nty - 1);
     const int d_begin = seg * TK_SEG, d_end = min(d_begin + TK_SEG, A.nslabs);
 
-    // two consecutive slabs per round
-    for (int d = d_begin; d < d_end; d += 2) {
-      const int nd = min(2, d_end - d);
-      // ---- targets of this round: flow events of the owner tile in slabs d, d+1 ----
-      uint32_t ta[2][2], tb[2][2], nraw[2] = {0u, 0u};
+    // TK_NSL consecutive slabs per round
+    for (int d = d_begin; d < d_end; d += TK_NSL) {
+      const int nd = min(TK_NSL, d_end - d);
+      // ---- targets of this round: flow events of the owner tile in slabs d .. d+nd-1 ----
+      uint32_t ta[TK_NSL][2], tb[TK_NSL][2], nraw[TK_NSL];
+      uint32_t nraw_all = 0, nmax = 0;
 #pragma unroll
-      for (int w = 0; w < 2; w++)
+      for (int w = 0; w < TK_NSL; w++) {
+        nraw[w] = 0;
 #pragma unroll
         for (int c = 0; c < 2; c++) {
           ta[w][c] = tb[w][c] = 0;
@@ -500,42 +503,48 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
           }
           nraw[w] += tb[w][c] - ta[w][c];
         }
-      if (nraw[0] + nraw[1] == 0) continue;  // uniform across the CTA
+        nraw_all += nraw[w];
+        nmax = max(nmax, nraw[w]);
+      }
+      if (nraw_all == 0) continue;  // uniform across the CTA
 
-      // ---- make sure the slabs of both 500-us windows are staged ----
-      int dlo[2], dhi[2];
+      // ---- make sure the slabs of all windows of the round are staged ----
+      int dlo[TK_NSL], dhi[TK_NSL];
+      int s_first = 0x7fffffff, s_last = -1;
 #pragma unroll
-      for (int w = 0; w < 2; w++) {
+      for (int w = 0; w < TK_NSL; w++) {
         const int dd = min(d + w, d_end - 1);
         const uint32_t t_first = A.slab_ids[dd] << FARMS_SLAB_SHIFT;
         const uint32_t lo_id =
             (t_first >= (uint32_t)(FARMS_KILL_OLD_FLOW_TIME - 1) ? t_first - (FARMS_KILL_OLD_FLOW_TIME - 1) : 0u) >> FARMS_SLAB_SHIFT;
         int l = dd;
-        while (l > 0 && dd - l < TK_RING - 2 && A.slab_ids[l - 1] >= lo_id) l--;
+        while (l > 0 && dd - l < 4 && A.slab_ids[l - 1] >= lo_id) l--;
         dlo[w] = l;
         dhi[w] = dd;
+        if (nraw[w]) {
+          s_first = min(s_first, l);
+          s_last = max(s_last, dd);
+        }
       }
-      const int s_first = nraw[0] ? dlo[0] : dlo[1], s_last = nraw[1] ? dhi[1] : dhi[0];
       for (int s = s_first; s <= s_last; s++) {
         const int slot = s % TK_RING;
         if (S.tag[slot] != s) stage_slab<SM, WARPS, CAP>(A, S, s, slot, R);  // uniform: tag is read after a barrier
         __syncthreads();
       }
-      bool ovf[2] = {false, false};
+      bool ovf[TK_NSL];
 #pragma unroll
-      for (int w = 0; w < 2; w++)
+      for (int w = 0; w < TK_NSL; w++) {
+        ovf[w] = false;
         for (int s = dlo[w]; s <= dhi[w]; s++) ovf[w] |= S.overflow[s % TK_RING] != 0;
+      }
 
-      const uint32_t nmax = max(nraw[0], nraw[1]);
       for (uint32_t t0 = 0; t0 < nmax; t0 += TK_MAXT) {
         __syncthreads();
-        if (tid == 0) {
-          S.ntg[0] = S.ntg[1] = 0;
-          S.tnext = 0;
-        }
+        if (tid < TK_NSL) S.ntg[tid] = 0;
+        if (tid == 0) S.tnext = 0;
         __syncthreads();
 #pragma unroll
-        for (int w = 0; w < 2; w++)
+        for (int w = 0; w < TK_NSL; w++)
           for (uint32_t f = t0 + tid; f < min(nraw[w], t0 + TK_MAXT); f += THREADS) {
             const uint32_t n0 = tb[w][0] - ta[w][0];
             const uint32_t pos = f < n0 ? ta[w][0] + f : ta[w][1] + (f - n0);
@@ -546,17 +555,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
             if (ok) S.tlist[w][atomicAdd(&S.ntg[w], 1u)] = pos;
           }
         __syncthreads();
-        const uint32_t ntg0 = S.ntg[0], ntg1 = S.ntg[1];
-        const uint32_t tasks0 = (ntg0 + 1) >> 1, tasks = tasks0 + ((ntg1 + 1) >> 1);
+        // tasks = pairs of targets of the same slab (both halves of a warp then share their loop bounds)
+        uint32_t tstart[TK_NSL + 1];
+        tstart[0] = 0;
+#pragma unroll
+        for (int w = 0; w < TK_NSL; w++) tstart[w + 1] = tstart[w] + ((S.ntg[w] + 1) >> 1);
+        const uint32_t tasks = tstart[TK_NSL];
 
-        // ---- two targets (of the same slab) per warp: lanes 0-15 pool one event, lanes 16-31 the next ----
+        // ---- two targets per warp: lanes 0-15 pool one event, lanes 16-31 the next ----
         for (;;) {
           uint32_t k = 0;
           if (lane == 0) k = atomicAdd(&S.tnext, 1u);
           k = __shfl_sync(0xffffffffu, k, 0);
           if (k >= tasks) break;
-          const int w = k >= tasks0;
-          const uint32_t kk = (w ? k - tasks0 : k) * 2 + half, nt = w ? ntg1 : ntg0;
+          int w = 0;
+#pragma unroll
+          for (int q = 1; q < TK_NSL; q++) w += (k >= tstart[q]) ? 1 : 0;
+          const uint32_t kk = (k - tstart[w]) * 2 + half, nt = S.ntg[w];
           const bool have = kk < nt;
           const uint32_t tpos = S.tlist[w][have ? kk : nt - 1];
           const uint4 r = A.rec[tpos];
@@ -569,7 +584,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
           const int xoff = FARMS_MAX_WINDOW - xi;
 #pragma unroll
           for (int q = 0; q < FARMS_NSCALES; q++) S.acc[warp][q][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int sl = w ? dlo[1] : dlo[0], sh = w ? dhi[1] : dhi[0];
+          int sl = dlo[0], sh = dhi[0];
+#pragma unroll
+          for (int q = 1; q < TK_NSL; q++)
+            if (w == q) {
+              sl = dlo[q];
+              sh = dhi[q];
+            }
           for (int s = sl; s <= sh; s++) {
             const int slot = s % TK_RING;
             const int n = S.count[slot];
@@ -656,7 +677,7 @@ void launch_build_records(const uint32_t *skeys, const uint32_t *sidx, size_t m,
                                                    pay, cell_start, ncells);
 }
 
-int pool_tile_smem_bytes() { return (int)sizeof(TileSmem<16, 768>); }
+int pool_tile_smem_bytes() { return (int)sizeof(TileSmem<16, 640>); }
 
 // Launches the fast path (when `fast` is set) and then the general, exact path for whatever is left.
 // work_counter: two zeroed words.  done: m zeroed bytes.
@@ -674,7 +695,7 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
   A.cand_count = cand_count;
   if (fast && g.tile_shift == 4) {
     A.work_counter = work_counter;
-    launch_tile<16, 768>(A, nslabs, num_sms, s);  // 16 warps, 1 CTA per SM, ~206 KB of shared memory
+    launch_tile<16, 640>(A, nslabs, num_sms, s);  // 16 warps, 1 CTA per SM, ~224 KB of shared memory
     launches++;
   }
   A.work_counter = work_counter + 1;
