@@ -84,7 +84,7 @@ struct farms_ctx {
   uint16_t *in_x[2] = {nullptr, nullptr}, *in_y[2] = {nullptr, nullptr};
   uint64_t *in_t[2] = {nullptr, nullptr};
   // misc
-  DevBuf sort_temp, scan_temp, cell_start;
+  DevBuf sort_temp, scan_temp, cell_start, fit_scratch;
   int *d_err = nullptr;
   unsigned long long *d_counters = nullptr;  // [0] valid events, [1] pool candidates
   unsigned int *d_work = nullptr;
@@ -247,6 +247,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   if (((int *)c->h_small)[0]) return fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
 
   // ---- K3 plane fit, chunk by chunk against the chunk-end SAE snapshot ----
+  if ((rc = ensure(c, c->fit_scratch, plane_fit_scratch_bytes(c->r, FIT_CHUNK)))) return rc;
   FitParams fp{c->W, c->H, c->r, c->P, c->min_inl};
   FitOut fo{w.vx, w.vy, w.len, w.theta, w.lcx, w.lcy, w.valid, w.bw, w.inl, w.det};
   for (size_t c0 = 0; c0 < m; c0 += FIT_CHUNK) {
@@ -254,8 +255,8 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
     launch_sae_advance(c->sae, w.pixkeep, w.et, w.nextp, (int)c0, (int)c1, s);
     *L += 1;
     if (c1 > h) {
-      launch_plane_fit(c->sae, w.prevp, w.ex, w.ey, w.et, (int)std::max(c0, h), (int)c1, fp, fo, c->d_counters, s);
-      *L += 1;
+      *L += launch_plane_fit(c->sae, w.prevp, w.ex, w.ey, w.et, (int)std::max(c0, h), (int)c1, fp, fo, c->d_counters,
+                             c->fit_scratch.p, s);
     }
   }
   launch_sae_finalize(c->sae, w.pixkeep, w.nextp, (int)m, s);
@@ -559,7 +560,7 @@ void farms_destroy(farms_ctx *c) {
   free_owned(c->ws[1]);
   void *ps[] = {c->sae, c->hx, c->hy, c->ht, c->hm, c->hlen, c->hlcx, c->hlcy, c->d_err, c->d_counters, c->d_work,
                 c->d_small, c->in_x[0], c->in_y[0], c->in_t[0], c->in_x[1], c->in_y[1], c->in_t[1], c->sort_temp.p,
-                c->scan_temp.p, c->cell_start.p};
+                c->scan_temp.p, c->cell_start.p, c->fit_scratch.p};
   for (void *p : ps)
     if (p) cudaFree(p);
   if (c->h_small) cudaFreeHost(c->h_small);

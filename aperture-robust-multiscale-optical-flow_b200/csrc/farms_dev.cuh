@@ -81,9 +81,10 @@ void launch_sae_init(uint2 *sae, size_t npx, cudaStream_t s);
 void launch_sae_advance(uint2 *sae, const uint32_t *pix, const uint32_t *et, const int32_t *nextp, int c0, int c1,
                         cudaStream_t s);
 void launch_sae_finalize(uint2 *sae, const uint32_t *pix, const int32_t *nextp, int m, cudaStream_t s);
-void launch_plane_fit(const uint2 *sae, const int2 *prevp, const uint16_t *ex, const uint16_t *ey,
-                      const uint32_t *et, int i0, int i1, FitParams fp, FitOut fo,
-                      unsigned long long *valid_count, cudaStream_t s);
+size_t plane_fit_scratch_bytes(int r, size_t chunk_events);
+int launch_plane_fit(const uint2 *sae, const int2 *prevp, const uint16_t *ex, const uint16_t *ey,
+                     const uint32_t *et, int i0, int i1, FitParams fp, FitOut fo, unsigned long long *valid_count,
+                     void *scratch, cudaStream_t s);
 void launch_sae_export(const uint2 *sae, size_t npx, uint32_t *last_t, uint8_t *hit, cudaStream_t s);
 void launch_sae_fold(uint2 *sae, size_t npx, const uint32_t *last_t, const uint8_t *hit, cudaStream_t s);
 

@@ -232,95 +232,173 @@ __global__ void __launch_bounds__(128) k_plane_fit(const uint2 *__restrict__ sae
   if ((threadIdx.x & 31) == 0 && bal) atomicAdd(valid_count, (unsigned long long)__popc(bal));
 }
 
-// Specialisation for the usual radii: the (4R+1)^2 footprint is gathered ONCE (column by column, all loads of
-// a column in flight together) into shared memory laid out [cell][thread]; window selection, AtA, the solve
-// and the inlier loop then read shared memory.  Same arithmetic, operation for operation, as k_plane_fit.
-template <int R, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_plane_fit_r(const uint2 *__restrict__ sae, const int2 *__restrict__ prevp,
-                                                         const uint16_t *__restrict__ ex,
-                                                         const uint16_t *__restrict__ ey,
-                                                         const uint32_t *__restrict__ et, int i0, int i1,
-                                                         FitParams fp, FitOut fo,
-                                                         unsigned long long *__restrict__ valid_count) {
-  constexpr int N = 4 * R + 1, N1 = 2 * R + 1;
-  extern __shared__ uint32_t s_tc[];  // times [N*N][THREADS], then hit flags (bytes) [N*N][THREADS]
-  uint32_t *my = s_tc + threadIdx.x;
-  uint8_t *myh = reinterpret_cast<uint8_t *>(s_tc + N * N * THREADS) + threadIdx.x;
-  const int i = i0 + blockIdx.x * THREADS + threadIdx.x;
-  bool valid = false;
-  if (i < i1) {
-    const int W = fp.W, H = fp.H;
-    const int x = ex[i], y = ey[i];
-    const uint32_t t = et[i];
-    unsigned long long sums[9];
+// ---------------------------------------------------------------------------------------------------
+// Specialisation for the usual radii (filtersize 3, 5, 7): two kernels per chunk.
+//
+// k_fit_gather: 16 lanes per event, lane = row of the (4R+1)^2 footprint.  The surface is x-major, so the cells
+// of one footprint column are contiguous in memory and the lanes of a group read them with one or two
+// 128-byte lines per column (a thread-per-event gather issues 81 fully scattered 8-byte loads and saturates
+// the L1 wavefront pipe).  Row sums -> prefix over lanes -> the 9 window sums -> best window; the winning
+// window's cells (time, hit) go to a small per-event record that stays in L2.
+// k_fit_solve: one thread per event reads its record with 16-byte loads and runs the FP64 algebra.
+// Same arithmetic, operation for operation, as k_plane_fit.
+// ---------------------------------------------------------------------------------------------------
+template <int R>
+struct FitRec {
+  static constexpr int N = 4 * R + 1, N1 = 2 * R + 1, P = N1 * N1;
+  static constexpr int WORDS = (P + 3) <= 16 ? 16 : (P + 3) <= 32 ? 32 : 64;  // t[P], hit mask lo/hi, best
+};
+
+template <int R>
+__global__ void __launch_bounds__(256) k_fit_gather(const uint2 *__restrict__ sae, const int2 *__restrict__ prevp,
+                                                    const uint16_t *__restrict__ ex, const uint16_t *__restrict__ ey,
+                                                    const uint32_t *__restrict__ et, int i0, int i1, int W, int H,
+                                                    uint32_t *__restrict__ recs) {
+  constexpr int N = FitRec<R>::N, N1 = FitRec<R>::N1, P = FitRec<R>::P, WORDS = FitRec<R>::WORDS;
+  const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int b = threadIdx.x & 15;  // footprint row handled by this lane
+  const int i = i0 + gid;
+  const bool live = i < i1;        // uniform per 16-lane group
+  const int ii = live ? i : i1 - 1;
+  const int x = ex[ii], y = ey[ii];
+  const uint32_t t = et[ii];
+  const int cy = y + b - 2 * R;
+  const bool row_ok = live && b < N && cy >= 0 && cy < H;
+  uint32_t tc[N];
+  uint32_t hit = 0;
+  unsigned long long r0 = 0, r1 = 0, r2 = 0;
+  {
+    uint2 cell[N];
 #pragma unroll
-    for (int w = 0; w < 9; w++) sums[w] = 0ull;
-#pragma unroll 1
     for (int a = 0; a < N; a++) {
       const int cx = x + a - 2 * R;
-      unsigned long long c0 = 0, c1 = 0, c2 = 0;
-      if (cx >= 0 && cx < W) {
-        uint2 cell[N];
-#pragma unroll
-        for (int b = 0; b < N; b++) {
-          const int cy = y + b - 2 * R;
-          cell[b] = (cy >= 0 && cy < H) ? sae[cx * H + cy] : make_uint2(0u, (uint32_t)SAE_NEVER);
-        }
-#pragma unroll
-        for (int b = 0; b < N; b++) {
-          const int cy = y + b - 2 * R;
-          int j = (int)cell[b].y;
-          uint32_t tc = cell[b].x;
-          while (j > i) {  // later events of this chunk: step back along the pixel's history
-            const int2 pp = prevp[j];
-            j = pp.x;
-            tc = (uint32_t)pp.y;
-          }
-          my[(a * N + b) * THREADS] = tc;
-          myh[(a * N + b) * THREADS] = j != SAE_NEVER;
-          if (cy >= 0 && cy < H) {
-            const unsigned long long age = (uint32_t)(t - tc);
-            if (b <= 2 * R) c0 += age;
-            if (b >= R && b <= 3 * R) c1 += age;
-            if (b >= 2 * R) c2 += age;
-          }
-        }
-      }
-      if (a <= 2 * R) { sums[0] += c0; sums[1] += c1; sums[2] += c2; }
-      if (a >= R && a <= 3 * R) { sums[3] += c0; sums[4] += c1; sums[5] += c2; }
-      if (a >= 2 * R) { sums[6] += c0; sums[7] += c1; sums[8] += c2; }
+      cell[a] = (row_ok && cx >= 0 && cx < W) ? sae[cx * H + cy] : make_uint2(0u, (uint32_t)SAE_NEVER);
     }
-    int best = -1;
-    unsigned long long bestsum = ~0ull;
 #pragma unroll
-    for (int w = 0; w < 9; w++) {
-      const int di = w / 3 - 1, dj = w % 3 - 1;
-      const int wx = x + di * R, wy = y + dj * R;
-      const bool inb = wx - R >= 0 && wx + R <= W - 1 && wy - R >= 0 && wy + R <= H - 1;  // src/vFlow.cpp:889
-      if (inb && sums[w] < bestsum) {  // strict '<' keeps the first minimum (:906)
-        bestsum = sums[w];
-        best = w;
+    for (int a = 0; a < N; a++) {
+      const int cx = x + a - 2 * R;
+      int j = (int)cell[a].y;
+      uint32_t tv = cell[a].x;
+      while (j > i) {  // later events of this chunk: step back along the pixel's history
+        const int2 pp = prevp[j];
+        j = pp.x;
+        tv = (uint32_t)pp.y;
+      }
+      tc[a] = tv;
+      if (j != SAE_NEVER) hit |= 1u << a;
+      if (row_ok && cx >= 0 && cx < W) {
+        const unsigned long long age = (uint32_t)(t - tv);  // src/vFlow.cpp:894-902 as a 32-bit wrap-around
+        if (a <= 2 * R) r0 += age;
+        if (a >= R && a <= 3 * R) r1 += age;
+        if (a >= 2 * R) r2 += age;
       }
     }
+  }
+  // inclusive prefix over the rows (lanes) of the group
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) {
+    const unsigned long long p0 = __shfl_up_sync(0xffffffffu, r0, o, 16), p1 = __shfl_up_sync(0xffffffffu, r1, o, 16),
+                             p2 = __shfl_up_sync(0xffffffffu, r2, o, 16);
+    if (b >= o) {
+      r0 += p0;
+      r1 += p1;
+      r2 += p2;
+    }
+  }
+  // window (di, dj): columns by di (r0/r1/r2), rows [dj*R, dj*R + 2R]
+  unsigned long long sums[9];
+#pragma unroll
+  for (int dj = 0; dj < 3; dj++) {
+    const int hi = dj * R + 2 * R, lo = dj * R - 1;
+    const unsigned long long h0 = __shfl_sync(0xffffffffu, r0, hi, 16), h1 = __shfl_sync(0xffffffffu, r1, hi, 16),
+                             h2 = __shfl_sync(0xffffffffu, r2, hi, 16);
+    unsigned long long l0 = 0, l1 = 0, l2 = 0;
+    if (lo >= 0) {
+      l0 = __shfl_sync(0xffffffffu, r0, lo, 16);
+      l1 = __shfl_sync(0xffffffffu, r1, lo, 16);
+      l2 = __shfl_sync(0xffffffffu, r2, lo, 16);
+    }
+    sums[0 * 3 + dj] = h0 - l0;
+    sums[1 * 3 + dj] = h1 - l1;
+    sums[2 * 3 + dj] = h2 - l2;
+  }
+  int best = -1;
+  unsigned long long bestsum = ~0ull;
+#pragma unroll
+  for (int w = 0; w < 9; w++) {
+    const int di = w / 3 - 1, dj = w % 3 - 1;
+    const int wx = x + di * R, wy = y + dj * R;
+    const bool inb = wx - R >= 0 && wx + R <= W - 1 && wy - R >= 0 && wy + R <= H - 1;  // src/vFlow.cpp:889
+    if (inb && sums[w] < bestsum) {  // strict '<' keeps the first minimum (:906)
+      bestsum = sums[w];
+      best = w;
+    }
+  }
+  // the winning window's cells, cx-major / cy-minor like the reference's regather (:923-930)
+  const int oa = best >= 0 ? (best / 3) * R : 0, ob = best >= 0 ? (best % 3) * R : 0;
+  const int brel = b - ob;
+  const bool mine = live && best >= 0 && brel >= 0 && brel < N1;
+  uint32_t *rec = recs + (size_t)gid * WORDS;
+  unsigned long long hm = 0ull;
+#pragma unroll
+  for (int k = 0; k < N1; k++) {
+    // a = oa + k with oa in {0, R, 2R}: static selects keep tc[] in registers
+    const uint32_t v = oa == 0 ? tc[k] : (oa == R ? tc[k + R] : tc[k + 2 * R]);
+    const uint32_t hb = oa == 0 ? (hit >> k) : (oa == R ? (hit >> (k + R)) : (hit >> (k + 2 * R)));
+    if (mine) {
+      rec[k * N1 + brel] = v;
+      if (hb & 1u) hm |= 1ull << (k * N1 + brel);
+    }
+  }
+  // OR of the group's hit bits
+  uint32_t hlo = (uint32_t)hm, hhi = (uint32_t)(hm >> 32);
+#pragma unroll
+  for (int o = 8; o; o >>= 1) {
+    hlo |= __shfl_xor_sync(0xffffffffu, hlo, o, 16);
+    hhi |= __shfl_xor_sync(0xffffffffu, hhi, o, 16);
+  }
+  if (live && b == 0) {
+    rec[P] = hlo;
+    rec[P + 1] = hhi;
+    rec[P + 2] = (uint32_t)best;
+  }
+}
 
+template <int R>
+__global__ void __launch_bounds__(128) k_fit_solve(const uint32_t *__restrict__ recs, const uint16_t *__restrict__ ex,
+                                                   const uint16_t *__restrict__ ey, const uint32_t *__restrict__ et,
+                                                   int i0, int i1, FitParams fp, FitOut fo,
+                                                   unsigned long long *__restrict__ valid_count) {
+  constexpr int N1 = FitRec<R>::N1, P = FitRec<R>::P, WORDS = FitRec<R>::WORDS;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = i0 + g;
+  bool valid = false;
+  if (i < i1) {
+    uint32_t wd[WORDS];
+    const uint4 *rp = reinterpret_cast<const uint4 *>(recs + (size_t)g * WORDS);
+#pragma unroll
+    for (int q = 0; q < (P + 3 + 3) / 4; q++) {
+      const uint4 v = rp[q];
+      wd[4 * q] = v.x; wd[4 * q + 1] = v.y; wd[4 * q + 2] = v.z; wd[4 * q + 3] = v.w;
+    }
+    const unsigned long long hm = (unsigned long long)wd[P] | ((unsigned long long)wd[P + 1] << 32);
+    const int best = (int)wd[P + 2];
+    const int x = ex[i], y = ey[i];
+    const uint32_t t = et[i];
     double vx = 0.0, vy = 0.0, det = __longlong_as_double(0x7ff8000000000000ll);
     int inliers = 0;
     if (best >= 0) {
-      const int oa = (best / 3) * R, ob = (best % 3) * R;  // window origin inside the footprint
-      const int bx0 = x - 2 * R + oa, by0 = y - 2 * R + ob;
+      const int bx0 = x + (best / 3 - 1) * R - R, by0 = y + (best % 3 - 1) * R - R;
       long long Sxx = 0, Sxy = 0, Sx = 0, Syy = 0, Sy = 0;
-#pragma unroll 1
-      for (int a = 0; a < N1; a++)
 #pragma unroll
-        for (int b = 0; b < N1; b++) {
-          const int cidx = (oa + a) * N + ob + b;
-          const bool hit = myh[cidx * THREADS] != 0;
-          const long long sx = hit ? bx0 + a : 0, sy = hit ? by0 + b : 0;
-          Sxx += sx * sx; Sxy += sx * sy; Sx += sx; Syy += sy * sy; Sy += sy;
-        }
+      for (int k = 0; k < P; k++) {
+        const bool hit = (hm >> k) & 1ull;
+        const long long sx = hit ? bx0 + k / N1 : 0, sy = hit ? by0 + k % N1 : 0;
+        Sxx += sx * sx; Sxy += sx * sy; Sx += sx; Syy += sy * sy; Sy += sy;
+      }
       const double m00 = (double)Sxx, m01 = (double)Sxy, m02 = (double)Sx, m11 = (double)Syy, m12 = (double)Sy,
-                   m22 = (double)(N1 * N1);
-      double DET = lu_det3(m00, m01, m02, m01, m11, m12, m02, m12, m22);  // :1316
+                   m22 = (double)P;
+      double DET = lu_det3(m00, m01, m02, m01, m11, m12, m02, m12, m22);  // src/vFlow.cpp:1316
       det = DET;
       if (!(DET < 1)) {  // :1323
         const double d0 = m00, d1 = m01, d2 = m02, d3 = m01, d4 = m11, d5 = m12, d6 = m02, d7 = m12, d8 = m22;
@@ -332,36 +410,30 @@ __global__ void __launch_bounds__(THREADS) k_plane_fit_r(const uint2 *__restrict
         const double A6 = dmul(DET, dsub(dmul(d7, d3), dmul(d6, d4)));
         const double A7 = dmul(DET, dsub(dmul(d6, d1), dmul(d7, d0)));
         double abc0 = 0.0, abc1 = 0.0;
-#pragma unroll 1
-        for (int a = 0; a < N1; a++)
 #pragma unroll
-          for (int b = 0; b < N1; b++) {
-            const int cidx = (oa + a) * N + ob + b;
-            const bool hit = myh[cidx * THREADS] != 0;
-            const uint32_t tc = my[cidx * THREADS];
-            const double sx = hit ? (double)(bx0 + a) : 0.0, sy = hit ? (double)(by0 + b) : 0.0;
-            const double Y = tc > t ? dmul(dsub((double)tc, MAXSTAMP_D), TSTOSEC_D) : dmul((double)tc, TSTOSEC_D);
-            const double mk0 = dadd(dadd(dadd(0.0, dmul(A0, sx)), dmul(A3, sy)), A6);
-            const double mk1 = dadd(dadd(dadd(0.0, dmul(A1, sx)), dmul(A4, sy)), A7);
-            abc0 = dadd(abc0, dmul(mk0, Y));
-            abc1 = dadd(abc1, dmul(mk1, Y));
-          }
+        for (int k = 0; k < P; k++) {  // (A2*At)*Y, left to right (:1338)
+          const bool hit = (hm >> k) & 1ull;
+          const uint32_t tc = wd[k];
+          const double sx = hit ? (double)(bx0 + k / N1) : 0.0, sy = hit ? (double)(by0 + k % N1) : 0.0;
+          const double Y = tc > t ? dmul(dsub((double)tc, MAXSTAMP_D), TSTOSEC_D) : dmul((double)tc, TSTOSEC_D);
+          const double mk0 = dadd(dadd(dadd(0.0, dmul(A0, sx)), dmul(A3, sy)), A6);
+          const double mk1 = dadd(dadd(dadd(0.0, dmul(A1, sx)), dmul(A4, sy)), A7);
+          abc0 = dadd(abc0, dmul(mk0, Y));
+          abc1 = dadd(abc1, dmul(mk1, Y));
+        }
         const double dtdp = __dsqrt_rn(dadd(dmul(abc0, abc0), dmul(abc1, abc1)));  // :1349
         const double half = dmul(dtdp, 0.5);
         const double cxd = (double)x, cyd = (double)y, cz = dmul((double)t, TSTOSEC_D);  // :1236-1237
-#pragma unroll 1
-        for (int a = 0; a < N1; a++)
 #pragma unroll
-          for (int b = 0; b < N1; b++) {  // :1352-1369
-            const int cidx = (oa + a) * N + ob + b;
-            const bool hit = myh[cidx * THREADS] != 0;
-            const uint32_t tc = my[cidx * THREADS];
-            const double sx = hit ? (double)(bx0 + a) : 0.0, sy = hit ? (double)(by0 + b) : 0.0;
-            const double Y = tc > t ? dmul(dsub((double)tc, MAXSTAMP_D), TSTOSEC_D) : dmul((double)tc, TSTOSEC_D);
-            const double planedt = dadd(dmul(abc0, dsub(sx, cxd)), dmul(abc1, dsub(sy, cyd)));
-            const double actualdt = dsub(Y, cz);
-            if (fabs(dsub(planedt, actualdt)) < half && Y > 0) inliers++;
-          }
+        for (int k = 0; k < P; k++) {  // :1352-1369
+          const bool hit = (hm >> k) & 1ull;
+          const uint32_t tc = wd[k];
+          const double sx = hit ? (double)(bx0 + k / N1) : 0.0, sy = hit ? (double)(by0 + k % N1) : 0.0;
+          const double Y = tc > t ? dmul(dsub((double)tc, MAXSTAMP_D), TSTOSEC_D) : dmul((double)tc, TSTOSEC_D);
+          const double planedt = dadd(dmul(abc0, dsub(sx, cxd)), dmul(abc1, dsub(sy, cyd)));
+          const double actualdt = dsub(Y, cz);
+          if (fabs(dsub(planedt, actualdt)) < half && Y > 0) inliers++;
+        }
         if (inliers >= fp.min_inl) {  // :934-939
           const double speed = ddiv(1.0, dtdp);  // :1373-1377
           const double angle = atan2(abc0, abc1);
@@ -370,7 +442,6 @@ __global__ void __launch_bounds__(THREADS) k_plane_fit_r(const uint2 *__restrict
         }
       }
     }
-
     valid = !isnan(vx) && !isnan(vy) && vx != 0.0 && vy != 0.0;  // src/vFlow.cpp:315
     double len = 0.0, theta = 0.0, lcx = 0.0, lcy = 0.0;
     if (valid) {
@@ -394,19 +465,13 @@ __global__ void __launch_bounds__(THREADS) k_plane_fit_r(const uint2 *__restrict
   if ((threadIdx.x & 31) == 0 && bal) atomicAdd(valid_count, (unsigned long long)__popc(bal));
 }
 
-template <int R, int THREADS>
+template <int R>
 void launch_fit_r(const uint2 *sae, const int2 *prevp, const uint16_t *ex, const uint16_t *ey, const uint32_t *et,
-                  int i0, int i1, FitParams fp, FitOut fo, unsigned long long *valid_count, cudaStream_t s) {
-  constexpr int N = 4 * R + 1;
-  constexpr size_t smem = (size_t)N * N * THREADS * (sizeof(uint32_t) + 1);
-  auto kern = k_plane_fit_r<R, THREADS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
-  const unsigned grid = (unsigned)((i1 - i0 + THREADS - 1) / THREADS);
-  kern<<<grid, THREADS, smem, s>>>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count);
+                  int i0, int i1, FitParams fp, FitOut fo, unsigned long long *valid_count, uint32_t *recs,
+                  cudaStream_t s) {
+  const size_t n = (size_t)(i1 - i0);
+  k_fit_gather<R><<<(unsigned)((n * 16 + 255) / 256), 256, 0, s>>>(sae, prevp, ex, ey, et, i0, i1, fp.W, fp.H, recs);
+  k_fit_solve<R><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(recs, ex, ey, et, i0, i1, fp, fo, valid_count);
 }
 
 __global__ void k_sae_init(uint2 *sae, size_t npx) {
@@ -459,14 +524,25 @@ void launch_sae_finalize(uint2 *sae, const uint32_t *pix, const int32_t *nextp, 
   if (m > 0) k_sae_finalize<<<nb((size_t)m, 256), 256, 0, s>>>(sae, pix, nextp, m);
 }
 
-void launch_plane_fit(const uint2 *sae, const int2 *prevp, const uint16_t *ex, const uint16_t *ey,
-                      const uint32_t *et, int i0, int i1, FitParams fp, FitOut fo, unsigned long long *valid_count,
-                      cudaStream_t s) {
-  if (i1 <= i0) return;
-  if (fp.r == 1) launch_fit_r<1, 128>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count, s);
-  else if (fp.r == 2) launch_fit_r<2, 128>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count, s);
-  else if (fp.r == 3) launch_fit_r<3, 64>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count, s);
-  else k_plane_fit<<<nb((size_t)(i1 - i0), 128), 128, 0, s>>>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count);
+size_t plane_fit_scratch_bytes(int r, size_t chunk_events) {
+  const size_t words = r == 1 ? FitRec<1>::WORDS : r == 2 ? FitRec<2>::WORDS : r == 3 ? FitRec<3>::WORDS : 0;
+  return words * sizeof(uint32_t) * chunk_events + 64;
+}
+
+// scratch: plane_fit_scratch_bytes(fp.r, i1 - i0) bytes.  Returns the number of kernels launched.
+int launch_plane_fit(const uint2 *sae, const int2 *prevp, const uint16_t *ex, const uint16_t *ey,
+                     const uint32_t *et, int i0, int i1, FitParams fp, FitOut fo, unsigned long long *valid_count,
+                     void *scratch, cudaStream_t s) {
+  if (i1 <= i0) return 0;
+  uint32_t *recs = (uint32_t *)scratch;
+  if (fp.r == 1) launch_fit_r<1>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count, recs, s);
+  else if (fp.r == 2) launch_fit_r<2>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count, recs, s);
+  else if (fp.r == 3) launch_fit_r<3>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count, recs, s);
+  else {
+    k_plane_fit<<<nb((size_t)(i1 - i0), 128), 128, 0, s>>>(sae, prevp, ex, ey, et, i0, i1, fp, fo, valid_count);
+    return 1;
+  }
+  return 2;
 }
 
 void launch_sae_export(const uint2 *sae, size_t npx, uint32_t *last_t, uint8_t *hit, cudaStream_t s) {
