@@ -84,7 +84,7 @@ struct farms_ctx {
   uint16_t *in_x[2] = {nullptr, nullptr}, *in_y[2] = {nullptr, nullptr};
   uint64_t *in_t[2] = {nullptr, nullptr};
   // misc
-  DevBuf sort_temp, scan_temp, cell_start, fit_scratch;
+  DevBuf sort_temp, scan_temp, cell_start, fit_scratch, surf_tmp;
   int *d_err = nullptr;
   unsigned long long *d_counters = nullptr;  // [0] valid events, [1] pool candidates
   unsigned int *d_work = nullptr;
@@ -560,7 +560,7 @@ void farms_destroy(farms_ctx *c) {
   free_owned(c->ws[1]);
   void *ps[] = {c->sae, c->hx, c->hy, c->ht, c->hm, c->hlen, c->hlcx, c->hlcy, c->d_err, c->d_counters, c->d_work,
                 c->d_small, c->in_x[0], c->in_y[0], c->in_t[0], c->in_x[1], c->in_y[1], c->in_t[1], c->sort_temp.p,
-                c->scan_temp.p, c->cell_start.p, c->fit_scratch.p};
+                c->scan_temp.p, c->cell_start.p, c->fit_scratch.p, c->surf_tmp.p};
   for (void *p : ps)
     if (p) cudaFree(p);
   if (c->h_small) cudaFreeHost(c->h_small);
@@ -652,16 +652,11 @@ int farms_slice_surface(farms_ctx *c, const uint16_t *d_x, const uint16_t *d_y, 
   if (n >= (1ull << 32) - 1) return fail(c, FARMS_ERR_ARG, "slice too long");
   CU(cudaSetDevice(c->cfg.device));
   int rc;
-  DevBuf tmp;
-  if ((rc = ensure(c, tmp, c->npx * sizeof(unsigned long long)))) return rc;
-  cudaError_t e = cudaMemsetAsync(tmp.p, 0, c->npx * sizeof(unsigned long long), c->stream);
-  if (e == cudaSuccess) {
-    launch_slice_surface(d_x, d_y, d_t, (size_t)n, t0, c->H, (unsigned long long *)tmp.p, c->stream);
-    launch_unpack_surface((const unsigned long long *)tmp.p, c->npx, d_last_t, d_hit, c->stream);
-    e = cudaStreamSynchronize(c->stream);
-  }
-  cudaFree(tmp.p);
-  if (e != cudaSuccess) return fail(c, FARMS_ERR_CUDA, "farms_slice_surface: %s", cudaGetErrorString(e));
+  if ((rc = ensure(c, c->surf_tmp, c->npx * sizeof(unsigned long long)))) return rc;
+  CU(cudaMemsetAsync(c->surf_tmp.p, 0, c->npx * sizeof(unsigned long long), c->stream));
+  launch_slice_surface(d_x, d_y, d_t, (size_t)n, t0, c->H, (unsigned long long *)c->surf_tmp.p, c->stream);
+  launch_unpack_surface((const unsigned long long *)c->surf_tmp.p, c->npx, d_last_t, d_hit, c->stream);
+  CU(cudaStreamSynchronize(c->stream));
   return FARMS_OK;
 }
 

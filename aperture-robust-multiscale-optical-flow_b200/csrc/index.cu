@@ -74,11 +74,16 @@ __global__ void k_slab_flags(const uint32_t *__restrict__ em, const uint32_t *__
 __global__ void k_slice_surface(const uint16_t *__restrict__ x, const uint16_t *__restrict__ y,
                                 const uint64_t *__restrict__ t, size_t n, uint64_t t0, int H,
                                 unsigned long long *__restrict__ packed) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t tr = (uint32_t)(t[i] - t0);
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  // Walk the slice backwards: blocks are scheduled roughly in order, so the latest events arrive first and
+  // almost every earlier event of the same pixel sees a larger value already and skips its atomic.
+  const size_t i = n - 1 - k;
+  const uint32_t tr = (uint32_t)(t[i] - t0);
+  unsigned long long *cell = &packed[(size_t)x[i] * H + y[i]];
   // later index wins: index in the high word
-  atomicMax(&packed[(size_t)x[i] * H + y[i]], ((unsigned long long)(i + 1) << 32) | tr);
+  const unsigned long long mine = ((unsigned long long)(i + 1) << 32) | tr;
+  if (*(volatile unsigned long long *)cell < mine) atomicMax(cell, mine);
 }
 
 __global__ void k_unpack_surface(const unsigned long long *__restrict__ packed, size_t npx,

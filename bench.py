@@ -238,24 +238,32 @@ def main():
     launches = [0]
     stage = {}
 
+    sect = {"exchange_s": 0.0, "process_s": 0.0, "gather_s": 0.0}
+
     def step_device():
         f.reset()
+        ta = time.perf_counter()
         exchange_state()
+        torch.cuda.synchronize()
+        tb = time.perf_counter()
         f.process_device(dx, dy, dt, columns=E2E_COLUMNS, out=dev_out)
+        tc = time.perf_counter()
+        sect["exchange_s"] += tb - ta
+        sect["process_s"] += tc - tb
         tm = f.timings()
         launches[0] += tm["kernel_launches"] + (3 + rank if dist else 0)
         for k, v in tm.items():
             stage[k] = stage.get(k, 0) + v
+        td = time.perf_counter()
         gather_outputs(dev_out)
+        torch.cuda.synchronize()
+        sect["gather_s"] += time.perf_counter() - td
 
     def step_host():
         f.reset()
         exchange_state()
+        # every rank's results land in pinned host memory of this node: nothing left to gather
         f.process(x, y, t, columns=E2E_COLUMNS, out=host_out)
-        if dist:
-            cols = {k: torch.from_numpy(host_out[k]).to(dev, non_blocking=True)
-                    for k in ("global_r", "global_theta", "local_r", "local_theta")}
-            gather_outputs(cols)
 
     def barrier():
         if dist:
@@ -284,6 +292,8 @@ def main():
         step_device()
     launches[0] = 0
     stage.clear()
+    for k in sect:
+        sect[k] = 0.0
     sampler = ClockSampler(local_rank)
     sampler.start()
     sec = timed(step_device, args.steps)
@@ -360,6 +370,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "stages_ms_per_step": {k: stage_avg[k] for k in ("total_ms", "ingest_ms", "index_ms", "fit_ms", "bin_ms",
                                                               "pool_ms") if k in stage_avg},
+            "rank0_sections_ms_per_step": {k: 1e3 * v / args.steps for k, v in sect.items()},
             "valid_events_per_step": int(stage_avg.get("valid_events", 0)),
             "pool_candidates_per_step": int(stage_avg.get("pool_candidates", 0))}
     print(json.dumps(line))
