@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "farms_b200.h"
+#include "farms_textio.h"
 
 namespace {
 
@@ -126,65 +127,6 @@ int parse_args(int argc, char **argv, Options &o) {
   return 0;
 }
 
-struct Events {
-  std::vector<uint16_t> x, y;
-  std::vector<uint64_t> t;
-  std::vector<int32_t> xi, yi, pol;  // echoes for the output rows
-};
-
-// Parses like `stream >> x >> y >> time_ >> pol` per line (src/vFlow.cpp:173-188): a field that fails to
-// parse leaves that and all later variables at the previous line's values.
-bool read_events(const std::string &path, unsigned long long maxn, Events &ev, std::string &err) {
-  FILE *f = std::fopen(path.c_str(), "rb");
-  if (!f) {
-    err = "Unable to open file " + path;
-    return false;
-  }
-  std::fseek(f, 0, SEEK_END);
-  long sz = std::ftell(f);
-  std::fseek(f, 0, SEEK_SET);
-  std::vector<char> buf((size_t)sz + 1);
-  size_t got = std::fread(buf.data(), 1, (size_t)sz, f);
-  std::fclose(f);
-  buf[got] = 0;
-  long long x = 0, y = 0, p = 0;
-  unsigned long long t = 0;
-  const char *s = buf.data(), *end = buf.data() + got;
-  size_t guess = got / 16 + 16;
-  ev.x.reserve(guess); ev.y.reserve(guess); ev.t.reserve(guess);
-  ev.xi.reserve(guess); ev.yi.reserve(guess); ev.pol.reserve(guess);
-  while (s < end && ev.x.size() < maxn) {
-    const char *eol = (const char *)std::memchr(s, '\n', (size_t)(end - s));
-    if (!eol) eol = end;
-    const char *q = s;
-    long long vals[4];
-    int nf = 0;
-    while (nf < 4) {
-      while (q < eol && (*q == ' ' || *q == '\t' || *q == '\r')) q++;
-      if (q >= eol) break;
-      bool neg = false;
-      if (*q == '-' || *q == '+') { neg = *q == '-'; q++; }
-      if (q >= eol || *q < '0' || *q > '9') break;
-      unsigned long long v = 0;
-      while (q < eol && *q >= '0' && *q <= '9') v = v * 10 + (unsigned long long)(*q++ - '0');
-      vals[nf++] = neg ? -(long long)v : (long long)v;
-    }
-    if (nf > 0) x = vals[0];
-    if (nf > 1) y = vals[1];
-    if (nf > 2) t = (unsigned long long)vals[2];
-    if (nf > 3) p = vals[3];
-    if (x < 0 || x > 65535 || y < 0 || y > 65535) {
-      err = "event " + std::to_string(ev.x.size()) + " has coordinates outside the sensor";
-      return false;
-    }
-    ev.x.push_back((uint16_t)x); ev.y.push_back((uint16_t)y); ev.t.push_back(t);
-    ev.xi.push_back((int32_t)x); ev.yi.push_back((int32_t)y);
-    ev.pol.push_back(p < 0 ? 0 : (int32_t)p);  // src/vFlow.cpp:246-247
-    s = eol + 1;
-  }
-  return true;
-}
-
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -210,17 +152,18 @@ int main(int argc, char **argv) {
 
   const std::string in_path = o.filename + ".txt";
   std::printf("%s\nReading input file \n", in_path.c_str());
-  Events ev;
-  std::string err;
-  if (!read_events(in_path, o.num_events, ev, err)) {
-    std::fprintf(stderr, "error: %s\n", err.c_str());
+  farms_events ev;
+  char errbuf[256] = "";
+  if (farms_text_read(in_path.c_str(), o.num_events, 0, &ev, errbuf, sizeof errbuf) != 0) {
+    std::fprintf(stderr, "error: %s\n", errbuf);
     farms_destroy(ctx);
     return 1;
   }
-  const size_t n = ev.x.size();
+  const size_t n = (size_t)ev.n;
   std::printf("Done reading %zu Events.\n", n);
   if (n == 0) {  // the reference dies in T.at(0) (src/vFlow.cpp:194)
     std::fprintf(stderr, "error: no events in %s\n", in_path.c_str());
+    farms_text_free(&ev);
     farms_destroy(ctx);
     return 1;
   }
@@ -235,10 +178,11 @@ int main(int argc, char **argv) {
   out.vy = vy.data(); out.local_r = lr.data(); out.local_theta = lth.data(); out.scale = scale.data();
 
   const auto a = std::chrono::system_clock::now();
-  rc = farms_process_host(ctx, ev.x.data(), ev.y.data(), ev.t.data(), nullptr, n, &out);
+  rc = farms_process_host(ctx, ev.x, ev.y, ev.t, nullptr, n, &out);
   const auto b = std::chrono::system_clock::now();
   if (rc != FARMS_OK) {
     std::fprintf(stderr, "error: %s\n", farms_last_error(ctx));
+    farms_text_free(&ev);
     farms_destroy(ctx);
     return 1;
   }
@@ -246,20 +190,14 @@ int main(int argc, char **argv) {
   std::printf("\nDone processing!\n\nWriting output file.\n");
 
   const std::string out11 = o.filename + "_FARMSOut_batch.txt", out8 = o.filename + "_FARMSOut_.txt";
-  FILE *f11 = std::fopen(out11.c_str(), "w"), *f8 = std::fopen(out8.c_str(), "w");
-  if (!f11 || !f8) {
-    std::fprintf(stderr, "error: cannot write %s\n", f11 ? out8.c_str() : out11.c_str());
+  if (farms_text_write(out11.c_str(), out8.c_str(), n, ev.xi, ev.yi, t_rel.data(), ev.pol, gr.data(), gth.data(),
+                       vx.data(), vy.data(), lr.data(), lth.data(), scale.data(), 0) != 0) {
+    std::fprintf(stderr, "error: cannot write %s / %s\n", out11.c_str(), out8.c_str());
+    farms_text_free(&ev);
+    farms_destroy(ctx);
     return 1;
   }
-  for (size_t i = 0; i < n; i++) {
-    // ostream << double with default flags == "%g"; T_out is a vector<int> (src/vFlow.cpp:136, 373)
-    std::fprintf(f11, "%d %d %d %d %g %g %g %g %g %g %d\n", ev.xi[i], ev.yi[i], (int32_t)t_rel[i], ev.pol[i], gr[i],
-                 gth[i], vx[i], vy[i], lr[i], lth[i], (int)scale[i]);
-    std::fprintf(f8, "%d %d %d %d %g %g %g %g\n", ev.xi[i], ev.yi[i], (int32_t)t_rel[i], ev.pol[i], gr[i], gth[i],
-                 lr[i], lth[i]);
-  }
-  std::fclose(f11);
-  std::fclose(f8);
+  farms_text_free(&ev);
 
   farms_timings tm;
   farms_get_timings(ctx, &tm);
