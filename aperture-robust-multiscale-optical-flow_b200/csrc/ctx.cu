@@ -24,7 +24,10 @@ namespace {
 constexpr uint64_t DEFAULT_MAX_BATCH = 16ull << 20;
 constexpr uint32_t DEFAULT_SLACK_US = 1000;
 constexpr size_t HALO_CAP = 8ull << 20;       // events carried across a batch boundary at most
-constexpr int FIT_CHUNK = 1 << 18;            // events per SAE snapshot
+#ifndef FARMS_FIT_CHUNK_LOG2
+#define FARMS_FIT_CHUNK_LOG2 17
+#endif
+constexpr int FIT_CHUNK = 1 << FARMS_FIT_CHUNK_LOG2;  // events per SAE snapshot
 constexpr size_t CSR_BUDGET = 96ull << 20;    // max (slab, tile) cells of the pooling index per batch
 
 enum { EV_START, EV_H2D, EV_INGEST, EV_INDEX, EV_FIT, EV_BIN, EV_POOL, EV_END, EV_COUNT };

@@ -279,7 +279,10 @@ constexpr int OT_SHIFT = 5, OT = 1 << OT_SHIFT;  // owner tile edge (pixels)
 constexpr int TK_NSL = 4;      // consecutive slabs pooled per round (more events per round => fewer, fuller waves)
 constexpr int TK_RING = 4 + TK_NSL;  // a 500-us window touches <= 5 slabs, so a round's windows span <= 4 + NSL
 constexpr int TK_PAD = 64;     // the pooling loop reads 4 x 16 records at a time without bounds checks
-constexpr int TK_SEG = 64;     // slabs per work item
+#ifndef FARMS_TK_SEG
+#define FARMS_TK_SEG 64
+#endif
+constexpr int TK_SEG = FARMS_TK_SEG;  // slabs per work item
 constexpr int TK_MAXT = 128;   // targets handled per round and slab
 constexpr int TK_MAXRUN = 24;  // tile-column runs of a region: <= 10 for rows < H plus <= 10 aliased
 constexpr float TK_TIE_TOL = 2e-5f;

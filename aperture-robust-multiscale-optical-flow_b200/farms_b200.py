@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfarms_b200.so")
+LIB_PATH = os.environ.get("FARMS_B200_LIB", os.path.join(_HERE, "libfarms_b200.so"))
 
 OK, ERR_ARG, ERR_RANGE, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4, -5
 FLAG_DEBUG_DET = 1
