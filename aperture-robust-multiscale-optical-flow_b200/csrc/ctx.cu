@@ -45,7 +45,7 @@ struct WorkSet {
   size_t cap = 0;  // capacity in events
   uint16_t *ex = nullptr, *ey = nullptr;
   uint32_t *et = nullptr, *em = nullptr, *keyA = nullptr, *valA = nullptr, *keyB = nullptr, *valB = nullptr,
-           *pixkeep = nullptr, *flags = nullptr, *slab_ids = nullptr;
+           *pixkeep = nullptr, *flags = nullptr, *slab_ids = nullptr, *slab_first = nullptr, *fin = nullptr;
   int2 *prevp = nullptr;
   int32_t *nextp = nullptr;
   double *vx = nullptr, *vy = nullptr, *len = nullptr, *theta = nullptr, *lcx = nullptr, *lcy = nullptr,
@@ -62,6 +62,7 @@ struct farms_ctx {
   int W = 0, H = 0, fs = 0, r = 0, P = 0, min_inl = 0;
   size_t npx = 0;
   int num_sms = 148;
+  int pool_impl = 1;  // 1 = staged-list fast path (k_pool_tile), 2 = bit-table variant (FARMS_POOL_IMPL=bits, A/B runs)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[EV_COUNT]{};
   std::string err;
@@ -149,7 +150,7 @@ int alloc_working(farms_ctx *c, WorkSet &w, size_t cap) {
   int rc = 0;
 #define A(ptr, n) if ((rc = dalloc(c, w, &w.ptr, (n)))) return rc;
   A(ex, cap) A(ey, cap) A(et, cap) A(em, cap) A(keyA, cap) A(valA, cap) A(keyB, cap) A(valB, cap)
-  A(pixkeep, cap) A(flags, cap) A(slab_ids, cap + 1) A(prevp, cap) A(nextp, cap)
+  A(pixkeep, cap) A(flags, cap) A(slab_ids, cap + 1) A(slab_first, cap + 1) A(fin, cap) A(prevp, cap) A(nextp, cap)
   A(vx, cap) A(vy, cap) A(len, cap) A(theta, cap) A(lcx, cap) A(lcy, cap) A(gr, cap) A(gth, cap)
   A(pay, 3 * cap) A(done, cap) A(valid, cap) A(scale, cap) A(bw, cap) A(inl, cap) A(rec, cap)
   if (c->cfg.flags & FARMS_FLAG_DEBUG_DET) { A(det, cap) } else w.det = nullptr;
@@ -295,7 +296,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   if (ncells >= (1ull << 31)) return fail(c, FARMS_ERR_NOMEM, "pooling index too large (%zu cells)", ncells);
   if ((rc = ensure(c, c->cell_start, (ncells + 1) * sizeof(uint32_t)))) return rc;
   CU(cudaMemsetAsync(c->cell_start.p, 0, (ncells + 1) * sizeof(uint32_t), s));
-  launch_cell_keys(w.ex, w.ey, w.em, w.flags, w.len, m, g, (uint32_t)ncells, w.keyA, w.valA, w.slab_ids, s);
+  launch_cell_keys(w.ex, w.ey, w.em, w.flags, w.len, m, g, (uint32_t)ncells, w.keyA, w.valA, w.slab_ids, w.slab_first, s);
   which = radix_sort_pairs(w.keyA, w.valA, w.keyB, w.valB, m, bits_for(ncells + 1), c->sort_temp.p, s, L);
   skeys = which ? w.keyB : w.keyA;
   svals = which ? w.valB : w.valA;
@@ -310,8 +311,9 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaMemsetAsync(w.scale, 0, n, s));
   CU(cudaMemsetAsync(c->d_work, 0, 2 * sizeof(unsigned int), s));
   CU(cudaMemsetAsync(w.done, 0, m, s));
-  const int fast = monotone && !(c->cfg.flags & FARMS_FLAG_GENERIC_POOLING);
-  *L += launch_pooling(w.rec, w.pay, (const uint32_t *)c->cell_start.p, w.slab_ids, w.done, m, (uint32_t)ncells,
+  CU(cudaMemsetAsync(w.fin, 0, n * sizeof(uint32_t), s));
+  const int fast = (monotone && !(c->cfg.flags & FARMS_FLAG_GENERIC_POOLING)) ? c->pool_impl : 0;
+  *L += launch_pooling(w.rec, w.pay, (const uint32_t *)c->cell_start.p, w.slab_ids, w.slab_first, w.fin, w.done, m, (uint32_t)ncells,
                        (int)h, (int)nslabs, g, fast, flow_frac * (double)m / (double)nslabs, w.gr, w.gth, w.scale,
                        c->d_work, c->d_counters + 1, c->num_sms, s);
   CU(cudaEventRecord(c->ev[EV_POOL], s));
@@ -522,6 +524,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (prop.major < 10) return bail(FARMS_ERR_CUDA);  // built for sm_100a only
   c->num_sms = prop.multiProcessorCount;
+  if (const char *e = getenv("FARMS_POOL_IMPL")) c->pool_impl = strcmp(e, "bits") == 0 ? 2 : 1;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);

@@ -91,14 +91,15 @@ void launch_sae_fold(uint2 *sae, size_t npx, const uint32_t *last_t, const uint8
 // ---- pooling.cu ----
 void launch_cell_keys(const uint16_t *ex, const uint16_t *ey, const uint32_t *em, const uint32_t *excl,
                       const double *len, size_t m, PoolGeom g, uint32_t ncells, uint32_t *keys, uint32_t *idx,
-                      uint32_t *slab_ids, cudaStream_t s);
+                      uint32_t *slab_ids, uint32_t *slab_first, cudaStream_t s);
 void launch_build_records(const uint32_t *skeys, const uint32_t *sidx, size_t m, const uint16_t *ex,
                           const uint16_t *ey, const uint32_t *et, const int32_t *nextp, const double *len,
                           const double *lcx, const double *lcy, int monotone, uint4 *rec, double *pay,
                           uint32_t *cell_start, uint32_t ncells, cudaStream_t s);
-// returns the number of kernels launched.  work_counter: two zeroed words; done: m zeroed bytes.
+// returns the number of kernels launched.  work_counter: two zeroed words; done: m zeroed bytes; fin: m - h zeroed words.
 int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_start, const uint32_t *slab_ids,
-                   uint8_t *done, size_t m, uint32_t ncells, int h, int nslabs, PoolGeom g, int fast,
+                   const uint32_t *slab_first, uint32_t *fin, uint8_t *done, size_t m, uint32_t ncells, int h,
+                   int nslabs, PoolGeom g, int fast,
                    double flow_per_slab, double *global_r, double *global_theta, uint8_t *scale,
                    unsigned int *work_counter, unsigned long long *cand_count, int num_sms, cudaStream_t s);
 int pool_tile_smem_bytes();

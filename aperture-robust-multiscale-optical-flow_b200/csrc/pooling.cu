@@ -39,13 +39,16 @@ __global__ void k_cell_keys(const uint16_t *__restrict__ ex, const uint16_t *__r
                             const uint32_t *__restrict__ em, const uint32_t *__restrict__ excl,
                             const double *__restrict__ len, size_t m, PoolGeom g, uint32_t ncells,
                             uint32_t *__restrict__ keys, uint32_t *__restrict__ idx,
-                            uint32_t *__restrict__ slab_ids) {
+                            uint32_t *__restrict__ slab_ids, uint32_t *__restrict__ slab_first) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
   const uint32_t sid = em[j] >> FARMS_SLAB_SHIFT;
   const bool first = j == 0 || (em[j - 1] >> FARMS_SLAB_SHIFT) != sid;
   const uint32_t dense = excl[j] + ((j > 0 && first) ? 1u : 0u);
-  if (first) slab_ids[dense] = sid;
+  if (first) {
+    slab_ids[dense] = sid;
+    slab_first[dense] = (uint32_t)j;
+  }
   const uint32_t tile = (uint32_t)(ex[j] >> g.tile_shift) * (uint32_t)g.nty + (uint32_t)(ey[j] >> g.tile_shift);
   keys[j] = len[j] > 0.0 ? dense * (uint32_t)(g.ntx * g.nty) + tile : ncells;
   idx[j] = (uint32_t)j;
@@ -93,6 +96,8 @@ struct PoolArgs {
   const double *pay;
   const uint32_t *cell_start;
   const uint32_t *slab_ids;
+  const uint32_t *slab_first;  // index of the first event of every dense slab
+  uint32_t *fin;               // per output event: contributor count | scale index << 16 of a fast-path result
   uint8_t *done;       // per index position: 1 once the fast path has pooled that event
   size_t m;            // stride of the pay arrays
   uint32_t ncells;     // cell_start[ncells] = entries in the index (events with flow)
@@ -298,6 +303,7 @@ struct TileSmem {
   int tag[TK_RING];
   int count[TK_RING];
   int overflow[TK_RING];
+  int dlo[TK_NSL], dhi[TK_NSL], ovf[TK_NSL];  // per target slab of the round: staged slabs its windows span
   unsigned int ntg[TK_NSL], tnext, item;
 };
 
@@ -310,7 +316,7 @@ struct Region {  // pixels an owner tile can reach, as physical rectangles
 // (ordered compaction => deterministic summation order).  Aliased events are stored with their LOGICAL
 // window coordinates (x - 1, y + H) so that the pooling loop needs no special case.
 template <class SM, int WARPS, int CAP>
-__device__ void stage_slab(const PoolArgs &A, SM &S, int s, int slot, const Region &R) {
+__device__ void stage_slab(const PoolArgs &A, SM &S, int s, int slot, const Region &R, uint32_t i_round) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ts = A.g.tile_shift, nty = A.g.nty, NT = A.g.ntx * A.g.nty, H = A.g.H;
   const int tx0 = R.rx0 >> ts, tx1 = R.rx1 >> ts, ty0 = R.ry0 >> ts, ty1 = R.ry1 >> ts;
@@ -365,6 +371,8 @@ __device__ void stage_slab(const PoolArgs &A, SM &S, int s, int slot, const Regi
         x -= 1;
         y += H;
       }
+      // superseded at its pixel (or past 500 us) before the first event of the round: dead for every target
+      pass = pass && rec.w > i_round;
       rec.x = (uint32_t)x | ((uint32_t)y << 16);
     }
     const unsigned bal = __ballot_sync(0xffffffffu, pass);
@@ -432,18 +440,14 @@ __device__ __forceinline__ bool finish_event_checked(const PoolArgs &A, int sub,
   const double wx = __shfl_sync(0xffffffffu, myx, srcl, 16), wy = __shfl_sync(0xffffffffu, myy, srcl, 16),
                wn = __shfl_sync(0xffffffffu, myn, srcl, 16);
   bool safe = have && bk >= 0 && !any_rival && best > 1e-30 && best < 1e30;
-  double bvx = 0.0, bvy = 0.0, r2 = 0.0;
-  if (safe) {
-    bvx = wx / wn;
-    bvy = wy / wn;
-    r2 = __dadd_rn(__dmul_rn(bvy, bvy), __dmul_rn(bvx, bvx));
-    // mean vector much shorter than the mean length: the FP32 sums cancelled, let the exact path do it
-    safe = r2 > 1e-4 * best * best;
-  }
+  // mean vector much shorter than the mean length: the FP32 sums cancelled, let the exact path do it
+  const double bl = best * wn;
+  safe = safe && (wx * wx + wy * wy) > 1e-4 * bl * bl;
   if (sub == 0 && safe) {
-    A.global_r[out_index] = __dsqrt_rn(r2);        // src/vFlow.cpp:365
-    A.global_theta[out_index] = atan2(bvy, bvx);   // :366
-    A.scale[out_index] = (uint8_t)(bk * FARMS_WINDOW_JUMP);
+    // k_pool_finish divides by the count and takes sqrt / atan2 (src/vFlow.cpp:365-366)
+    A.global_r[out_index] = wx;
+    A.global_theta[out_index] = wy;
+    A.fin[out_index] = (uint32_t)wn | ((uint32_t)bk << 16);
   }
   return safe;
 }
@@ -512,33 +516,36 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
       if (nraw_all == 0) continue;  // uniform across the CTA
 
       // ---- make sure the slabs of all windows of the round are staged ----
-      int dlo[TK_NSL], dhi[TK_NSL];
-      int s_first = 0x7fffffff, s_last = -1;
-#pragma unroll
-      for (int w = 0; w < TK_NSL; w++) {
-        const int dd = min(d + w, d_end - 1);
+      __syncthreads();  // the previous round is done with S.dlo / S.dhi / S.ovf
+      if (tid < TK_NSL) {
+        const int dd = min(d + tid, d_end - 1);
         const uint32_t t_first = A.slab_ids[dd] << FARMS_SLAB_SHIFT;
         const uint32_t lo_id =
             (t_first >= (uint32_t)(FARMS_KILL_OLD_FLOW_TIME - 1) ? t_first - (FARMS_KILL_OLD_FLOW_TIME - 1) : 0u) >> FARMS_SLAB_SHIFT;
         int l = dd;
         while (l > 0 && dd - l < 4 && A.slab_ids[l - 1] >= lo_id) l--;
-        dlo[w] = l;
-        dhi[w] = dd;
+        S.dlo[tid] = l;
+        S.dhi[tid] = dd;
+      }
+      const uint32_t i_round = A.slab_first[d];
+      __syncthreads();
+      int s_first = 0x7fffffff, s_last = -1;
+#pragma unroll
+      for (int w = 0; w < TK_NSL; w++) {
         if (nraw[w]) {
-          s_first = min(s_first, l);
-          s_last = max(s_last, dd);
+          s_first = min(s_first, S.dlo[w]);
+          s_last = max(s_last, S.dhi[w]);
         }
       }
       for (int s = s_first; s <= s_last; s++) {
         const int slot = s % TK_RING;
-        if (S.tag[slot] != s) stage_slab<SM, WARPS, CAP>(A, S, s, slot, R);  // uniform: tag is read after a barrier
+        if (S.tag[slot] != s) stage_slab<SM, WARPS, CAP>(A, S, s, slot, R, i_round);  // uniform: tag is read after a barrier
         __syncthreads();
       }
-      bool ovf[TK_NSL];
-#pragma unroll
-      for (int w = 0; w < TK_NSL; w++) {
-        ovf[w] = false;
-        for (int s = dlo[w]; s <= dhi[w]; s++) ovf[w] |= S.overflow[s % TK_RING] != 0;
+      if (tid < TK_NSL) {
+        int o = 0;
+        for (int s = S.dlo[tid]; s <= S.dhi[tid]; s++) o |= S.overflow[s % TK_RING];
+        S.ovf[tid] = o;
       }
 
       for (uint32_t t0 = 0; t0 < nmax; t0 += TK_MAXT) {
@@ -554,7 +561,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
             const uint4 r = A.rec[pos];
             const int yi = (int)(r.x >> 16);
             // fast-path conditions: not a halo event, window rows stay below 2H, staging complete
-            const bool ok = (int)r.z >= A.h && min(yi + FARMS_MAX_WINDOW, W - 1) <= 2 * H - 1 && !ovf[w];
+            const bool ok = (int)r.z >= A.h && min(yi + FARMS_MAX_WINDOW, W - 1) <= 2 * H - 1 && !S.ovf[w];
             if (ok) S.tlist[w][atomicAdd(&S.ntg[w], 1u)] = pos;
           }
         __syncthreads();
@@ -587,13 +594,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
           const int xoff = FARMS_MAX_WINDOW - xi;
 #pragma unroll
           for (int q = 0; q < FARMS_NSCALES; q++) S.acc[warp][q][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-          int sl = dlo[0], sh = dhi[0];
-#pragma unroll
-          for (int q = 1; q < TK_NSL; q++)
-            if (w == q) {
-              sl = dlo[q];
-              sh = dhi[q];
-            }
+          const int sl = S.dlo[w], sh = S.dhi[w];
           for (int s = sl; s <= sh; s++) {
             const int slot = s % TK_RING;
             const int n = S.count[slot];
@@ -662,14 +663,569 @@ void launch_tile(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
   kern<<<grid, WARPS * 32, sizeof(SM), s>>>(A, otx, oty, nseg);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fast path, bit-parallel: prefix bitmask tables over the staged records
+// ------------------------------------------------------------------------------------------------
+// A CTA owns a 32x32 owner tile and advances through its time slabs in rounds.  Per round it stages the flow
+// events of the tile's (32+100)^2 region (<= 2048 records: the look-back slabs plus the round's own slabs) and
+// builds three bit tables over the staged POSITIONS:
+//   PX[j]  records whose window column is < j          (prefix-OR over 133 rows)
+//   PY[j]  records whose (logical) window row is < j
+//   AL[q]  records that are contributors of query q in time:  idx <= i_q < end   (prefix-XOR over the
+//          queries sorted by index: a record toggles its bit at the first and past-the-last query it serves)
+// The contributors of query q inside scale k's square are then  (PX[xb]&~PX[xa]) & (PY[yb]&~PY[ya]) & AL[q]
+// -- a few 128-bit loads and LOP3s for 256 records per lane -- and ring k is that mask minus scale k-1's.
+// Ring sums are accumulated in registers (the ring is static per pass) by walking the set bits.
+// Eight lanes serve one query (lane i owns the records with position = i mod 8), four queries per warp.
+// FP32 partial sums, FP64 combination and the same safety margin as k_pool_tile: an event whose scale decision
+// is not clear-cut is left to k_pool_any.
+constexpr int BP_WARPS = 8, BP_THREADS = BP_WARPS * 32;
+constexpr int BP_LW = 8;                    // mask words per lane
+constexpr int BP_CAP = BP_LW * 256;         // staged records per round
+constexpr int BP_PITCH = BP_LW * 8 + 4;     // words per table row (+4: conflict-free 128-bit column access)
+constexpr int BP_ROWQ = BP_PITCH / 4;       // uint4 per row
+constexpr int BP_NROW = OT + 2 * FARMS_MAX_WINDOW + 1;
+constexpr int BP_MAXQ = 64;                 // queries per round
+constexpr int BP_NDMAX = 8;                 // query slabs per round at most
+constexpr int BP_MAXSLAB = 4 + BP_NDMAX;    // + look-back slabs (a 500-us window touches <= 5 slabs)
+constexpr int BP_RUNS_PER_SLAB = 20;        // <= 10 tile columns for rows < H plus <= 10 aliased
+constexpr int BP_MAXRUNS = 256;
+static_assert(BP_MAXSLAB * BP_RUNS_PER_SLAB + 2 * BP_NDMAX <= BP_THREADS, "one thread per run descriptor");
+
+struct BitsSmem {
+  uint32_t px[BP_NROW][BP_PITCH];
+  uint32_t py[BP_NROW][BP_PITCH];
+  uint32_t al[BP_MAXQ + 1][BP_PITCH];
+  // payload by staged position: |flow|cos, |flow|sin (|flow| is recomputed); entry BP_CAP stays (0, 0)
+  float2 pxy[BP_CAP + 2];
+  struct {
+    uint32_t s[BP_MAXRUNS], n[BP_MAXRUNS], b[BP_MAXRUNS];  // start in the index, raw length | aliased << 31, count -> base
+  } run;
+  uint32_t q_pos[BP_MAXQ], q_xy[BP_MAXQ], q_ii[BP_MAXQ];                  // queries as loaded
+  uint32_t s_pos[BP_MAXQ], s_xy[BP_MAXQ], s_ii[BP_MAXQ], s_ok[BP_MAXQ];   // sorted by event index
+  uint32_t qrun_s[2 * BP_NDMAX], qrun_n[2 * BP_NDMAX];
+  uint32_t slab_ub[BP_MAXSLAB], slab_cnt[BP_MAXSLAB];
+  int nd, nq, count, skip;
+  float fest;
+  unsigned int item;
+};
+
+// first dense slab a query of dense slab dd can need (|dt| < 500 us, at most 4 slabs back)
+__device__ __forceinline__ int slab_lookback(const PoolArgs &A, int dd) {
+  const uint32_t t_first = A.slab_ids[dd] << FARMS_SLAB_SHIFT;
+  const uint32_t lo_id =
+      (t_first >= (uint32_t)(FARMS_KILL_OLD_FLOW_TIME - 1) ? t_first - (FARMS_KILL_OLD_FLOW_TIME - 1) : 0u) >> FARMS_SLAB_SHIFT;
+  int l = dd;
+  while (l > 0 && dd - l < 4 && A.slab_ids[l - 1] >= lo_id) l--;
+  return l;
+}
+
+__device__ __forceinline__ uint4 and4(uint4 a, uint4 b) { return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w); }
+__device__ __forceinline__ uint4 andn4(uint4 a, uint4 b) { return make_uint4(a.x & ~b.x, a.y & ~b.y, a.z & ~b.z, a.w & ~b.w); }
+__device__ __forceinline__ uint4 or4(uint4 a, uint4 b) { return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
+__device__ __forceinline__ uint4 xor4(uint4 a, uint4 b) { return make_uint4(a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w); }
+template <bool XOR>
+__device__ __forceinline__ uint4 comb4(uint4 a, uint4 b) { return XOR ? xor4(a, b) : or4(a, b); }
+__device__ __forceinline__ uint4 shfl_up4(uint4 v, int d) {
+  return make_uint4(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d),
+                    __shfl_up_sync(0xffffffffu, v.z, d), __shfl_up_sync(0xffffffffu, v.w, d));
+}
+
+// Inclusive prefix (OR or XOR) down the rows of one uint4 column of a table; one warp, RPL consecutive rows
+// per lane.  Row pitch 17 uint4 => the eight lanes of a quarter-warp hit eight different 16-byte bank groups.
+template <bool XOR, int RPL>
+__device__ __forceinline__ void prefix_column(uint32_t *table, int rows, int col4, int lane) {
+  uint4 v[RPL];
+  uint4 *base = reinterpret_cast<uint4 *>(table) + col4;
+#pragma unroll
+  for (int j = 0; j < RPL; j++) {
+    const int r = lane * RPL + j;
+    v[j] = r < rows ? base[r * BP_ROWQ] : make_uint4(0u, 0u, 0u, 0u);
+    if (j) v[j] = comb4<XOR>(v[j], v[j - 1]);
+  }
+  uint4 tot = v[RPL - 1];
+#pragma unroll
+  for (int dlt = 1; dlt < 32; dlt <<= 1) {
+    const uint4 o = shfl_up4(tot, dlt);
+    if (lane >= dlt) tot = comb4<XOR>(tot, o);
+  }
+  uint4 carry = shfl_up4(tot, 1);
+  if (lane == 0) carry = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int j = 0; j < RPL; j++) {
+    const int r = lane * RPL + j;
+    if (r < rows) base[r * BP_ROWQ] = comb4<XOR>(v[j], carry);
+  }
+}
+
+// word offset inside a table row of staged position r: lane i = r & 7 owns it, as bit (r >> 3) of its LW words
+__device__ __forceinline__ int bit_word(int r) {
+  const int i = r & 7, k = r >> 8;
+  return (((k >> 2) << 3) + i) * 4 + (k & 3);
+}
+
+__global__ void __launch_bounds__(BP_THREADS, 2) k_pool_bits(PoolArgs A, int otx_n, int oty_n, int nseg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BitsSmem &S = *reinterpret_cast<BitsSmem *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = lane >> 3, li = lane & 7;
+  const int W = A.g.W, H = A.g.H, ts = A.g.tile_shift, nty = A.g.nty, NT = A.g.ntx * A.g.nty;
+  const unsigned int nitems = (unsigned int)otx_n * oty_n * nseg;
+  const double *pay_cx = A.pay + A.m, *pay_cy = A.pay + 2 * A.m;
+  unsigned long long ncand = 0;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) S.item = atomicAdd(A.work_counter, 1u);
+    __syncthreads();
+    const unsigned int item = S.item;
+    if (item >= nitems) break;
+    // items are ordered segment-major so that CTAs running together work on the same time span (L2 reuse)
+    const int seg = item / (otx_n * oty_n), ot = item % (otx_n * oty_n);
+    const int TX = ot / oty_n, TY = ot % oty_n;
+    const int X0 = TX << OT_SHIFT, Y0 = TY << OT_SHIFT;
+    Region R;
+    R.rx0 = max(X0 - FARMS_MAX_WINDOW, 0);
+    R.rx1 = min(X0 + OT - 1 + FARMS_MAX_WINDOW, W - 1);                       // src/vFlow.cpp:998
+    R.ry0 = max(Y0 - FARMS_MAX_WINDOW, 0);
+    const int jmax = min(min(Y0 + OT - 1, H - 1) + FARMS_MAX_WINDOW, W - 1);  // :1000 (sic: width - 1)
+    R.ry1 = min(jmax, H - 1);
+    // logical rows j in [H, 2H) alias pixel (i + 1, j - H); rows >= 2H are left to k_pool_any
+    R.ay1 = min(jmax, 2 * H - 1) - H;
+    R.ax0 = R.rx0 + 1;
+    R.ax1 = min(R.rx1 + 1, W - 1);
+    if (R.ax0 > R.ax1) R.ay1 = -1;
+    const int tx0 = R.rx0 >> ts, tx1 = R.rx1 >> ts, ty0 = R.ry0 >> ts, ty1 = R.ry1 >> ts;
+    const int nrun0 = tx1 - tx0 + 1;
+    const int atx0 = R.ax0 >> ts, atx1 = R.ax1 >> ts;
+    const int nrun1 = R.ay1 >= 0 ? atx1 - atx0 + 1 : 0;
+    const int nrun = nrun0 + nrun1;
+    const int aty1 = R.ay1 >= 0 ? (R.ay1 >> ts) : 0;
+    // index tiles (16x16) of the owner tile: 2 columns x 2 rows, clipped
+    const int itx0 = X0 >> 4, itx1 = min((X0 + OT - 1) >> 4, A.g.ntx - 1);
+    const int ity0 = Y0 >> 4, ity1 = min((Y0 + OT - 1) >> 4, nty - 1);
+    const int d_begin = seg * TK_SEG, d_end = min(d_begin + TK_SEG, A.nslabs);
+    float fest = 0.75f;  // staged records / raw records of the covering index tiles, refined every round
+
+    int d = d_begin;
+    while (d < d_end) {
+      // ---- A: run descriptors of the candidate slabs, query runs, clear the tables ----
+      const int s_lo = slab_lookback(A, d);
+      const int lb = d - s_lo;
+      const int ncs = min(BP_NDMAX, d_end - d);
+      const int nsl = lb + ncs;
+      __syncthreads();  // the previous round is done with shared memory
+      if (tid < nsl * nrun) {
+        const int sl = tid / nrun, c = tid - sl * nrun;
+        uint32_t a, b;
+        if (c < nrun0) {
+          const size_t cb = (size_t)(s_lo + sl) * NT + (size_t)(tx0 + c) * nty;
+          a = A.cell_start[cb + ty0];
+          b = A.cell_start[cb + ty1 + 1];
+        } else {
+          const size_t cb = (size_t)(s_lo + sl) * NT + (size_t)(atx0 + c - nrun0) * nty;
+          a = A.cell_start[cb];
+          b = A.cell_start[cb + aty1 + 1];
+        }
+        S.run.s[tid] = a;
+        S.run.n[tid] = (b - a) | (c >= nrun0 ? 0x80000000u : 0u);
+      }
+      if (tid >= BP_THREADS - 2 * BP_NDMAX) {
+        const int q = tid - (BP_THREADS - 2 * BP_NDMAX), w = q >> 1, c = q & 1;
+        uint32_t a = 0, b = 0;
+        if (w < ncs && itx0 + c <= itx1) {
+          const size_t cb = (size_t)(d + w) * NT + (size_t)(itx0 + c) * nty;
+          a = A.cell_start[cb + ity0];
+          b = A.cell_start[cb + ity1 + 1];
+        }
+        S.qrun_s[q] = a;
+        S.qrun_n[q] = b - a;
+      }
+      {
+        uint4 *z = reinterpret_cast<uint4 *>(&S.px[0][0]);
+        constexpr int NZ = (2 * BP_NROW + BP_MAXQ + 1) * BP_ROWQ;
+        for (int q = tid; q < NZ; q += BP_THREADS) z[q] = make_uint4(0u, 0u, 0u, 0u);
+        if (tid < 2) S.pxy[BP_CAP + tid] = make_float2(0.f, 0.f);
+      }
+      __syncthreads();
+      // ---- A2 (warp 0): skip slabs without queries; candidate slab count from the raw-size estimate ----
+      if (warp == 0) {
+        if (lane < nsl) {
+          uint32_t ub = 0;
+          for (int c = 0; c < nrun; c++) ub += S.run.n[lane * nrun + c] & 0x7fffffffu;
+          S.slab_ub[lane] = ub;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          int w0 = 0;
+          while (w0 < ncs && S.qrun_n[2 * w0] + S.qrun_n[2 * w0 + 1] == 0) w0++;
+          if (w0 > 0) {  // nothing to pool in the first w0 slabs
+            S.nd = w0;
+            S.skip = 1;
+          } else {
+            uint32_t ubsum = 0, qsum = 0;
+            for (int sl = 0; sl < lb; sl++) ubsum += S.slab_ub[sl];
+            int ndc = 0;
+            for (int w = 0; w < ncs; w++) {
+              ubsum += S.slab_ub[lb + w];
+              qsum += S.qrun_n[2 * w] + S.qrun_n[2 * w + 1];
+              if (w > 0 && (qsum > (uint32_t)BP_MAXQ || fest * (float)ubsum > 1.04f * (float)BP_CAP)) break;
+              ndc = w + 1;
+            }
+            S.nd = ndc;
+            S.skip = 0;
+          }
+        }
+      }
+      __syncthreads();
+      if (S.skip) {  // uniform
+        d += S.nd;
+        continue;
+      }
+      const int ndc = S.nd;
+      const int nruns_c = (lb + ndc) * nrun;
+      // ---- B: exact number of region records per run ----
+      // a record whose successor at its pixel (or whose 500-us expiry) precedes the round is dead for every query
+      const uint32_t i_round = A.slab_first[d];
+      for (int run = warp; run < nruns_c; run += BP_WARPS) {
+        const uint32_t s0 = S.run.s[run], nn = S.run.n[run];
+        const uint32_t n = nn & 0x7fffffffu;
+        const bool alias = (nn >> 31) != 0u;
+        uint32_t cnt = 0;
+        for (uint32_t o = 0; o < n; o += 32) {
+          bool pass = false;
+          if (o + lane < n) {
+            const uint4 rec = A.rec[s0 + o + lane];
+            const int x = (int)(rec.x & 0xffffu), y = (int)(rec.x >> 16);
+            pass = !alias ? (x >= R.rx0 && x <= R.rx1 && y >= R.ry0 && y <= R.ry1)
+                          : (x >= R.ax0 && x <= R.ax1 && y <= R.ay1);
+            pass = pass && rec.w > i_round;
+          }
+          cnt += __popc(__ballot_sync(0xffffffffu, pass));
+        }
+        if (lane == 0) S.run.b[run] = cnt;
+      }
+      __syncthreads();
+      // ---- B2 (warp 0): slabs that fit, positions of the runs ----
+      if (warp == 0) {
+        if (lane < lb + ndc) {
+          uint32_t c = 0;
+          for (int q = 0; q < nrun; q++) c += S.run.b[lane * nrun + q];
+          S.slab_cnt[lane] = c;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          uint32_t tot = 0, ub = 0, q = 0;
+          for (int sl = 0; sl < lb; sl++) {
+            tot += S.slab_cnt[sl];
+            ub += S.slab_ub[sl];
+          }
+          int nd = 0;
+          for (int w = 0; w < ndc; w++) {
+            const uint32_t t2 = tot + S.slab_cnt[lb + w], q2 = q + S.qrun_n[2 * w] + S.qrun_n[2 * w + 1];
+            if (w > 0 && (t2 > (uint32_t)BP_CAP || q2 > (uint32_t)BP_MAXQ)) break;
+            tot = t2;
+            q = q2;
+            ub += S.slab_ub[lb + w];
+            nd = w + 1;
+          }
+          S.nd = nd;
+          S.nq = (int)min(q, (uint32_t)BP_MAXQ);  // a slab with more queries than that leaves the rest to k_pool_any
+          S.count = (int)tot;
+          S.skip = tot > (uint32_t)BP_CAP;        // even one slab does not fit: k_pool_any pools it
+          S.fest = ub ? fminf(1.0f, (float)tot / (float)ub) : 0.75f;
+        }
+        __syncwarp();
+        // exclusive prefix of the run counts over the runs in use
+        const int nru = (lb + S.nd) * nrun;
+        uint32_t loc[BP_MAXRUNS / 32];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < BP_MAXRUNS / 32; j++) {
+          const int run = lane * (BP_MAXRUNS / 32) + j;
+          loc[j] = run < nru ? S.run.b[run] : 0u;
+          sum += loc[j];
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xffffffffu, inc, dlt);
+          if (lane >= dlt) inc += o;
+        }
+        uint32_t pos0 = inc - sum;
+#pragma unroll
+        for (int j = 0; j < BP_MAXRUNS / 32; j++) {
+          const int run = lane * (BP_MAXRUNS / 32) + j;
+          if (run < nru) S.run.b[run] = pos0;
+          pos0 += loc[j];
+        }
+      }
+      __syncthreads();
+      const int nd = S.nd, nq = S.nq, count = S.count;
+      fest = S.fest;
+      if (S.skip || nq == 0) {  // uniform
+        d += nd;
+        continue;
+      }
+      // ---- C: the round's queries = flow events of the owner tile in slabs d .. d+nd-1 ----
+      if (tid < nq) {
+        uint32_t f = (uint32_t)tid, pos = 0;
+        for (int q = 0; q < 2 * nd; q++) {
+          const uint32_t n = S.qrun_n[q];
+          if (f < n) {
+            pos = S.qrun_s[q] + f;
+            break;
+          }
+          f -= n;
+        }
+        const uint4 r = A.rec[pos];
+        S.q_pos[tid] = pos;
+        S.q_xy[tid] = r.x;
+        S.q_ii[tid] = r.z;
+      }
+      __syncthreads();
+      if (tid < nq) {
+        const uint32_t my = S.q_ii[tid];
+        int rank = 0;
+        for (int g = 0; g < nq; g++) rank += S.q_ii[g] < my ? 1 : 0;
+        const uint32_t xy = S.q_xy[tid];
+        const int yi = (int)(xy >> 16);
+        // fast-path conditions: not a halo event, window rows stay below 2H, the event's own row is inside the
+        // reference's width-1 row bound (always when W >= H)
+        const bool ok = (int)my >= A.h && min(yi + FARMS_MAX_WINDOW, W - 1) <= 2 * H - 1 && yi <= W - 1;
+        S.s_pos[rank] = S.q_pos[tid];
+        S.s_xy[rank] = xy;
+        S.s_ii[rank] = my;
+        S.s_ok[rank] = ok ? 1u : 0u;
+      }
+      __syncthreads();
+      // ---- D: stage the region records in run order (deterministic positions) and set their table bits ----
+      {
+        const int nru = (lb + nd) * nrun;
+        const uint32_t ii_first = S.s_ii[0], ii_last = S.s_ii[nq - 1];
+        for (int run = warp; run < nru; run += BP_WARPS) {
+          const uint32_t s0 = S.run.s[run], nn = S.run.n[run];
+          const uint32_t n = nn & 0x7fffffffu;
+          const bool alias = (nn >> 31) != 0u;
+          uint32_t base = S.run.b[run];
+          for (uint32_t o = 0; o < n; o += 32) {
+            bool pass = false;
+            uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t pos = s0 + o + lane;
+            int x = 0, y = 0;
+            if (o + lane < n) {
+              rec = A.rec[pos];
+              x = (int)(rec.x & 0xffffu);
+              y = (int)(rec.x >> 16);
+              if (!alias) {
+                pass = x >= R.rx0 && x <= R.rx1 && y >= R.ry0 && y <= R.ry1;
+              } else {
+                pass = x >= R.ax0 && x <= R.ax1 && y <= R.ay1;
+                x -= 1;   // logical window coordinates of the aliased cell
+                y += H;
+              }
+              pass = pass && rec.w > i_round;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            if (pass) {
+              const int r = (int)(base + __popc(bal & ((1u << lane) - 1u)));
+              S.pxy[r] = make_float2(__double2float_rn(pay_cx[pos]), __double2float_rn(pay_cy[pos]));
+              const int wo = bit_word(r);
+              const uint32_t bit = 1u << ((r >> 3) & 31);
+              atomicOr(&S.px[x - R.rx0 + 1][wo], bit);
+              atomicOr(&S.py[y - R.ry0 + 1][wo], bit);
+              // contributor of query q  <=>  idx <= i_q < end  <=>  qa <= q < qb  in index order
+              const uint32_t idx = rec.z, end = rec.w;
+              int qa = 0, qb = nq;
+              if (idx > ii_first) {  // first query with i_q >= idx
+                int lo = 0, hi = nq;
+                while (lo < hi) {
+                  const int mid = (lo + hi) >> 1;
+                  if (S.s_ii[mid] >= idx) hi = mid; else lo = mid + 1;
+                }
+                qa = lo;
+              }
+              if (end <= ii_last) {  // first query with i_q >= end
+                int lo = 0, hi = nq;
+                while (lo < hi) {
+                  const int mid = (lo + hi) >> 1;
+                  if (S.s_ii[mid] >= end) hi = mid; else lo = mid + 1;
+                }
+                qb = lo;
+              }
+              if (qa < qb) {
+                atomicXor(&S.al[qa][wo], bit);
+                atomicXor(&S.al[qb][wo], bit);
+              }
+            }
+            base += __popc(bal);
+          }
+        }
+      }
+      __syncthreads();
+      // ---- E: prefix passes over the uint4 columns in use ----
+      {
+        const int k4n = (count + 1023) >> 10;  // groups of 4 mask words in use (1024 positions each)
+        const int ncol = k4n * 8;
+        for (int task = warp; task < 3 * ncol; task += BP_WARPS) {
+          const int tab = task / ncol, col = task - tab * ncol;
+          if (tab == 0) prefix_column<false, (BP_NROW + 31) / 32>(&S.px[0][0], BP_NROW, col, lane);
+          else if (tab == 1) prefix_column<false, (BP_NROW + 31) / 32>(&S.py[0][0], BP_NROW, col, lane);
+          else prefix_column<true, (BP_MAXQ + 1 + 31) / 32>(&S.al[0][0], nq + 1, col, lane);
+        }
+      }
+      __syncthreads();
+      // ---- F: four queries per warp, eight lanes each ----
+      for (int task = warp; task * 4 < nq; task += BP_WARPS) {
+        const int q = task * 4 + grp;
+        const int qc = min(q, nq - 1);
+        const bool act = q < nq && S.s_ok[qc] != 0u;
+        const uint32_t xy = S.s_xy[qc];
+        // lanes without a query walk the tables from the tile corner with an empty mask
+        const int xi = act ? (int)(xy & 0xffffu) : X0, yi = act ? (int)(xy >> 16) : Y0;
+        uint4 T4[BP_LW / 4], P4[BP_LW / 4];
+#pragma unroll
+        for (int k4 = 0; k4 < BP_LW / 4; k4++) {
+          T4[k4] = reinterpret_cast<const uint4 *>(&S.al[qc][0])[k4 * 8 + li];
+          if (!act) T4[k4] = make_uint4(0u, 0u, 0u, 0u);
+          P4[k4] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        double Sl = 0.0, Sx = 0.0, Sy = 0.0;
+        int Sn = 0;
+        float best = 0.f, mean[FARMS_NSCALES];
+        int ncum[FARMS_NSCALES];
+        int bk = -1, bn = 0;
+        double bx = 0.0, by = 0.0;
+        // byte address of this lane's payload column; the dummy entry BP_CAP holds (0, 0)
+        const char *pay0 = reinterpret_cast<const char *>(&S.pxy[li]);
+        const char *payz = reinterpret_cast<const char *>(&S.pxy[BP_CAP]);
+#pragma unroll
+        for (int k = 0; k < FARMS_NSCALES; k++) {
+          const int s = k * FARMS_WINDOW_JUMP;
+          const int xa = max(xi - s, 0) - R.rx0, xb = min(xi + s, W - 1) - R.rx0 + 1;   // src/vFlow.cpp:998
+          const int ya = max(yi - s, 0) - R.ry0, yb = max(min(yi + s, W - 1) - R.ry0 + 1, 0);   // :1000 (sic)
+          const uint4 *rxa = reinterpret_cast<const uint4 *>(&S.px[xa][0]) + li;
+          const uint4 *rxb = reinterpret_cast<const uint4 *>(&S.px[xb][0]) + li;
+          const uint4 *rya = reinterpret_cast<const uint4 *>(&S.py[ya][0]) + li;
+          const uint4 *ryb = reinterpret_cast<const uint4 *>(&S.py[yb][0]) + li;
+          float sl = 0.f, sx = 0.f, sy = 0.f;
+          int cn = 0;
+#pragma unroll
+          for (int k4 = 0; k4 < BP_LW / 4; k4++) {
+            const uint4 sq = and4(andn4(rxb[k4 * 8], rxa[k4 * 8]), andn4(ryb[k4 * 8], rya[k4 * 8]));
+            const uint4 m4 = and4(andn4(sq, P4[k4]), T4[k4]);
+            P4[k4] = sq;
+            const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              uint32_t mm = mw[j];
+              cn += __popc(mm);
+              // staged position of bit b of this word: ((k4*4+j)*32 + b)*8 + li; 8 bytes of payload each
+              const char *wbase = pay0 + (k4 * 4 + j) * 256 * 8;
+              while (mm) {  // two contributors per trip (independent loads); a missing second one reads (0, 0)
+                const float2 c0 = *reinterpret_cast<const float2 *>(wbase + ((__ffs(mm) - 1) << 6));
+                mm &= mm - 1;
+                const float2 c1 = *reinterpret_cast<const float2 *>(mm ? wbase + ((__ffs(mm) - 1) << 6) : payz);
+                mm &= mm - 1;
+                float l0, l1;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(c0.x * c0.x + c0.y * c0.y));
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(c1.x * c1.x + c1.y * c1.y));
+                sl += l0;
+                sx += c0.x;
+                sy += c0.y;
+                sl += l1;
+                sx += c1.x;
+                sy += c1.y;
+              }
+            }
+          }
+          // ring totals over the eight lanes, in FP64
+          double dl = (double)sl, dx = (double)sx, dy = (double)sy;
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            dl += __shfl_xor_sync(0xffffffffu, dl, o);
+            dx += __shfl_xor_sync(0xffffffffu, dx, o);
+            dy += __shfl_xor_sync(0xffffffffu, dy, o);
+            cn += __shfl_xor_sync(0xffffffffu, cn, o);
+          }
+          // nested-square sums are prefix sums over rings (src/vFlow.cpp:1023-1036); an empty ring adds exactly 0
+          Sl += dl;
+          Sx += dx;
+          Sy += dy;
+          Sn += cn;
+          const float mk = Sn > 0 ? __fdiv_rn((float)Sl, (float)Sn) : 0.f;
+          mean[k] = mk;
+          ncum[k] = Sn;
+          if (mk > best) {  // strict '>' from 0: first maximum (:1047-1059)
+            best = mk;
+            bk = k;
+            bn = Sn;
+            bx = Sx;
+            by = Sy;
+          }
+        }
+        // is any other scale (with a different contributor set) within the FP32 noise of the winner?
+        bool rival = false;
+#pragma unroll
+        for (int k = 0; k < FARMS_NSCALES; k++) rival |= ncum[k] != bn && fabsf(mean[k] - best) <= TK_TIE_TOL * best;
+        bool safe = act && bk >= 0 && !rival && best > 1e-30f && best < 1e30f;
+        // mean vector much shorter than the mean length: the FP32 sums cancelled, let the exact path do it
+        const double bl = (double)best * (double)bn;
+        safe = safe && (bx * bx + by * by) > 1e-4 * bl * bl;
+        if (li == 0 && act) ncand += (unsigned long long)Sn;
+        if (li == 0 && safe) {
+          // k_pool_finish divides by the count and takes sqrt / atan2 (src/vFlow.cpp:365-366)
+          const int out_index = (int)S.s_ii[qc] - A.h;
+          A.global_r[out_index] = bx;
+          A.global_theta[out_index] = by;
+          A.fin[out_index] = (uint32_t)bn | ((uint32_t)bk << 16);
+          A.done[S.s_pos[qc]] = 1;
+        }
+      }
+      d += nd;
+    }
+  }
+  if (ncand) atomicAdd(A.cand_count, ncand);
+}
+
+// Second half of the fast path's output: mean vector = sums / count, then length and angle (src/vFlow.cpp:365-366).
+__global__ void k_pool_finish(const uint32_t *__restrict__ fin, size_t n, double *__restrict__ gr,
+                              double *__restrict__ gth, uint8_t *__restrict__ scale) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const uint32_t v = fin[e];
+  if (!v) return;
+  const double wn = (double)(v & 0xffffu);
+  const double bvx = gr[e] / wn, bvy = gth[e] / wn;
+  gr[e] = __dsqrt_rn(__dadd_rn(__dmul_rn(bvy, bvy), __dmul_rn(bvx, bvx)));
+  gth[e] = atan2(bvy, bvx);
+  scale[e] = (uint8_t)((v >> 16) * FARMS_WINDOW_JUMP);
+}
+
+void launch_bits(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
+  PoolArgs A = A0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_pool_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BitsSmem));
+    cudaFuncSetAttribute(k_pool_bits, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    attr_set = true;
+  }
+  const int otx = (A.g.W + OT - 1) >> OT_SHIFT, oty = (A.g.H + OT - 1) >> OT_SHIFT;
+  const int nseg = (nslabs + TK_SEG - 1) / TK_SEG;
+  const long long items = (long long)otx * oty * nseg;
+  unsigned grid = (unsigned)std::min<long long>(items, 2ll * num_sms);
+  k_pool_bits<<<grid, BP_THREADS, sizeof(BitsSmem), s>>>(A, otx, oty, nseg);
+}
+
 inline unsigned nb(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
 
 void launch_cell_keys(const uint16_t *ex, const uint16_t *ey, const uint32_t *em, const uint32_t *excl,
                       const double *len, size_t m, PoolGeom g, uint32_t ncells, uint32_t *keys, uint32_t *idx,
-                      uint32_t *slab_ids, cudaStream_t s) {
-  if (m) k_cell_keys<<<nb(m, 256), 256, 0, s>>>(ex, ey, em, excl, len, m, g, ncells, keys, idx, slab_ids);
+                      uint32_t *slab_ids, uint32_t *slab_first, cudaStream_t s) {
+  if (m) k_cell_keys<<<nb(m, 256), 256, 0, s>>>(ex, ey, em, excl, len, m, g, ncells, keys, idx, slab_ids, slab_first);
 }
 
 void launch_build_records(const uint32_t *skeys, const uint32_t *sidx, size_t m, const uint16_t *ex,
@@ -680,12 +1236,13 @@ void launch_build_records(const uint32_t *skeys, const uint32_t *sidx, size_t m,
                                                    pay, cell_start, ncells);
 }
 
-int pool_tile_smem_bytes() { return (int)sizeof(TileSmem<16, 640>); }
+int pool_tile_smem_bytes() { return (int)sizeof(BitsSmem); }
 
 // Launches the fast path (when `fast` is set) and then the general, exact path for whatever is left.
 // work_counter: two zeroed words.  done: m zeroed bytes.
 int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_start, const uint32_t *slab_ids,
-                   uint8_t *done, size_t m, uint32_t ncells, int h, int nslabs, PoolGeom g, int fast,
+                   const uint32_t *slab_first, uint32_t *fin, uint8_t *done, size_t m, uint32_t ncells, int h,
+                   int nslabs, PoolGeom g, int fast,
                    double flow_per_slab, double *global_r, double *global_theta, uint8_t *scale,
                    unsigned int *work_counter, unsigned long long *cand_count, int num_sms, cudaStream_t s) {
   if (!m) return 0;
@@ -693,13 +1250,18 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
   int launches = 0;
   PoolArgs A;
   A.rec = rec; A.pay = pay; A.cell_start = cell_start; A.slab_ids = slab_ids; A.done = done;
+  A.slab_first = slab_first; A.fin = fin;
   A.m = m; A.ncells = ncells; A.h = h; A.nslabs = nslabs; A.g = g;
   A.global_r = global_r; A.global_theta = global_theta; A.scale = scale;
   A.cand_count = cand_count;
   if (fast && g.tile_shift == 4) {
     A.work_counter = work_counter;
-    launch_tile<16, 640>(A, nslabs, num_sms, s);  // 16 warps, 1 CTA per SM, ~224 KB of shared memory
-    launches++;
+    if (fast == 2) launch_bits(A, nslabs, num_sms, s);  // bit-table variant: 8 warps, 2 CTAs per SM, ~110 KB each
+    else launch_tile<16, 640>(A, nslabs, num_sms, s);   // 16 warps, 1 CTA per SM, ~224 KB of shared memory
+    const size_t nout = m - (size_t)h;
+    // the fast kernels leave sums and counts; this pass turns them into globalR / globalTheta / scale
+    if (nout) k_pool_finish<<<nb(nout, 256), 256, 0, s>>>(fin, nout, global_r, global_theta, scale);
+    launches += 2;
   }
   A.work_counter = work_counter + 1;
   // persistent warps pulling 32-slot groups from a global counter: grid = SMs x resident CTAs

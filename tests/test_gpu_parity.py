@@ -97,3 +97,24 @@ def test_unsorted_timestamps():
     rep = compare(f.process(x, y, t2), ref, "cfg1 unsorted timestamps")
     print(json.dumps(rep))
     assert_parity(rep)
+
+
+@pytest.mark.parametrize("config,n,start", [(4, 3_000_000, 2000), (3, 1_500_000, 0), (2, 400_000, 0)])
+def test_fast_pooling_equals_exact_pooling_on_long_dense_streams(config, n, start):
+    """Size-independent property at densities the oracle cannot reach in seconds: the bit-table fast path
+    (FP32 partial sums, declines unclear decisions) must pick the same scale as the exact FP64 kernel for every
+    event and agree on globalR / globalTheta within the north_star tolerances."""
+    import farms_b200
+    s, x, y, t, p = synth_stream(config, n, start)
+    fast = farms_b200.Farms(s.width, s.height, s.filtersize, 5).process(x, y, t)
+    exact = farms_b200.Farms(s.width, s.height, s.filtersize, 5, flags=farms_b200.FLAG_EXACT_POOLING).process(x, y, t)
+    for k in ("valid", "best_window", "inliers", "t_rel", "vx", "vy", "local_r", "local_theta"):
+        assert np.array_equal(fast[k], exact[k], equal_nan=k in ("vx", "vy")), k
+    assert np.array_equal(fast["scale"], exact["scale"])
+    v = exact["valid"].astype(bool)
+    assert v.sum() > n // 10
+    gr, ge = fast["global_r"][v], exact["global_r"][v]
+    assert np.all(np.abs(gr - ge) <= 1e-4 * np.abs(ge))
+    from helpers import angle_diff
+    assert np.all(angle_diff(fast["global_theta"][v], exact["global_theta"][v]) <= 1e-3)
+    assert np.array_equal(fast["global_r"][~v], exact["global_r"][~v])
