@@ -524,7 +524,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (prop.major < 10) return bail(FARMS_ERR_CUDA);  // built for sm_100a only
   c->num_sms = prop.multiProcessorCount;
-  if (const char *e = getenv("FARMS_POOL_IMPL")) c->pool_impl = strcmp(e, "bits") == 0 ? 2 : 1;
+  if (const char *e = getenv("FARMS_POOL_IMPL")) c->pool_impl = strcmp(e, "bits") == 0 ? 2 : strcmp(e, "tile1") == 0 ? 3 : 1;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);

@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
 // everything else (measured: well under 1 % of events) is left to k_pool_any, which is exact.  Scales whose
 // extra rings are empty have bit-identical sums in both arithmetics, so exact ties behave like the reference.
 constexpr int OT_SHIFT = 5, OT = 1 << OT_SHIFT;  // owner tile edge (pixels)
-constexpr int TK_NSL = 4;      // consecutive slabs pooled per round (more events per round => fewer, fuller waves)
-constexpr int TK_RING = 4 + TK_NSL;  // a 500-us window touches <= 5 slabs, so a round's windows span <= 4 + NSL
+// NSL (template parameter): consecutive slabs pooled per round (more events per round => fewer, fuller waves).
+// A 500-us window touches <= 5 slabs, so a round's windows span <= 4 + NSL staged slabs (the slot ring).
 constexpr int TK_PAD = 64;     // the pooling loop reads 4 x 16 records at a time without bounds checks
 #ifndef FARMS_TK_SEG
 #define FARMS_TK_SEG 64
@@ -292,19 +292,19 @@ constexpr int TK_MAXT = 128;   // targets handled per round and slab
 constexpr int TK_MAXRUN = 24;  // tile-column runs of a region: <= 10 for rows < H plus <= 10 aliased
 constexpr float TK_TIE_TOL = 2e-5f;
 
-template <int WARPS, int CAP>
+template <int WARPS, int CAP, int NSL>
 struct TileSmem {
-  uint4 ra[TK_RING][CAP + TK_PAD];        // {x | y<<16 (logical window coordinates), idx, end - idx, len as f32}
-  float2 rb[TK_RING][CAP];                // lcx, lcy
+  uint4 ra[(4 + NSL)][CAP + TK_PAD];        // {x | y<<16 (logical window coordinates), idx, end - idx, len as f32}
+  float2 rb[(4 + NSL)][CAP];                // lcx, lcy
   float4 acc[WARPS][FARMS_NSCALES][32];   // per-lane ring partials: len, lcx, lcy, count
-  uint32_t tlist[TK_NSL][TK_MAXT];
+  uint32_t tlist[NSL][TK_MAXT];
   uint32_t run_s[TK_MAXRUN], run_o[TK_MAXRUN + 1];
   uint32_t wcount[WARPS];
-  int tag[TK_RING];
-  int count[TK_RING];
-  int overflow[TK_RING];
-  int dlo[TK_NSL], dhi[TK_NSL], ovf[TK_NSL];  // per target slab of the round: staged slabs its windows span
-  unsigned int ntg[TK_NSL], tnext, item;
+  int tag[(4 + NSL)];
+  int count[(4 + NSL)];
+  int overflow[(4 + NSL)];
+  int dlo[NSL], dhi[NSL], ovf[NSL];  // per target slab of the round: staged slabs its windows span
+  unsigned int ntg[NSL], tnext, item;
 };
 
 struct Region {  // pixels an owner tile can reach, as physical rectangles
@@ -452,9 +452,9 @@ __device__ __forceinline__ bool finish_event_checked(const PoolArgs &A, int sub,
   return safe;
 }
 
-template <int WARPS, int CAP>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx_n, int oty_n, int nseg) {
-  using SM = TileSmem<WARPS, CAP>;
+template <int WARPS, int CAP, int NSL, int CTAS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int otx_n, int oty_n, int nseg) {
+  using SM = TileSmem<WARPS, CAP, NSL>;
   constexpr int THREADS = WARPS * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM &S = *reinterpret_cast<SM *>(smem_raw);
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
   for (;;) {
     __syncthreads();
     if (tid == 0) S.item = atomicAdd(A.work_counter, 1u);
-    if (tid < TK_RING) S.tag[tid] = -1;
+    if (tid < (4 + NSL)) S.tag[tid] = -1;
     __syncthreads();
     const unsigned int item = S.item;
     if (item >= nitems) break;
@@ -491,14 +491,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
     const int ity0 = Y0 >> 4, ity1 = min((Y0 + OT - 1) >> 4, nty - 1);
     const int d_begin = seg * TK_SEG, d_end = min(d_begin + TK_SEG, A.nslabs);
 
-    // TK_NSL consecutive slabs per round
-    for (int d = d_begin; d < d_end; d += TK_NSL) {
-      const int nd = min(TK_NSL, d_end - d);
+    // NSL consecutive slabs per round
+    for (int d = d_begin; d < d_end; d += NSL) {
+      const int nd = min(NSL, d_end - d);
       // ---- targets of this round: flow events of the owner tile in slabs d .. d+nd-1 ----
-      uint32_t ta[TK_NSL][2], tb[TK_NSL][2], nraw[TK_NSL];
+      uint32_t ta[NSL][2], tb[NSL][2], nraw[NSL];
       uint32_t nraw_all = 0, nmax = 0;
 #pragma unroll
-      for (int w = 0; w < TK_NSL; w++) {
+      for (int w = 0; w < NSL; w++) {
         nraw[w] = 0;
 #pragma unroll
         for (int c = 0; c < 2; c++) {
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
 
       // ---- make sure the slabs of all windows of the round are staged ----
       __syncthreads();  // the previous round is done with S.dlo / S.dhi / S.ovf
-      if (tid < TK_NSL) {
+      if (tid < NSL) {
         const int dd = min(d + tid, d_end - 1);
         const uint32_t t_first = A.slab_ids[dd] << FARMS_SLAB_SHIFT;
         const uint32_t lo_id =
@@ -531,30 +531,30 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
       __syncthreads();
       int s_first = 0x7fffffff, s_last = -1;
 #pragma unroll
-      for (int w = 0; w < TK_NSL; w++) {
+      for (int w = 0; w < NSL; w++) {
         if (nraw[w]) {
           s_first = min(s_first, S.dlo[w]);
           s_last = max(s_last, S.dhi[w]);
         }
       }
       for (int s = s_first; s <= s_last; s++) {
-        const int slot = s % TK_RING;
+        const int slot = s % (4 + NSL);
         if (S.tag[slot] != s) stage_slab<SM, WARPS, CAP>(A, S, s, slot, R, i_round);  // uniform: tag is read after a barrier
         __syncthreads();
       }
-      if (tid < TK_NSL) {
+      if (tid < NSL) {
         int o = 0;
-        for (int s = S.dlo[tid]; s <= S.dhi[tid]; s++) o |= S.overflow[s % TK_RING];
+        for (int s = S.dlo[tid]; s <= S.dhi[tid]; s++) o |= S.overflow[s % (4 + NSL)];
         S.ovf[tid] = o;
       }
 
       for (uint32_t t0 = 0; t0 < nmax; t0 += TK_MAXT) {
         __syncthreads();
-        if (tid < TK_NSL) S.ntg[tid] = 0;
+        if (tid < NSL) S.ntg[tid] = 0;
         if (tid == 0) S.tnext = 0;
         __syncthreads();
 #pragma unroll
-        for (int w = 0; w < TK_NSL; w++)
+        for (int w = 0; w < NSL; w++)
           for (uint32_t f = t0 + tid; f < min(nraw[w], t0 + TK_MAXT); f += THREADS) {
             const uint32_t n0 = tb[w][0] - ta[w][0];
             const uint32_t pos = f < n0 ? ta[w][0] + f : ta[w][1] + (f - n0);
@@ -566,11 +566,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
           }
         __syncthreads();
         // tasks = pairs of targets of the same slab (both halves of a warp then share their loop bounds)
-        uint32_t tstart[TK_NSL + 1];
+        uint32_t tstart[NSL + 1];
         tstart[0] = 0;
 #pragma unroll
-        for (int w = 0; w < TK_NSL; w++) tstart[w + 1] = tstart[w] + ((S.ntg[w] + 1) >> 1);
-        const uint32_t tasks = tstart[TK_NSL];
+        for (int w = 0; w < NSL; w++) tstart[w + 1] = tstart[w] + ((S.ntg[w] + 1) >> 1);
+        const uint32_t tasks = tstart[NSL];
 
         // ---- two targets per warp: lanes 0-15 pool one event, lanes 16-31 the next ----
         for (;;) {
@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
           if (k >= tasks) break;
           int w = 0;
 #pragma unroll
-          for (int q = 1; q < TK_NSL; q++) w += (k >= tstart[q]) ? 1 : 0;
+          for (int q = 1; q < NSL; q++) w += (k >= tstart[q]) ? 1 : 0;
           const uint32_t kk = (k - tstart[w]) * 2 + half, nt = S.ntg[w];
           const bool have = kk < nt;
           const uint32_t tpos = S.tlist[w][have ? kk : nt - 1];
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
           for (int q = 0; q < FARMS_NSCALES; q++) S.acc[warp][q][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
           const int sl = S.dlo[w], sh = S.dhi[w];
           for (int s = sl; s <= sh; s++) {
-            const int slot = s % TK_RING;
+            const int slot = s % (4 + NSL);
             const int n = S.count[slot];
             ncand += (sub == 0 && have) ? n : 0;
             for (int q0 = sub; q0 < n; q0 += 64) {
@@ -646,20 +646,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pool_tile(PoolArgs A, int otx
   if ((lane & 15) == 0 && ncand) atomicAdd(A.cand_count, ncand);
 }
 
-template <int WARPS, int CAP>
+template <int WARPS, int CAP, int NSL, int CTAS>
 void launch_tile(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
   PoolArgs A = A0;
-  using SM = TileSmem<WARPS, CAP>;
-  auto kern = k_pool_tile<WARPS, CAP>;
+  using SM = TileSmem<WARPS, CAP, NSL>;
+  auto kern = k_pool_tile<WARPS, CAP, NSL, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     attr_set = true;
   }
   const int otx = (A.g.W + OT - 1) >> OT_SHIFT, oty = (A.g.H + OT - 1) >> OT_SHIFT;
   const int nseg = (nslabs + TK_SEG - 1) / TK_SEG;
   const long long items = (long long)otx * oty * nseg;
-  unsigned grid = (unsigned)std::min<long long>(items, (long long)num_sms);
+  unsigned grid = (unsigned)std::min<long long>(items, (long long)num_sms * CTAS);
   kern<<<grid, WARPS * 32, sizeof(SM), s>>>(A, otx, oty, nseg);
 }
 
@@ -1257,7 +1258,8 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
   if (fast && g.tile_shift == 4) {
     A.work_counter = work_counter;
     if (fast == 2) launch_bits(A, nslabs, num_sms, s);  // bit-table variant: 8 warps, 2 CTAs per SM, ~110 KB each
-    else launch_tile<16, 640>(A, nslabs, num_sms, s);   // 16 warps, 1 CTA per SM, ~224 KB of shared memory
+    else if (fast == 3) launch_tile<16, 640, 4, 1>(A, nslabs, num_sms, s);  // 16 warps, 1 CTA per SM, ~224 KB
+    else launch_tile<8, 416, 2, 2>(A, nslabs, num_sms, s);  // 8 warps, 2 CTAs per SM, ~110 KB each
     const size_t nout = m - (size_t)h;
     // the fast kernels leave sums and counts; this pass turns them into globalR / globalTheta / scale
     if (nout) k_pool_finish<<<nb(nout, 256), 256, 0, s>>>(fin, nout, global_r, global_theta, scale);
