@@ -88,7 +88,7 @@ struct farms_ctx {
   uint16_t *in_x[2] = {nullptr, nullptr}, *in_y[2] = {nullptr, nullptr};
   uint64_t *in_t[2] = {nullptr, nullptr};
   // misc
-  DevBuf sort_temp, scan_temp, cell_start, fit_scratch, surf_tmp;
+  DevBuf sort_temp, scan_temp, cell_start, fit_scratch, surf_tmp, item_ovf;
   int *d_err = nullptr;
   unsigned long long *d_counters = nullptr;  // [0] valid events, [1] pool candidates
   unsigned int *d_work = nullptr;
@@ -309,12 +309,17 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaMemsetAsync(w.gr, 0, n * 8, s));
   CU(cudaMemsetAsync(w.gth, 0, n * 8, s));
   CU(cudaMemsetAsync(w.scale, 0, n, s));
-  CU(cudaMemsetAsync(c->d_work, 0, 2 * sizeof(unsigned int), s));
+  CU(cudaMemsetAsync(c->d_work, 0, 4 * sizeof(unsigned int), s));
   CU(cudaMemsetAsync(w.done, 0, m, s));
   CU(cudaMemsetAsync(w.fin, 0, n * sizeof(uint32_t), s));
+  {
+    const size_t iw = pool_item_words(c->W, c->H, (int)nslabs);
+    if ((rc = ensure(c, c->item_ovf, iw * sizeof(uint32_t)))) return rc;
+    CU(cudaMemsetAsync(c->item_ovf.p, 0, iw * sizeof(uint32_t), s));
+  }
   const int fast = (monotone && !(c->cfg.flags & FARMS_FLAG_GENERIC_POOLING)) ? c->pool_impl : 0;
-  *L += launch_pooling(w.rec, w.pay, (const uint32_t *)c->cell_start.p, w.slab_ids, w.slab_first, w.fin, w.done, m, (uint32_t)ncells,
-                       (int)h, (int)nslabs, g, fast, flow_frac * (double)m / (double)nslabs, w.gr, w.gth, w.scale,
+  *L += launch_pooling(w.rec, w.pay, (const uint32_t *)c->cell_start.p, w.slab_ids, w.slab_first, w.fin, (uint32_t *)c->item_ovf.p, w.done, m, (uint32_t)ncells,
+                       (int)h, w.len, w.lcx, w.lcy, (int)nslabs, g, fast, flow_frac * (double)m / (double)nslabs, w.gr, w.gth, w.scale,
                        c->d_work, c->d_counters + 1, c->num_sms, s);
   CU(cudaEventRecord(c->ev[EV_POOL], s));
 
@@ -547,7 +552,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   ok &= cudaMalloc((void **)&c->hlcy, HALO_CAP * 8) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->d_err, sizeof(int)) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->d_counters, 2 * sizeof(unsigned long long)) == cudaSuccess;
-  ok &= cudaMalloc((void **)&c->d_work, 2 * sizeof(unsigned int)) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->d_work, 4 * sizeof(unsigned int)) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->d_small, 64) == cudaSuccess;
   ok &= cudaMallocHost((void **)&c->h_small, 64) == cudaSuccess;
   if (!ok) return bail(FARMS_ERR_NOMEM);
@@ -566,7 +571,7 @@ void farms_destroy(farms_ctx *c) {
   free_owned(c->ws[1]);
   void *ps[] = {c->sae, c->hx, c->hy, c->ht, c->hm, c->hlen, c->hlcx, c->hlcy, c->d_err, c->d_counters, c->d_work,
                 c->d_small, c->in_x[0], c->in_y[0], c->in_t[0], c->in_x[1], c->in_y[1], c->in_t[1], c->sort_temp.p,
-                c->scan_temp.p, c->cell_start.p, c->fit_scratch.p, c->surf_tmp.p};
+                c->scan_temp.p, c->cell_start.p, c->fit_scratch.p, c->surf_tmp.p, c->item_ovf.p};
   for (void *p : ps)
     if (p) cudaFree(p);
   if (c->h_small) cudaFreeHost(c->h_small);

@@ -96,10 +96,12 @@ void launch_build_records(const uint32_t *skeys, const uint32_t *sidx, size_t m,
                           const uint16_t *ey, const uint32_t *et, const int32_t *nextp, const double *len,
                           const double *lcx, const double *lcy, int monotone, uint4 *rec, double *pay,
                           uint32_t *cell_start, uint32_t ncells, cudaStream_t s);
-// returns the number of kernels launched.  work_counter: two zeroed words; done: m zeroed bytes; fin: m - h zeroed words.
+// returns the number of kernels launched.  work_counter: four zeroed words; done: m zeroed bytes; fin: m - h zeroed words.
 int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_start, const uint32_t *slab_ids,
-                   const uint32_t *slab_first, uint32_t *fin, uint8_t *done, size_t m, uint32_t ncells, int h,
-                   int nslabs, PoolGeom g, int fast,
+                   const uint32_t *slab_first, uint32_t *fin, uint32_t *item_ovf, uint8_t *done, size_t m, uint32_t ncells, int h,
+                   const double *ev_len, const double *ev_lcx, const double *ev_lcy, int nslabs, PoolGeom g, int fast,
                    double flow_per_slab, double *global_r, double *global_theta, uint8_t *scale,
                    unsigned int *work_counter, unsigned long long *cand_count, int num_sms, cudaStream_t s);
 int pool_tile_smem_bytes();
+// words of the zeroed item_ovf array launch_pooling needs
+size_t pool_item_words(int W, int H, int nslabs);

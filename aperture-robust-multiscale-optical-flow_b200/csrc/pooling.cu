@@ -24,6 +24,7 @@
 // (src/vFlow.cpp:1000, 1113) and indexes _data[i*H + j] unchecked (include/EventMatrix.h:32-34), so a
 // logical cell (i, j >= H) aliases pixel (i + j/H, j mod H), and indices past W*H read as "no flow".
 #include <algorithm>
+#include <cstdlib>
 
 #include "farms_dev.cuh"
 
@@ -97,7 +98,10 @@ struct PoolArgs {
   const uint32_t *cell_start;
   const uint32_t *slab_ids;
   const uint32_t *slab_first;  // index of the first event of every dense slab
+  const double *ev_len, *ev_lcx, *ev_lcy;  // FP64 flow values by event index (exact re-pooling of undecided events)
   uint32_t *fin;               // per output event: contributor count | scale index << 16 of a fast-path result
+  uint32_t *item_ovf;          // per (owner tile, slab segment) item: bit (slab - first slab) / 2 = that pair of slabs
+                               // had targets the first pass could not stage (slot overflow)
   uint8_t *done;       // per index position: 1 once the fast path has pooled that event
   size_t m;            // stride of the pay arrays
   uint32_t ncells;     // cell_start[ncells] = entries in the index (events with flow)
@@ -174,10 +178,13 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
   const double *pay_len = A.pay, *pay_cx = A.pay + m, *pay_cy = A.pay + 2 * m;
   unsigned long long ncand = 0;
 
-  for (;;) {
-    unsigned int base = 0;
-    if (lane == 0) base = atomicAdd(A.work_counter, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
+  constexpr unsigned int CHUNK = 32;  // index positions per grab: few atomics even when almost nothing is left to pool
+  for (unsigned int base = 0, chunk_end = 0;; base += 32) {
+    if (base >= chunk_end) {
+      if (lane == 0) base = atomicAdd(A.work_counter, CHUNK);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      chunk_end = base + CHUNK;
+    }
     if (base >= mi) break;
     const uint32_t pos = base + lane;
     uint4 r = make_uint4(0, 0, 0, 0);
@@ -294,8 +301,10 @@ constexpr float TK_TIE_TOL = 2e-5f;
 
 template <int WARPS, int CAP, int NSL>
 struct TileSmem {
-  uint4 ra[(4 + NSL)][CAP + TK_PAD];        // {x | y<<16 (logical window coordinates), idx, end - idx, len as f32}
-  float2 rb[(4 + NSL)][CAP];                // lcx, lcy
+  // {x | y<<16 (logical window coordinates), idx, end - idx, |flow|cos as f32} and |flow|sin; |flow| itself is
+  // recomputed from the two (4 bytes per staged record buy 23 % more records per slot)
+  uint4 ra[(4 + NSL)][CAP + TK_PAD];
+  float rb[(4 + NSL)][CAP];
   float4 acc[WARPS][FARMS_NSCALES][32];   // per-lane ring partials: len, lcx, lcy, count
   uint32_t tlist[NSL][TK_MAXT];
   uint32_t run_s[TK_MAXRUN], run_o[TK_MAXRUN + 1];
@@ -351,7 +360,7 @@ __device__ void stage_slab(const PoolArgs &A, SM &S, int s, int slot, const Regi
   }
   __syncthreads();
   const uint32_t total = S.run_o[nrun];
-  const double *pay_len = A.pay, *pay_cx = A.pay + A.m, *pay_cy = A.pay + 2 * A.m;
+  const double *pay_cx = A.pay + A.m, *pay_cy = A.pay + 2 * A.m;
   uint32_t out_base = 0;
   for (uint32_t r0 = 0; r0 < total; r0 += WARPS * 32) {
     const uint32_t f = r0 + tid;
@@ -387,8 +396,8 @@ __device__ void stage_slab(const PoolArgs &A, SM &S, int s, int slot, const Regi
     }
     const uint32_t o = out_base + pre + __popc(bal & ((1u << lane) - 1u));
     if (pass && o < (uint32_t)CAP) {
-      S.ra[slot][o] = make_uint4(rec.x, rec.z, rec.w - rec.z, __float_as_uint(__double2float_rn(pay_len[pos])));
-      S.rb[slot][o] = make_float2(__double2float_rn(pay_cx[pos]), __double2float_rn(pay_cy[pos]));
+      S.ra[slot][o] = make_uint4(rec.x, rec.z, rec.w - rec.z, __float_as_uint(__double2float_rn(pay_cx[pos])));
+      S.rb[slot][o] = __double2float_rn(pay_cy[pos]);
     }
     out_base += all;
     __syncthreads();
@@ -452,7 +461,9 @@ __device__ __forceinline__ bool finish_event_checked(const PoolArgs &A, int sub,
   return safe;
 }
 
-template <int WARPS, int CAP, int NSL, int CTAS>
+// SECOND: a later pass over the same items with larger slots; only rounds that still hold undone targets (their
+// staging overflowed the slots of the first pass: locally dense scenes) do any work.
+template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND>
 __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int otx_n, int oty_n, int nseg) {
   using SM = TileSmem<WARPS, CAP, NSL>;
   constexpr int THREADS = WARPS * 32;
@@ -514,6 +525,11 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
         nmax = max(nmax, nraw[w]);
       }
       if (nraw_all == 0) continue;  // uniform across the CTA
+      if (SECOND) {  // only rounds the first pass flagged do any work here
+        const uint32_t bits = A.item_ovf[item];
+        const int b0 = (d - d_begin) >> 1, nb2 = (nd + 1) >> 1;
+        if (((bits >> b0) & ((1u << nb2) - 1u)) == 0u) continue;
+      }
 
       // ---- make sure the slabs of all windows of the round are staged ----
       __syncthreads();  // the previous round is done with S.dlo / S.dhi / S.ovf
@@ -546,6 +562,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
         int o = 0;
         for (int s = S.dlo[tid]; s <= S.dhi[tid]; s++) o |= S.overflow[s % (4 + NSL)];
         S.ovf[tid] = o;
+        if (!SECOND && o && nraw[tid]) atomicOr(&A.item_ovf[item], 1u << ((d + tid - d_begin) >> 1));
       }
 
       for (uint32_t t0 = 0; t0 < nmax; t0 += TK_MAXT) {
@@ -561,8 +578,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
             const uint4 r = A.rec[pos];
             const int yi = (int)(r.x >> 16);
             // fast-path conditions: not a halo event, window rows stay below 2H, staging complete
-            const bool ok = (int)r.z >= A.h && min(yi + FARMS_MAX_WINDOW, W - 1) <= 2 * H - 1 && !S.ovf[w];
+            const bool ok = (int)r.z >= A.h && min(yi + FARMS_MAX_WINDOW, W - 1) <= 2 * H - 1 && !S.ovf[w] &&
+                            (!SECOND || !A.done[pos]);
             if (ok) S.tlist[w][atomicAdd(&S.ntg[w], 1u)] = pos;
+
           }
         __syncthreads();
         // tasks = pairs of targets of the same slab (both halves of a warp then share their loop bounds)
@@ -612,11 +631,13 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
                 if (ok) {
                   const int m = max(abs(cx - xi), abs(cy - yi));
                   const int ring = ((m + FARMS_WINDOW_JUMP - 1) * 205) >> 10;  // /5 for values <= 54
-                  const float2 l = S.rb[slot][q0 + 16 * u];
+                  const float fx = __uint_as_float(c[u].w), fy = S.rb[slot][q0 + 16 * u];
+                  float fl;
+                  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(fl) : "f"(fx * fx + fy * fy));
                   float4 v = S.acc[warp][ring][lane];
-                  v.x += __uint_as_float(c[u].w);
-                  v.y += l.x;
-                  v.z += l.y;
+                  v.x += fl;
+                  v.y += fx;
+                  v.z += fy;
                   v.w += 1.f;
                   S.acc[warp][ring][lane] = v;
                 }
@@ -638,7 +659,56 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
           }
           __syncwarp();
           const bool fin = finish_event_checked(A, sub, rl, rx, ry, rn, (int)ii - A.h, have);
+
           if (sub == 0 && fin) A.done[tpos] = 1;
+          // ---- undecided targets (a rival scale within the FP32 noise, cancelling vectors): pool them again
+          // exactly, FP64 partials and the FP64 flow values of the contributors, one half-warp at a time
+          // (the FP64 partials of one target take the warp's whole accumulator space) ----
+          const unsigned need = __ballot_sync(0xffffffffu, have && !fin && sub == 0);
+          for (int hsel = 0; hsel < 2; hsel++) {
+            if (!((need >> (16 * hsel)) & 1u)) continue;  // uniform across the warp
+            __syncwarp();
+            double4 *dacc = reinterpret_cast<double4 *>(&S.acc[warp][0][0]);  // [ring][16 lanes] {len, lcx, lcy, n}
+            if (half == hsel) {
+#pragma unroll
+              for (int q = 0; q < FARMS_NSCALES; q++) dacc[q * 16 + sub] = make_double4(0.0, 0.0, 0.0, 0.0);
+              for (int s = sl; s <= sh; s++) {
+                const int slot = s % (4 + NSL);
+                const int n = S.count[slot];
+                for (int q0 = sub; q0 < n; q0 += 16) {
+                  const uint4 c = S.ra[slot][q0];
+                  const int cx = (int)(c.x & 0xffffu), cy = (int)(c.x >> 16);
+                  const bool ok = (ii - c.y) < c.z && (uint32_t)(cx + xoff) <= 2u * FARMS_MAX_WINDOW &&
+                                  (uint32_t)(cy - ylo) <= jspan;
+                  if (ok) {
+                    const int mch = max(abs(cx - xi), abs(cy - yi));
+                    const int ring = ((mch + FARMS_WINDOW_JUMP - 1) * 205) >> 10;
+                    double4 v = dacc[ring * 16 + sub];
+                    v.x += A.ev_len[c.y];
+                    v.y += A.ev_lcx[c.y];
+                    v.z += A.ev_lcy[c.y];
+                    v.w += 1.0;
+                    dacc[ring * 16 + sub] = v;
+                  }
+                }
+              }
+            }
+            __syncwarp();
+            double el = 0.0, ex2 = 0.0, ey2 = 0.0, en = 0.0;
+            if (half == hsel && sub < FARMS_NSCALES) {
+#pragma unroll 4
+              for (int q = 0; q < 16; q++) {
+                const double4 v = dacc[sub * 16 + ((q + sub) & 15)];
+                el += v.x;
+                ex2 += v.y;
+                ey2 += v.z;
+                en += v.w;
+              }
+            }
+            __syncwarp();
+            finish_event<16>(A, sub, el, ex2, ey2, en, A.ev_lcx[ii], A.ev_lcy[ii], (int)ii - A.h, half == hsel);
+            if (half == hsel && sub == 0) A.done[tpos] = 1;
+          }
         }
       }
     }
@@ -646,11 +716,11 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
   if ((lane & 15) == 0 && ncand) atomicAdd(A.cand_count, ncand);
 }
 
-template <int WARPS, int CAP, int NSL, int CTAS>
+template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND>
 void launch_tile(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
   PoolArgs A = A0;
   using SM = TileSmem<WARPS, CAP, NSL>;
-  auto kern = k_pool_tile<WARPS, CAP, NSL, CTAS>;
+  auto kern = k_pool_tile<WARPS, CAP, NSL, CTAS, SECOND>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
@@ -1241,9 +1311,14 @@ int pool_tile_smem_bytes() { return (int)sizeof(BitsSmem); }
 
 // Launches the fast path (when `fast` is set) and then the general, exact path for whatever is left.
 // work_counter: two zeroed words.  done: m zeroed bytes.
+size_t pool_item_words(int W, int H, int nslabs) {
+  const size_t otx = (size_t)(W + OT - 1) >> OT_SHIFT, oty = (size_t)(H + OT - 1) >> OT_SHIFT;
+  return otx * oty * (size_t)((nslabs + TK_SEG - 1) / TK_SEG);
+}
+
 int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_start, const uint32_t *slab_ids,
-                   const uint32_t *slab_first, uint32_t *fin, uint8_t *done, size_t m, uint32_t ncells, int h,
-                   int nslabs, PoolGeom g, int fast,
+                   const uint32_t *slab_first, uint32_t *fin, uint32_t *item_ovf, uint8_t *done, size_t m, uint32_t ncells, int h,
+                   const double *ev_len, const double *ev_lcx, const double *ev_lcy, int nslabs, PoolGeom g, int fast,
                    double flow_per_slab, double *global_r, double *global_theta, uint8_t *scale,
                    unsigned int *work_counter, unsigned long long *cand_count, int num_sms, cudaStream_t s) {
   if (!m) return 0;
@@ -1251,15 +1326,23 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
   int launches = 0;
   PoolArgs A;
   A.rec = rec; A.pay = pay; A.cell_start = cell_start; A.slab_ids = slab_ids; A.done = done;
-  A.slab_first = slab_first; A.fin = fin;
+  A.slab_first = slab_first; A.fin = fin; A.item_ovf = item_ovf;
+  A.ev_len = ev_len; A.ev_lcx = ev_lcx; A.ev_lcy = ev_lcy;
   A.m = m; A.ncells = ncells; A.h = h; A.nslabs = nslabs; A.g = g;
   A.global_r = global_r; A.global_theta = global_theta; A.scale = scale;
   A.cand_count = cand_count;
   if (fast && g.tile_shift == 4) {
     A.work_counter = work_counter;
     if (fast == 2) launch_bits(A, nslabs, num_sms, s);  // bit-table variant: 8 warps, 2 CTAs per SM, ~110 KB each
-    else if (fast == 3) launch_tile<16, 640, 4, 1>(A, nslabs, num_sms, s);  // 16 warps, 1 CTA per SM, ~224 KB
-    else launch_tile<8, 416, 2, 2>(A, nslabs, num_sms, s);  // 8 warps, 2 CTAs per SM, ~110 KB each
+    else if (fast == 3) launch_tile<16, 768, 4, 1, false>(A, nslabs, num_sms, s);  // 16 warps, 1 CTA per SM, ~222 KB
+    else {
+      launch_tile<8, 512, 2, 2, false>(A, nslabs, num_sms, s);  // 8 warps, 2 CTAs per SM, ~112 KB each
+      // rounds whose staging overflowed those slots (locally dense scenes) get a second chance with 640-record
+      // slots before the general kernel takes what is left
+      A.work_counter = work_counter + 2;
+      launch_tile<16, 768, 4, 1, true>(A, nslabs, num_sms, s);
+      launches++;
+    }
     const size_t nout = m - (size_t)h;
     // the fast kernels leave sums and counts; this pass turns them into globalR / globalTheta / scale
     if (nout) k_pool_finish<<<nb(nout, 256), 256, 0, s>>>(fin, nout, global_r, global_theta, scale);
@@ -1270,7 +1353,8 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
   unsigned grid = (unsigned)num_sms * 5u;
   unsigned need = nb(m, 32 * PW);
   if (grid > need) grid = need;
-  k_pool_any<<<grid, PW * 32, 0, s>>>(A);
+  static const bool skip_any = getenv("FARMS_DEBUG_SKIP_ANY") != nullptr;  // timing experiments only
+  if (!skip_any) k_pool_any<<<grid, PW * 32, 0, s>>>(A);
   launches++;
   return launches;
 }
