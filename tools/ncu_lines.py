@@ -32,7 +32,7 @@ for ln in dis.splitlines():
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
         lines.append(cur)
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern],
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + os.environ.get("NCU_KERNEL", kern)],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
@@ -40,6 +40,10 @@ hdr = rows[hi]
 ci = hdr.index("Instructions Executed")
 cs = hdr.index("# Samples")
 body = rows[hi + 1:]
+for j, r in enumerate(body):  # several kernels matched: keep the first one
+    if r and r[0] == "Kernel Name":
+        body = body[:j]
+        break
 if len(body) != len(lines):
     print(f"warning: {len(body)} SASS rows in the report vs {len(lines)} in the object", file=sys.stderr)
 agg = {}
