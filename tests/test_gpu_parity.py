@@ -118,3 +118,21 @@ def test_fast_pooling_equals_exact_pooling_on_long_dense_streams(config, n, star
     from helpers import angle_diff
     assert np.all(angle_diff(fast["global_theta"][v], exact["global_theta"][v]) <= 1e-3)
     assert np.array_equal(fast["global_r"][~v], exact["global_r"][~v])
+
+
+def test_bit_table_pooling_variant_matches_oracle_and_exact_kernel(monkeypatch):
+    """k_pool_bits (FARMS_POOL_IMPL=bits: prefix bit tables over the staged records, a measured alternative to the
+    default staged-list kernel) obeys the same contract: oracle parity on a short stream, and the same scale as
+    the exact FP64 kernel on a long dense one."""
+    import farms_b200
+    monkeypatch.setenv("FARMS_POOL_IMPL", "bits")
+    s, x, y, t, ref, f = _run_case(4, 120000, 0, None)
+    rep = compare(f.process(x, y, t), ref, "cfg4 bit-table pooling")
+    assert_parity(rep)
+    s, x, y, t, p = synth_stream(4, 2_000_000, 2000)
+    fast = farms_b200.Farms(s.width, s.height, s.filtersize, 5).process(x, y, t)
+    monkeypatch.delenv("FARMS_POOL_IMPL")
+    exact = farms_b200.Farms(s.width, s.height, s.filtersize, 5, flags=farms_b200.FLAG_EXACT_POOLING).process(x, y, t)
+    assert np.array_equal(fast["scale"], exact["scale"])
+    v = exact["valid"].astype(bool)
+    assert np.all(np.abs(fast["global_r"][v] - exact["global_r"][v]) <= 1e-4 * np.abs(exact["global_r"][v]))
