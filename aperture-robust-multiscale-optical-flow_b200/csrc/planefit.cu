@@ -247,6 +247,8 @@ template <int R>
 struct FitRec {
   static constexpr int N = 4 * R + 1, N1 = 2 * R + 1, P = N1 * N1;
   static constexpr int WORDS = (P + 3) <= 16 ? 16 : (P + 3) <= 32 ? 32 : 64;  // t[P], hit mask lo/hi, best
+  // lanes per event in k_fit_gather (>= N footprint rows) and events per warp: 8 x 4, 10 x 3 (two lanes idle), 16 x 2
+  static constexpr int G = R == 1 ? 8 : R == 2 ? 10 : 16, EPW = 32 / G;
 };
 
 template <int R>
@@ -255,10 +257,13 @@ __global__ void __launch_bounds__(256) k_fit_gather(const uint2 *__restrict__ sa
                                                     const uint32_t *__restrict__ et, int i0, int i1, int W, int H,
                                                     uint32_t *__restrict__ recs) {
   constexpr int N = FitRec<R>::N, N1 = FitRec<R>::N1, P = FitRec<R>::P, WORDS = FitRec<R>::WORDS;
-  const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-  const int b = threadIdx.x & 15;  // footprint row handled by this lane
+  constexpr int G = FitRec<R>::G, EPW = FitRec<R>::EPW;
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / G, gbase = grp * G;
+  const int b = lane - gbase;  // footprint row handled by this lane
+  const int gid = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * EPW + grp;
   const int i = i0 + gid;
-  const bool live = i < i1;        // uniform per 16-lane group
+  const bool live = grp < EPW && i < i1;  // uniform per group of G lanes
   const int ii = live ? i : i1 - 1;
   const int x = ex[ii], y = ey[ii];
   const uint32_t t = et[ii];
@@ -296,9 +301,9 @@ __global__ void __launch_bounds__(256) k_fit_gather(const uint2 *__restrict__ sa
   }
   // inclusive prefix over the rows (lanes) of the group
 #pragma unroll
-  for (int o = 1; o < 16; o <<= 1) {
-    const unsigned long long p0 = __shfl_up_sync(0xffffffffu, r0, o, 16), p1 = __shfl_up_sync(0xffffffffu, r1, o, 16),
-                             p2 = __shfl_up_sync(0xffffffffu, r2, o, 16);
+  for (int o = 1; o < G; o <<= 1) {
+    const unsigned long long p0 = __shfl_up_sync(0xffffffffu, r0, o), p1 = __shfl_up_sync(0xffffffffu, r1, o),
+                             p2 = __shfl_up_sync(0xffffffffu, r2, o);
     if (b >= o) {
       r0 += p0;
       r1 += p1;
@@ -309,14 +314,14 @@ __global__ void __launch_bounds__(256) k_fit_gather(const uint2 *__restrict__ sa
   unsigned long long sums[9];
 #pragma unroll
   for (int dj = 0; dj < 3; dj++) {
-    const int hi = dj * R + 2 * R, lo = dj * R - 1;
-    const unsigned long long h0 = __shfl_sync(0xffffffffu, r0, hi, 16), h1 = __shfl_sync(0xffffffffu, r1, hi, 16),
-                             h2 = __shfl_sync(0xffffffffu, r2, hi, 16);
+    const int hi = gbase + dj * R + 2 * R, lo = dj * R - 1;
+    const unsigned long long h0 = __shfl_sync(0xffffffffu, r0, hi), h1 = __shfl_sync(0xffffffffu, r1, hi),
+                             h2 = __shfl_sync(0xffffffffu, r2, hi);
     unsigned long long l0 = 0, l1 = 0, l2 = 0;
     if (lo >= 0) {
-      l0 = __shfl_sync(0xffffffffu, r0, lo, 16);
-      l1 = __shfl_sync(0xffffffffu, r1, lo, 16);
-      l2 = __shfl_sync(0xffffffffu, r2, lo, 16);
+      l0 = __shfl_sync(0xffffffffu, r0, gbase + lo);
+      l1 = __shfl_sync(0xffffffffu, r1, gbase + lo);
+      l2 = __shfl_sync(0xffffffffu, r2, gbase + lo);
     }
     sums[0 * 3 + dj] = h0 - l0;
     sums[1 * 3 + dj] = h1 - l1;
@@ -350,13 +355,18 @@ __global__ void __launch_bounds__(256) k_fit_gather(const uint2 *__restrict__ sa
       if (hb & 1u) hm |= 1ull << (k * N1 + brel);
     }
   }
-  // OR of the group's hit bits
+  // OR of the group's hit bits: inclusive OR-scan over the lanes of the group, total from its last lane
   uint32_t hlo = (uint32_t)hm, hhi = (uint32_t)(hm >> 32);
 #pragma unroll
-  for (int o = 8; o; o >>= 1) {
-    hlo |= __shfl_xor_sync(0xffffffffu, hlo, o, 16);
-    hhi |= __shfl_xor_sync(0xffffffffu, hhi, o, 16);
+  for (int o = 1; o < G; o <<= 1) {
+    const uint32_t plo = __shfl_up_sync(0xffffffffu, hlo, o), phi = __shfl_up_sync(0xffffffffu, hhi, o);
+    if (b >= o) {
+      hlo |= plo;
+      hhi |= phi;
+    }
   }
+  hlo = __shfl_sync(0xffffffffu, hlo, gbase + G - 1);
+  hhi = __shfl_sync(0xffffffffu, hhi, gbase + G - 1);
   if (live && b == 0) {
     rec[P] = hlo;
     rec[P + 1] = hhi;
@@ -470,7 +480,8 @@ void launch_fit_r(const uint2 *sae, const int2 *prevp, const uint16_t *ex, const
                   int i0, int i1, FitParams fp, FitOut fo, unsigned long long *valid_count, uint32_t *recs,
                   cudaStream_t s) {
   const size_t n = (size_t)(i1 - i0);
-  k_fit_gather<R><<<(unsigned)((n * 16 + 255) / 256), 256, 0, s>>>(sae, prevp, ex, ey, et, i0, i1, fp.W, fp.H, recs);
+  constexpr int EPB = FitRec<R>::EPW * 8;  // events per 256-thread block
+  k_fit_gather<R><<<(unsigned)((n + EPB - 1) / EPB), 256, 0, s>>>(sae, prevp, ex, ey, et, i0, i1, fp.W, fp.H, recs);
   k_fit_solve<R><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(recs, ex, ey, et, i0, i1, fp, fo, valid_count);
 }
 
