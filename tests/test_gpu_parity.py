@@ -136,3 +136,25 @@ def test_bit_table_pooling_variant_matches_oracle_and_exact_kernel(monkeypatch):
     assert np.array_equal(fast["scale"], exact["scale"])
     v = exact["valid"].astype(bool)
     assert np.all(np.abs(fast["global_r"][v] - exact["global_r"][v]) <= 1e-4 * np.abs(exact["global_r"][v]))
+
+
+@pytest.mark.parametrize("squeeze", [2.5, 6.0])
+def test_locally_dense_streams_overflowing_the_staging_slots(squeeze):
+    """Time-compressed 1280x720 stream: 2.5x the event density overflows the 512-record slots of the first
+    pooling pass (the flagged second pass with 768-record slots takes those rounds), 6x overflows both (the
+    general kernel takes them).  Every route must give the exact kernel's scales and the oracle's numbers."""
+    import farms_b200
+    s, x, y, t, p = synth_stream(4, 700_000, 2000)
+    t = (t[0] + ((t - t[0]).astype(np.float64) / squeeze).astype(np.uint64)).astype(np.uint64)
+    fast = farms_b200.Farms(s.width, s.height, s.filtersize, 5).process(x, y, t)
+    exact = farms_b200.Farms(s.width, s.height, s.filtersize, 5, flags=farms_b200.FLAG_EXACT_POOLING).process(x, y, t)
+    assert np.array_equal(fast["valid"], exact["valid"])
+    assert np.array_equal(fast["scale"], exact["scale"])
+    v = exact["valid"].astype(bool)
+    assert v.sum() > 100_000
+    assert np.all(np.abs(fast["global_r"][v] - exact["global_r"][v]) <= 1e-4 * np.abs(exact["global_r"][v]))
+    n = 60_000
+    ref = run_oracle(s.width, s.height, s.filtersize, 5, x[:n], y[:n], t[:n], p[:n])
+    rep = compare(farms_b200.Farms(s.width, s.height, s.filtersize, 5).process(x[:n], y[:n], t[:n]), ref,
+                  f"cfg4 time-compressed x{squeeze}")
+    assert_parity(rep)
