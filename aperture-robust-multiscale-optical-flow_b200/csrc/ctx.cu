@@ -27,7 +27,8 @@ constexpr size_t HALO_CAP = 8ull << 20;       // events carried across a batch b
 #ifndef FARMS_FIT_CHUNK_LOG2
 #define FARMS_FIT_CHUNK_LOG2 17
 #endif
-constexpr int FIT_CHUNK = 1 << FARMS_FIT_CHUNK_LOG2;  // events per SAE snapshot
+constexpr int FIT_CHUNK_MAX = 1 << FARMS_FIT_CHUNK_LOG2;  // events per SAE snapshot at most
+constexpr int FIT_CHUNK_MIN = 1 << 13;
 constexpr size_t CSR_BUDGET = 96ull << 20;    // max (slab, tile) cells of the pooling index per batch
 
 enum { EV_START, EV_H2D, EV_INGEST, EV_INDEX, EV_FIT, EV_BIN, EV_POOL, EV_END, EV_COUNT };
@@ -62,6 +63,11 @@ struct farms_ctx {
   int W = 0, H = 0, fs = 0, r = 0, P = 0, min_inl = 0;
   size_t npx = 0;
   int num_sms = 148;
+  // Events per SAE snapshot.  A fit thread walks back one history link for every footprint cell that was hit
+  // again later in its chunk, so the chunk is kept to about a third of an event per pixel: 2^17 events at
+  // 1280x720, 2^15 at 346x260 (measured there: 2^13 73 ms, 2^14 46, 2^15 39, 2^16 49, 2^17 66 ms per 20 M events;
+  // small chunks are launch-bound, large ones walk ~100 dependent history links per event).
+  int fit_chunk = FIT_CHUNK_MAX;
   int pool_impl = 1;  // 1 = staged-list fast path (k_pool_tile), 2 = bit-table variant (FARMS_POOL_IMPL=bits, A/B runs)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[EV_COUNT]{};
@@ -251,11 +257,12 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   if (((int *)c->h_small)[0]) return fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
 
   // ---- K3 plane fit, chunk by chunk against the chunk-end SAE snapshot ----
+  const size_t FIT_CHUNK = (size_t)c->fit_chunk;
   if ((rc = ensure(c, c->fit_scratch, plane_fit_scratch_bytes(c->r, FIT_CHUNK)))) return rc;
   FitParams fp{c->W, c->H, c->r, c->P, c->min_inl};
   FitOut fo{w.vx, w.vy, w.len, w.theta, w.lcx, w.lcy, w.valid, w.bw, w.inl, w.det};
   for (size_t c0 = 0; c0 < m; c0 += FIT_CHUNK) {
-    const size_t c1 = std::min(m, c0 + (size_t)FIT_CHUNK);
+    const size_t c1 = std::min(m, c0 + FIT_CHUNK);
     launch_sae_advance(c->sae, w.pixkeep, w.et, w.nextp, (int)c0, (int)c1, s);
     *L += 1;
     if (c1 > h) {
@@ -529,6 +536,9 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (prop.major < 10) return bail(FARMS_ERR_CUDA);  // built for sm_100a only
   c->num_sms = prop.multiProcessorCount;
+  c->fit_chunk = FIT_CHUNK_MIN;
+  while (c->fit_chunk < FIT_CHUNK_MAX && (size_t)c->fit_chunk * 3 < c->npx) c->fit_chunk *= 2;
+  if (const char *e = getenv("FARMS_FIT_CHUNK")) c->fit_chunk = std::max(1024, atoi(e));  // tuning runs
   if (const char *e = getenv("FARMS_POOL_IMPL")) c->pool_impl = strcmp(e, "bits") == 0 ? 2 : strcmp(e, "tile1") == 0 ? 3 : 1;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
