@@ -30,6 +30,7 @@ struct Options {
   std::string filename = "/home/himanshu/POST_DOC/DATA/atisData/bar_square/multiPattern1_fixed_";  // :30
   bool serial = true, verbose = false;
   bool fast = false;  // --fast 1: FP32 ring partials in the pooling kernel (about 1e-7 relative on columns 5-6)
+  bool binary = false;  // --binary 1: <filename>.evb in, <filename>_FARMSOut_.bin out (include/farms_textio.h)
 };
 
 void usage() {
@@ -47,7 +48,8 @@ void usage() {
       "  --SERIAL arg          Serial or Batch processing\n"
       "  --v arg               set verbose to 1 for full debug mode\n"
       "  --device arg          CUDA device ordinal (extension)\n"
-      "  --fast arg            1 = fastest pooling kernel, columns 5-6 accurate to ~1e-7 (extension)\n");
+      "  --fast arg            1 = fastest pooling kernel, columns 5-6 accurate to ~1e-7 (extension)\n"
+      "  --binary arg          1 = binary side-format: <filename>.evb in, <filename>_FARMSOut_.bin out (extension)\n");
 }
 
 bool parse_int(const std::string &s, int &out) {
@@ -81,7 +83,7 @@ int parse_args(int argc, char **argv, Options &o) {
       return 2;
     }
     static const char *known[] = {"filename", "height", "width", "filtersize", "inlierCheck", "numEvents",
-                                  "numevents", "NUMEVENTS", "SERIAL", "v", "device", "fast"};
+                                  "numevents", "NUMEVENTS", "SERIAL", "v", "device", "fast", "binary"};
     bool ok = false;
     for (const char *k : known) ok |= name == k;
     if (!ok) {
@@ -115,6 +117,7 @@ int parse_args(int argc, char **argv, Options &o) {
     } else if (name == "v") { o.verbose = iv == 1; std::printf("Verbose mode set to %d\n", iv); }
     else if (name == "device") { o.device = iv; }
     else if (name == "fast") { o.fast = iv == 1; }
+    else if (name == "binary") { o.binary = iv == 1; }
   }
   // the reference honours the spellings in the order numEvents, numevents, NUMEVENTS (src/main.cpp:131-151)
   // and converts the int to unsigned long
@@ -141,7 +144,7 @@ int main(int argc, char **argv) {
   cfg.device = o.device;
   // text output prints 6 significant digits: keep the FP64 pooling sums unless told otherwise (the text
   // parse/format around it costs far more than the kernel)
-  cfg.flags = o.fast ? 0u : FARMS_FLAG_EXACT_POOLING;
+  cfg.flags = (o.fast || o.binary) ? 0u : FARMS_FLAG_EXACT_POOLING;
   farms_ctx *ctx = nullptr;
   int rc = farms_create(&ctx, &cfg);
   if (rc != FARMS_OK) {
@@ -150,11 +153,12 @@ int main(int argc, char **argv) {
   }
   std::printf("[debug Main] : size of lastFlowTime is [sx sy]: [%d %d]\n", o.width, o.height);
 
-  const std::string in_path = o.filename + ".txt";
+  const std::string in_path = o.filename + (o.binary ? ".evb" : ".txt");
   std::printf("%s\nReading input file \n", in_path.c_str());
   farms_events ev;
   char errbuf[256] = "";
-  if (farms_text_read(in_path.c_str(), o.num_events, 0, &ev, errbuf, sizeof errbuf) != 0) {
+  if ((o.binary ? farms_bin_read(in_path.c_str(), o.num_events, &ev, errbuf, sizeof errbuf)
+                : farms_text_read(in_path.c_str(), o.num_events, 0, &ev, errbuf, sizeof errbuf)) != 0) {
     std::fprintf(stderr, "error: %s\n", errbuf);
     farms_destroy(ctx);
     return 1;
@@ -189,9 +193,12 @@ int main(int argc, char **argv) {
   const long usec = (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count();
   std::printf("\nDone processing!\n\nWriting output file.\n");
 
-  const std::string out11 = o.filename + "_FARMSOut_batch.txt", out8 = o.filename + "_FARMSOut_.txt";
-  if (farms_text_write(out11.c_str(), out8.c_str(), n, ev.xi, ev.yi, t_rel.data(), ev.pol, gr.data(), gth.data(),
-                       vx.data(), vy.data(), lr.data(), lth.data(), scale.data(), 0) != 0) {
+  const std::string out11 = o.filename + (o.binary ? "_FARMSOut_.bin" : "_FARMSOut_batch.txt"),
+                    out8 = o.filename + "_FARMSOut_.txt";
+  if ((o.binary ? farms_bin_write(out11.c_str(), n, ev.xi, ev.yi, t_rel.data(), ev.pol, gr.data(), gth.data(),
+                                  vx.data(), vy.data(), lr.data(), lth.data(), scale.data())
+                : farms_text_write(out11.c_str(), out8.c_str(), n, ev.xi, ev.yi, t_rel.data(), ev.pol, gr.data(),
+                                   gth.data(), vx.data(), vy.data(), lr.data(), lth.data(), scale.data(), 0)) != 0) {
     std::fprintf(stderr, "error: cannot write %s / %s\n", out11.c_str(), out8.c_str());
     farms_text_free(&ev);
     farms_destroy(ctx);

@@ -299,3 +299,93 @@ extern "C" int farms_text_write(const char *path11, const char *path8, uint64_t 
   if (f8 && std::fclose(f8) != 0) io_error = true;
   return io_error ? -1 : 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// binary side-format (include/farms_textio.h): little-endian SoA columns behind an 8-byte magic and a count
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+template <class T>
+bool read_col(FILE *f, T *dst, uint64_t n_file, uint64_t n_take) {
+  if (n_take && std::fread(dst, sizeof(T), (size_t)n_take, f) != (size_t)n_take) return false;
+  return std::fseek(f, (long)((n_file - n_take) * sizeof(T)), SEEK_CUR) == 0;
+}
+
+template <class T>
+bool write_col(FILE *f, const T *src, uint64_t n) {
+  return n == 0 || std::fwrite(src, sizeof(T), (size_t)n, f) == (size_t)n;
+}
+
+}  // namespace
+
+extern "C" int farms_bin_read(const char *path, uint64_t max_events, farms_events *out, char *err, size_t errlen) {
+  auto fail = [&](const std::string &m) {
+    if (err && errlen) std::snprintf(err, errlen, "%s", m.c_str());
+    return -1;
+  };
+  if (!out) return fail("null output");
+  std::memset(out, 0, sizeof *out);
+  FILE *f = std::fopen(path, "rb");
+  if (!f) return fail(std::string("Unable to open file ") + path);
+  char magic[8];
+  uint64_t n_file = 0;
+  if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, "FARMSEV1", 8) != 0 || std::fread(&n_file, 8, 1, f) != 1) {
+    std::fclose(f);
+    return fail(std::string(path) + ": not a FARMSEV1 event file");
+  }
+  const uint64_t n = std::min(n_file, max_events);
+  const size_t cap = (size_t)std::max<uint64_t>(n, 1);
+  out->x = (uint16_t *)std::malloc(cap * 2);
+  out->y = (uint16_t *)std::malloc(cap * 2);
+  out->t = (uint64_t *)std::malloc(cap * 8);
+  out->xi = (int32_t *)std::malloc(cap * 4);
+  out->yi = (int32_t *)std::malloc(cap * 4);
+  out->pol = (int32_t *)std::malloc(cap * 4);
+  std::vector<uint8_t> p((size_t)n);
+  bool ok = out->x && out->y && out->t && out->xi && out->yi && out->pol;
+  ok = ok && read_col(f, out->x, n_file, n) && read_col(f, out->y, n_file, n) && read_col(f, out->t, n_file, n) &&
+       read_col(f, p.data(), n_file, n);
+  std::fclose(f);
+  if (!ok) {
+    farms_text_free(out);
+    return fail(std::string(path) + ": truncated event file");
+  }
+  for (uint64_t i = 0; i < n; i++) {
+    out->xi[i] = out->x[i];
+    out->yi[i] = out->y[i];
+    out->pol[i] = p[i];  // u8: already >= 0 (src/vFlow.cpp:246-247 clamps negatives)
+  }
+  out->n = n;
+  return 0;
+}
+
+extern "C" int farms_bin_write_events(const char *path, uint64_t n, const uint16_t *x, const uint16_t *y,
+                                      const uint64_t *t, const uint8_t *p) {
+  FILE *f = std::fopen(path, "wb");
+  if (!f) return -1;
+  bool ok = std::fwrite("FARMSEV1", 1, 8, f) == 8 && std::fwrite(&n, 8, 1, f) == 1 && write_col(f, x, n) &&
+            write_col(f, y, n) && write_col(f, t, n) && write_col(f, p, n);
+  ok = std::fclose(f) == 0 && ok;
+  return ok ? 0 : -1;
+}
+
+extern "C" int farms_bin_write(const char *path, uint64_t n, const int32_t *xi, const int32_t *yi,
+                               const uint32_t *t_rel, const int32_t *pol, const double *gr, const double *gth,
+                               const double *vx, const double *vy, const double *lr, const double *lth,
+                               const uint8_t *scale) {
+  FILE *f = std::fopen(path, "wb");
+  if (!f) return -1;
+  std::vector<uint16_t> x16((size_t)n), y16((size_t)n);
+  std::vector<uint8_t> p8((size_t)n);
+  for (uint64_t i = 0; i < n; i++) {
+    x16[i] = (uint16_t)xi[i];
+    y16[i] = (uint16_t)yi[i];
+    p8[i] = (uint8_t)pol[i];
+  }
+  bool ok = std::fwrite("FARMSOU1", 1, 8, f) == 8 && std::fwrite(&n, 8, 1, f) == 1 && write_col(f, x16.data(), n) &&
+            write_col(f, y16.data(), n) && write_col(f, t_rel, n) && write_col(f, p8.data(), n) &&
+            write_col(f, scale, n) && write_col(f, gr, n) && write_col(f, gth, n) && write_col(f, vx, n) &&
+            write_col(f, vy, n) && write_col(f, lr, n) && write_col(f, lth, n);
+  ok = std::fclose(f) == 0 && ok;
+  return ok ? 0 : -1;
+}

@@ -35,6 +35,21 @@ int farms_text_write(const char *path11, const char *path8, uint64_t n, const in
                      const uint32_t *t_rel, const int32_t *pol, const double *global_r, const double *global_theta,
                      const double *vx, const double *vy, const double *local_r, const double *local_theta,
                      const uint8_t *scale, int nthreads);
+
+/* ---- binary side-format (not in the reference) ---------------------------------
+ * At 10^9 events the text files are 19 GB in and ~60 GB out; these little-endian SoA files carry the same
+ * columns at 13 and 58 bytes per event and load with one read per column.
+ *   events  "<name>.evb":  "FARMSEV1", u64 n, then x u16[n], y u16[n], t u64[n], p u8[n]
+ *   results "<name>_FARMSOut_.bin": "FARMSOU1", u64 n, then x u16[n], y u16[n], t_rel u32[n], p u8[n], scale u8[n],
+ *            globalR, globalTheta, Vx, Vy, localR, localTheta f64[n] each  (the 11 columns of src/vFlow.cpp:438)
+ * farms_bin_read fills the same farms_events as the text reader (polarity clamped like src/vFlow.cpp:246-247);
+ * both return 0, or -1 with a message in err. */
+int farms_bin_read(const char *path, uint64_t max_events, farms_events *out, char *err, size_t errlen);
+int farms_bin_write_events(const char *path, uint64_t n, const uint16_t *x, const uint16_t *y, const uint64_t *t,
+                           const uint8_t *p);
+int farms_bin_write(const char *path, uint64_t n, const int32_t *xi, const int32_t *yi, const uint32_t *t_rel,
+                    const int32_t *pol, const double *global_r, const double *global_theta, const double *vx,
+                    const double *vy, const double *local_r, const double *local_theta, const uint8_t *scale);
 #ifdef __cplusplus
 }
 #endif

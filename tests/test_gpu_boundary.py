@@ -189,3 +189,36 @@ def test_state_export_matches_oracle_surface():
     assert np.array_equal(sh.cpu().numpy(), hit)
     m = hit.astype(bool)
     assert np.array_equal(st.cpu().numpy().view(np.uint32)[m], lt[m].astype(np.uint32))
+
+
+def test_cli_binary_side_format_carries_the_same_columns_as_the_text_files(tmp_path):
+    """FARMS_Flow --binary 1 (include/farms_textio.h): <name>.evb in, <name>_FARMSOut_.bin out, the
+    11 columns of src/vFlow.cpp:438 as arrays; compared with the library called directly on the same events."""
+    import ctypes as C
+    import farms_b200
+    from helpers import synth_stream
+    s, x, y, t, p = synth_stream(2, 40000, 0)
+    L = C.CDLL(os.path.join(PKG, "libfarms_textio.so"))
+    L.farms_bin_write_events.argtypes = [C.c_char_p, C.c_uint64] + [C.c_void_p] * 4
+    base = str(tmp_path / "ev")
+    x16, y16, t64, p8 = (np.ascontiguousarray(a, d) for a, d in ((x, np.uint16), (y, np.uint16), (t, np.uint64), (p, np.uint8)))
+    assert L.farms_bin_write_events((base + ".evb").encode(), len(x), x16.ctypes.data, y16.ctypes.data, t64.ctypes.data,
+                                    p8.ctypes.data) == 0
+    out = subprocess.run([CLI, "--width", str(s.width), "--height", str(s.height), "--filtersize", str(s.filtersize),
+                          "--filename", base, "--binary", "1", "--numEvents", "30000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    n = 30000
+    raw = open(base + "_FARMSOut_.bin", "rb").read()
+    assert raw[:8] == b"FARMSOU1" and int(np.frombuffer(raw, np.uint64, 1, 8)[0]) == n
+    ref = farms_b200.Farms(s.width, s.height, s.filtersize, 5).process(x[:n], y[:n], t[:n])
+    off = 16
+    cols = {}
+    for k, dt in (("x", np.uint16), ("y", np.uint16), ("t_rel", np.uint32), ("p", np.uint8), ("scale", np.uint8),
+                  ("global_r", np.float64), ("global_theta", np.float64), ("vx", np.float64), ("vy", np.float64),
+                  ("local_r", np.float64), ("local_theta", np.float64)):
+        cols[k] = np.frombuffer(raw, dt, n, off)
+        off += n * np.dtype(dt).itemsize
+    assert off == len(raw)
+    assert np.array_equal(cols["x"], x16[:n]) and np.array_equal(cols["y"], y16[:n]) and np.array_equal(cols["p"], p8[:n])
+    for k in ("t_rel", "scale", "global_r", "global_theta", "vx", "vy", "local_r", "local_theta"):
+        assert np.array_equal(cols[k], ref[k], equal_nan=True), k

@@ -132,3 +132,52 @@ def test_writer_is_byte_identical_to_percent_g(lib, tmp_path):
                 continue
             assert got11[i] == f"{xi[i]} {yi[i]} {ti[i]} {pol[i]} {d[0]} {d[1]} {d[2]} {d[3]} {d[4]} {d[5]} {scale[i]}"
             assert got8[i] == f"{xi[i]} {yi[i]} {ti[i]} {pol[i]} {d[0]} {d[1]} {d[4]} {d[5]}"
+
+
+def test_binary_side_format_round_trip(lib, tmp_path):
+    """include/farms_textio.h binary side-format: events written, read back (with a count limit),
+    results written and decoded column by column."""
+    lib.farms_bin_read.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(Events), C.c_char_p, C.c_size_t]
+    lib.farms_bin_write_events.argtypes = [C.c_char_p, C.c_uint64] + [C.c_void_p] * 4
+    lib.farms_bin_write.argtypes = [C.c_char_p, C.c_uint64] + [C.c_void_p] * 11
+    rng = np.random.default_rng(3)
+    n = 1000
+    x = rng.integers(0, 1280, n).astype(np.uint16)
+    y = rng.integers(0, 720, n).astype(np.uint16)
+    t = np.sort(rng.integers(1000, 2**40, n)).astype(np.uint64)
+    p = rng.integers(0, 2, n).astype(np.uint8)
+    path = str(tmp_path / "ev.evb")
+    assert lib.farms_bin_write_events(path.encode(), n, x.ctypes.data, y.ctypes.data, t.ctypes.data, p.ctypes.data) == 0
+    for take in (n, 137, 0):
+        ev = Events()
+        err = C.create_string_buffer(256)
+        assert lib.farms_bin_read(path.encode(), take, C.byref(ev), err, 256) == 0, err.value
+        assert ev.n == take
+        for k, ref in (("x", x), ("y", y), ("t", t), ("xi", x), ("yi", y), ("pol", p)):
+            got = np.ctypeslib.as_array(getattr(ev, k), shape=(max(take, 1),))[:take]
+            assert np.array_equal(got, ref[:take].astype(got.dtype)), k
+        lib.farms_text_free(C.byref(ev))
+    bad = str(tmp_path / "bad.evb")
+    open(bad, "wb").write(b"not an event file")
+    ev = Events()
+    err = C.create_string_buffer(256)
+    assert lib.farms_bin_read(bad.encode(), n, C.byref(ev), err, 256) == -1 and b"FARMSEV1" in err.value
+    # results
+    cols = [rng.standard_normal(n) for _ in range(6)]
+    t_rel = (t - t[0]).astype(np.uint32)
+    scale = (rng.integers(0, 11, n) * 5).astype(np.uint8)
+    xi, yi, pol = x.astype(np.int32), y.astype(np.int32), p.astype(np.int32)
+    out = str(tmp_path / "res.bin")
+    assert lib.farms_bin_write(out.encode(), n, xi.ctypes.data, yi.ctypes.data, t_rel.ctypes.data, pol.ctypes.data,
+                               *[c.ctypes.data for c in cols], scale.ctypes.data) == 0
+    raw = open(out, "rb").read()
+    assert raw[:8] == b"FARMSOU1" and int(np.frombuffer(raw, np.uint64, 1, 8)[0]) == n
+    off = 16
+    for ref, dt in ((x, np.uint16), (y, np.uint16), (t_rel, np.uint32), (p, np.uint8), (scale, np.uint8)):
+        got = np.frombuffer(raw, dt, n, off)
+        assert np.array_equal(got, ref.astype(dt))
+        off += n * np.dtype(dt).itemsize
+    for c in cols:
+        assert np.array_equal(np.frombuffer(raw, np.float64, n, off), c)
+        off += 8 * n
+    assert off == len(raw)
