@@ -172,3 +172,19 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "Mevents/s" and line["value"] > 0
     assert line["cpu_baseline"]["cores"] == 1 and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_viewer_reads_the_reference_output_format(capsys):
+    """tools/farms_view.py on a golden reference output: Appendix B's plane has one flow direction,
+    theta = 1.27934 rad = 73.3 deg, for all 184 valid events."""
+    import farms_view
+    import sys
+    argv = sys.argv
+    sys.argv = ["farms_view.py", os.path.join(ROOT, "tests", "golden", "kat_plane_16x12.ref.txt"), "--bins", "36"]
+    try:
+        assert farms_view.main() == 0
+    finally:
+        sys.argv = argv
+    out = capsys.readouterr().out
+    assert "192 events, 184 with flow" in out
+    assert "      70.0      184" in out and "circular spread: local 0.0 deg, global 0.0 deg" in out
