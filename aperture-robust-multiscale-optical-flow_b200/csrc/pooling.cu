@@ -362,44 +362,68 @@ __device__ void stage_slab(const PoolArgs &A, SM &S, int s, int slot, const Regi
   const uint32_t total = S.run_o[nrun];
   const double *pay_cx = A.pay + A.m, *pay_cy = A.pay + 2 * A.m;
   uint32_t out_base = 0;
-  for (uint32_t r0 = 0; r0 < total; r0 += WARPS * 32) {
-    const uint32_t f = r0 + tid;
-    bool pass = false;
-    uint32_t pos = 0;
-    uint4 rec = make_uint4(0, 0, 0, 0);
-    if (f < total) {
-      int c = 0;
-      while (c + 1 < nrun && S.run_o[c + 1] <= f) c++;
-      pos = S.run_s[c] + (f - S.run_o[c]);
-      rec = A.rec[pos];
-      int x = (int)(rec.x & 0xffffu), y = (int)(rec.x >> 16);
-      if (c < nrun0) {
-        pass = x >= R.rx0 && x <= R.rx1 && y >= R.ry0 && y <= R.ry1;
+  // two records per thread and trip (flat positions r0 + tid and r0 + THREADS + tid): one pair of barriers per
+  // 2 * THREADS records, and the index record and both payload values of a record are requested together
+  constexpr int THREADS = WARPS * 32;
+  for (uint32_t r0 = 0; r0 < total; r0 += 2 * THREADS) {
+    bool pass[2] = {false, false};
+    uint4 rec[2];
+    double cxv[2] = {0.0, 0.0}, cyv[2] = {0.0, 0.0};
+    int cc[2] = {0, 0};
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const uint32_t f = r0 + e * THREADS + tid;
+      rec[e] = make_uint4(0, 0, 0, 0);
+      if (f < total) {
+        int c = 0;
+        while (c + 1 < nrun && S.run_o[c + 1] <= f) c++;
+        const uint32_t pos = S.run_s[c] + (f - S.run_o[c]);
+        rec[e] = A.rec[pos];
+        cxv[e] = pay_cx[pos];
+        cyv[e] = pay_cy[pos];
+        cc[e] = c;
+        pass[e] = true;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      int x = (int)(rec[e].x & 0xffffu), y = (int)(rec[e].x >> 16);
+      if (cc[e] < nrun0) {
+        pass[e] = pass[e] && x >= R.rx0 && x <= R.rx1 && y >= R.ry0 && y <= R.ry1;
       } else {
-        pass = x >= R.ax0 && x <= R.ax1 && y <= R.ay1;
+        pass[e] = pass[e] && x >= R.ax0 && x <= R.ax1 && y <= R.ay1;
         x -= 1;
         y += H;
       }
       // superseded at its pixel (or past 500 us) before the first event of the round: dead for every target
-      pass = pass && rec.w > i_round;
-      rec.x = (uint32_t)x | ((uint32_t)y << 16);
+      pass[e] = pass[e] && rec[e].w > i_round;
+      rec[e].x = (uint32_t)x | ((uint32_t)y << 16);
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, pass);
-    if (lane == 0) S.wcount[warp] = __popc(bal);
+    const unsigned bal0 = __ballot_sync(0xffffffffu, pass[0]), bal1 = __ballot_sync(0xffffffffu, pass[1]);
+    if (lane == 0) S.wcount[warp] = (uint32_t)__popc(bal0) | ((uint32_t)__popc(bal1) << 16);
     __syncthreads();
-    uint32_t pre = 0, all = 0;
+    uint32_t pre0 = 0, pre1 = 0, all0 = 0, all1 = 0;
 #pragma unroll
     for (int w = 0; w < WARPS; w++) {
       const uint32_t cw = S.wcount[w];
-      if (w < warp) pre += cw;
-      all += cw;
+      if (w < warp) {
+        pre0 += cw & 0xffffu;
+        pre1 += cw >> 16;
+      }
+      all0 += cw & 0xffffu;
+      all1 += cw >> 16;
     }
-    const uint32_t o = out_base + pre + __popc(bal & ((1u << lane) - 1u));
-    if (pass && o < (uint32_t)CAP) {
-      S.ra[slot][o] = make_uint4(rec.x, rec.z, rec.w - rec.z, __float_as_uint(__double2float_rn(pay_cx[pos])));
-      S.rb[slot][o] = __double2float_rn(pay_cy[pos]);
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t o0 = out_base + pre0 + __popc(bal0 & lt), o1 = out_base + all0 + pre1 + __popc(bal1 & lt);
+    if (pass[0] && o0 < (uint32_t)CAP) {
+      S.ra[slot][o0] = make_uint4(rec[0].x, rec[0].z, rec[0].w - rec[0].z, __float_as_uint(__double2float_rn(cxv[0])));
+      S.rb[slot][o0] = __double2float_rn(cyv[0]);
     }
-    out_base += all;
+    if (pass[1] && o1 < (uint32_t)CAP) {
+      S.ra[slot][o1] = make_uint4(rec[1].x, rec[1].z, rec[1].w - rec[1].z, __float_as_uint(__double2float_rn(cxv[1])));
+      S.rb[slot][o1] = __double2float_rn(cyv[1]);
+    }
+    out_base += all0 + all1;
     __syncthreads();
   }
   const uint32_t cnt = min(out_base, (uint32_t)CAP);
