@@ -334,29 +334,29 @@ __device__ void stage_slab(const PoolArgs &A, SM &S, int s, int slot, const Regi
   const int nrun1 = R.ay1 >= 0 ? atx1 - atx0 + 1 : 0;
   const int nrun = nrun0 + nrun1;
   __syncthreads();  // previous users of run_s/run_o/wcount and of this slot are done
-  if (tid < nrun) {
+  if (tid < 32) {  // warp 0: one run descriptor per lane, offsets by a warp scan (nrun <= 24)
     const int c = tid;
-    uint32_t a, b;
+    uint32_t a = 0, b = 0;
     if (c < nrun0) {
       const size_t cb = (size_t)s * NT + (size_t)(tx0 + c) * nty;
       a = A.cell_start[cb + ty0];
       b = A.cell_start[cb + ty1 + 1];
-    } else {
+    } else if (c < nrun) {
       const size_t cb = (size_t)s * NT + (size_t)(atx0 + c - nrun0) * nty;
       a = A.cell_start[cb];
       b = A.cell_start[cb + (R.ay1 >> ts) + 1];
     }
-    S.run_s[c] = a;
-    S.run_o[c + 1] = b - a;  // lengths first, prefix below
-  }
-  __syncthreads();
-  if (tid == 0) {
-    uint32_t o = 0;
-    S.run_o[0] = 0;
-    for (int c = 0; c < nrun; c++) {
-      o += S.run_o[c + 1];
-      S.run_o[c + 1] = o;
+    uint32_t inc = b - a;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
     }
+    if (c < nrun) {
+      S.run_s[c] = a;
+      S.run_o[c + 1] = inc;
+    }
+    if (c == 0) S.run_o[0] = 0;
   }
   __syncthreads();
   const uint32_t total = S.run_o[nrun];
