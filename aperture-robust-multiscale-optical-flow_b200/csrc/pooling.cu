@@ -296,7 +296,7 @@ constexpr int TK_PAD = 64;     // the pooling loop reads 4 x 16 records at a tim
 #endif
 constexpr int TK_SEG = FARMS_TK_SEG;  // slabs per work item
 constexpr int TK_MAXT = 128;   // targets handled per round and slab
-constexpr int TK_MAXRUN = 24;  // tile-column runs of a region: <= 10 for rows < H plus <= 10 aliased
+constexpr int TK_MAXRUN = 20;  // tile-column runs of a region: <= 10 for rows < H plus <= 10 aliased
 constexpr float TK_TIE_TOL = 2e-5f;
 
 template <int WARPS, int CAP, int NSL>
@@ -307,7 +307,10 @@ struct TileSmem {
   float rb[(4 + NSL)][CAP];
   float4 acc[WARPS][FARMS_NSCALES][32];   // per-lane ring partials: len, lcx, lcy, count
   uint32_t tlist[NSL][TK_MAXT];
-  uint32_t run_s[TK_MAXRUN], run_o[TK_MAXRUN + 1];
+  // staging pass: run descriptors of all slabs being staged (start in the index, flat offset, slab | aliased << 7)
+  uint32_t run_s[(4 + NSL) * TK_MAXRUN], run_o[(4 + NSL) * TK_MAXRUN + 1];
+  uint8_t run_info[(4 + NSL) * TK_MAXRUN];
+  uint32_t slab_f[(4 + NSL) + 1], slab_pre[(4 + NSL) + 1];  // per staged slab: first flat position, passes before it
   uint32_t wcount[WARPS];
   int tag[(4 + NSL)];
   int count[(4 + NSL)];
@@ -321,11 +324,15 @@ struct Region {  // pixels an owner tile can reach, as physical rectangles
   int ax0, ax1, ay1;       // aliased part (k = 1): physical x in [ax0, ax1], y in [0, ay1]; empty if ay1 < 0
 };
 
-// Stage the flow events of dense slab `s` inside region R into ring slot `slot`, preserving index order
-// (ordered compaction => deterministic summation order).  Aliased events are stored with their LOGICAL
-// window coordinates (x - 1, y + H) so that the pooling loop needs no special case.
-template <class SM, int WARPS, int CAP>
-__device__ void stage_slab(const PoolArgs &A, SM &S, int s, int slot, const Region &R, uint32_t i_round) {
+// Stage the flow events of the dense slabs s0 .. s1 inside region R into their ring slots (slab s -> slot
+// s mod ring) in ONE pass over the concatenation of their index runs, preserving index order inside every slab
+// (ordered compaction => deterministic summation order).  One pass for all slabs of a round matters for sparse
+// streams, where a slab holds a few dozen records and the fixed cost of a pass (barriers, L2 latency) dominates.
+// Aliased events are stored with their LOGICAL window coordinates (x - 1, y + H) so that the pooling loop needs
+// no special case.
+template <class SM, int WARPS, int CAP, int NSL>
+__device__ void stage_slabs(const PoolArgs &A, SM &S, int s0, int s1, const Region &R, uint32_t i_round) {
+  constexpr int THREADS = WARPS * 32, RING = 4 + NSL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ts = A.g.tile_shift, nty = A.g.nty, NT = A.g.ntx * A.g.nty, H = A.g.H;
   const int tx0 = R.rx0 >> ts, tx1 = R.rx1 >> ts, ty0 = R.ry0 >> ts, ty1 = R.ry1 >> ts;
@@ -333,62 +340,86 @@ __device__ void stage_slab(const PoolArgs &A, SM &S, int s, int slot, const Regi
   const int atx0 = R.ax0 >> ts, atx1 = R.ax1 >> ts;
   const int nrun1 = R.ay1 >= 0 ? atx1 - atx0 + 1 : 0;
   const int nrun = nrun0 + nrun1;
-  __syncthreads();  // previous users of run_s/run_o/wcount and of this slot are done
-  if (tid < 32) {  // warp 0: one run descriptor per lane, offsets by a warp scan (nrun <= 24)
-    const int c = tid;
-    uint32_t a = 0, b = 0;
+  const int nsl = s1 - s0 + 1, nruns = nsl * nrun;
+  __syncthreads();  // previous users of the run tables, of wcount and of these slots are done
+  for (int q = tid; q < nruns; q += THREADS) {
+    const int sl = q / nrun, c = q - sl * nrun;
+    uint32_t a, b;
     if (c < nrun0) {
-      const size_t cb = (size_t)s * NT + (size_t)(tx0 + c) * nty;
+      const size_t cb = (size_t)(s0 + sl) * NT + (size_t)(tx0 + c) * nty;
       a = A.cell_start[cb + ty0];
       b = A.cell_start[cb + ty1 + 1];
-    } else if (c < nrun) {
-      const size_t cb = (size_t)s * NT + (size_t)(atx0 + c - nrun0) * nty;
+    } else {
+      const size_t cb = (size_t)(s0 + sl) * NT + (size_t)(atx0 + c - nrun0) * nty;
       a = A.cell_start[cb];
       b = A.cell_start[cb + (R.ay1 >> ts) + 1];
     }
-    uint32_t inc = b - a;
+    S.run_s[q] = a;
+    S.run_o[q + 1] = b - a;  // lengths first, offsets below
+    S.run_info[q] = (uint8_t)(sl | (c >= nrun0 ? 0x80 : 0));
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive offsets of the runs in the flat list: consecutive runs per lane + a warp scan
+    constexpr int RPL = (RING * TK_MAXRUN + 31) / 32;
+    uint32_t loc[RPL], sum = 0;
+#pragma unroll
+    for (int j = 0; j < RPL; j++) {
+      const int q = lane * RPL + j;
+      loc[j] = q < nruns ? S.run_o[q + 1] : 0u;
+      sum += loc[j];
+    }
+    uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += t;
     }
-    if (c < nrun) {
-      S.run_s[c] = a;
-      S.run_o[c + 1] = inc;
+    uint32_t run = inc - sum;
+#pragma unroll
+    for (int j = 0; j < RPL; j++) {
+      const int q = lane * RPL + j;
+      run += loc[j];
+      if (q < nruns) S.run_o[q + 1] = run;
     }
-    if (c == 0) S.run_o[0] = 0;
+    if (lane == 0) S.run_o[0] = 0;
   }
   __syncthreads();
-  const uint32_t total = S.run_o[nrun];
+  const uint32_t total = S.run_o[nruns];
+  if (tid <= nsl) {
+    S.slab_f[tid] = tid < nsl ? S.run_o[tid * nrun] : total;
+    S.slab_pre[tid] = 0;
+  }
   const double *pay_cx = A.pay + A.m, *pay_cy = A.pay + 2 * A.m;
   uint32_t out_base = 0;
-  // two records per thread and trip (flat positions r0 + tid and r0 + THREADS + tid): one pair of barriers per
-  // 2 * THREADS records, and the index record and both payload values of a record are requested together
-  constexpr int THREADS = WARPS * 32;
+  // two records per thread and trip (flat positions r0 + tid and r0 + THREADS + tid): the index record and both
+  // payload values of a record are requested together
   for (uint32_t r0 = 0; r0 < total; r0 += 2 * THREADS) {
     bool pass[2] = {false, false};
     uint4 rec[2];
     double cxv[2] = {0.0, 0.0}, cyv[2] = {0.0, 0.0};
-    int cc[2] = {0, 0};
+    uint32_t info[2] = {0, 0};
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       const uint32_t f = r0 + e * THREADS + tid;
       rec[e] = make_uint4(0, 0, 0, 0);
       if (f < total) {
-        int c = 0;
-        while (c + 1 < nrun && S.run_o[c + 1] <= f) c++;
-        const uint32_t pos = S.run_s[c] + (f - S.run_o[c]);
+        int lo = 0, hi = nruns - 1;  // last run whose offset is <= f
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (S.run_o[mid] <= f) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t pos = S.run_s[lo] + (f - S.run_o[lo]);
         rec[e] = A.rec[pos];
         cxv[e] = pay_cx[pos];
         cyv[e] = pay_cy[pos];
-        cc[e] = c;
+        info[e] = S.run_info[lo];
         pass[e] = true;
       }
     }
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       int x = (int)(rec[e].x & 0xffffu), y = (int)(rec[e].x >> 16);
-      if (cc[e] < nrun0) {
+      if (!(info[e] & 0x80u)) {
         pass[e] = pass[e] && x >= R.rx0 && x <= R.rx1 && y >= R.ry0 && y <= R.ry1;
       } else {
         pass[e] = pass[e] && x >= R.ax0 && x <= R.ax1 && y <= R.ay1;
@@ -414,25 +445,46 @@ __device__ void stage_slab(const PoolArgs &A, SM &S, int s, int slot, const Regi
       all1 += cw >> 16;
     }
     const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t o0 = out_base + pre0 + __popc(bal0 & lt), o1 = out_base + all0 + pre1 + __popc(bal1 & lt);
-    if (pass[0] && o0 < (uint32_t)CAP) {
-      S.ra[slot][o0] = make_uint4(rec[0].x, rec[0].z, rec[0].w - rec[0].z, __float_as_uint(__double2float_rn(cxv[0])));
-      S.rb[slot][o0] = __double2float_rn(cyv[0]);
+    // passes before this record in the flat order
+    const uint32_t g0 = out_base + pre0 + __popc(bal0 & lt), g1 = out_base + all0 + pre1 + __popc(bal1 & lt);
+    // the thread that holds the first flat position of a slab publishes how many passes precede that slab
+    // (several empty slabs can share one first position)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const uint32_t f = r0 + e * THREADS + tid;
+      if (f < total)
+        for (int sl = 0; sl < nsl; sl++)
+          if (S.slab_f[sl] == f) S.slab_pre[sl] = e ? g1 : g0;
     }
-    if (pass[1] && o1 < (uint32_t)CAP) {
-      S.ra[slot][o1] = make_uint4(rec[1].x, rec[1].z, rec[1].w - rec[1].z, __float_as_uint(__double2float_rn(cxv[1])));
-      S.rb[slot][o1] = __double2float_rn(cyv[1]);
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int sl = (int)(info[e] & 0x7fu);
+      const uint32_t o = (e ? g1 : g0) - S.slab_pre[sl];
+      if (pass[e] && o < (uint32_t)CAP) {
+        const int slot = (s0 + sl) % RING;
+        S.ra[slot][o] = make_uint4(rec[e].x, rec[e].z, rec[e].w - rec[e].z, __float_as_uint(__double2float_rn(cxv[e])));
+        S.rb[slot][o] = __double2float_rn(cyv[e]);
+      }
     }
     out_base += all0 + all1;
-    __syncthreads();
   }
-  const uint32_t cnt = min(out_base, (uint32_t)CAP);
-  // entries the unrolled loop may touch past the end: span 0 never passes
-  if (tid < TK_PAD) S.ra[slot][cnt + tid] = make_uint4(0u, 0u, 0u, 0u);
-  if (tid == 0) {
-    S.tag[slot] = s;
-    S.count[slot] = (int)cnt;
-    S.overflow[slot] = out_base > (uint32_t)CAP;
+  __syncthreads();
+  // slabs without any raw record at or after their first position (trailing empties) start at the end
+  if (tid <= nsl && S.slab_f[tid] >= total) S.slab_pre[tid] = out_base;
+  __syncthreads();
+  if (tid < nsl) {
+    const uint32_t raw = S.slab_pre[tid + 1] - S.slab_pre[tid];
+    const int slot = (s0 + tid) % RING;
+    S.tag[slot] = s0 + tid;
+    S.count[slot] = (int)min(raw, (uint32_t)CAP);
+    S.overflow[slot] = raw > (uint32_t)CAP;
+  }
+  // entries the unrolled pooling loop may touch past the end of a slot: span 0 never passes
+  for (int q = tid; q < nsl * TK_PAD; q += THREADS) {
+    const int sl = q / TK_PAD;
+    const uint32_t cnt = min(S.slab_pre[sl + 1] - S.slab_pre[sl], (uint32_t)CAP);
+    S.ra[(s0 + sl) % RING][cnt + (q - sl * TK_PAD)] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -577,11 +629,11 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
           s_last = max(s_last, S.dhi[w]);
         }
       }
-      for (int s = s_first; s <= s_last; s++) {
-        const int slot = s % (4 + NSL);
-        if (S.tag[slot] != s) stage_slab<SM, WARPS, CAP>(A, S, s, slot, R, i_round);  // uniform: tag is read after a barrier
-        __syncthreads();
-      }
+      // staged slabs are a contiguous range ending at the last staged slab, so what is missing is a suffix
+      int s_new = s_first;
+      while (s_new <= s_last && S.tag[s_new % (4 + NSL)] == s_new) s_new++;  // uniform: tags are read after a barrier
+      if (s_new <= s_last) stage_slabs<SM, WARPS, CAP, NSL>(A, S, s_new, s_last, R, i_round);
+      __syncthreads();
       if (tid < NSL) {
         int o = 0;
         for (int s = S.dlo[tid]; s <= S.dhi[tid]; s++) o |= S.overflow[s % (4 + NSL)];
@@ -1346,7 +1398,6 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
                    double flow_per_slab, double *global_r, double *global_theta, uint8_t *scale,
                    unsigned int *work_counter, unsigned long long *cand_count, int num_sms, cudaStream_t s) {
   if (!m) return 0;
-  (void)flow_per_slab;
   int launches = 0;
   PoolArgs A;
   A.rec = rec; A.pay = pay; A.cell_start = cell_start; A.slab_ids = slab_ids; A.done = done;
@@ -1360,7 +1411,12 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
     if (fast == 2) launch_bits(A, nslabs, num_sms, s);  // bit-table variant: 8 warps, 2 CTAs per SM, ~110 KB each
     else if (fast == 3) launch_tile<16, 768, 4, 1, false>(A, nslabs, num_sms, s);  // 16 warps, 1 CTA per SM, ~222 KB
     else {
-      launch_tile<8, 512, 2, 2, false>(A, nslabs, num_sms, s);  // 8 warps, 2 CTAs per SM, ~112 KB each
+      // flow events a slab holds inside one (32+100)^2 region, from the batch average
+      const double per_region = flow_per_slab * 17424.0 / ((double)g.W * (double)g.H);
+      if (per_region < 110.0)  // sparse stream: 8 slabs per round keep the round's task list full (160-record slots)
+        launch_tile<8, 160, 8, 2, false>(A, nslabs, num_sms, s);
+      else
+        launch_tile<8, 512, 2, 2, false>(A, nslabs, num_sms, s);  // 8 warps, 2 CTAs per SM, ~112 KB each
       // rounds whose staging overflowed those slots (locally dense scenes) get a second chance with 640-record
       // slots before the general kernel takes what is left
       A.work_counter = work_counter + 2;
