@@ -490,49 +490,60 @@ __device__ void stage_slabs(const PoolArgs &A, SM &S, int s0, int s1, const Regi
 
 // Like finish_event, but from FP32 partial sums: writes only when the decision is safe; returns (in every lane
 // of the segment) whether the event was finished.
+// The nested-square sums are an inclusive scan over the ring lanes (4 shuffle steps instead of 11 broadcasts).
+// A scan associates differently from the reference's running sum, so "an empty ring adds exactly nothing" is
+// enforced through the counts instead: a scale whose count equals the previous scale's holds the same
+// contributors, has the same mean in the reference's arithmetic and can never beat it under the strict '>'
+// (src/vFlow.cpp:1054); only scales that add contributors compete.
 __device__ __forceinline__ bool finish_event_checked(const PoolArgs &A, int sub, double rl, double rx, double ry,
-                                                     double rn, int out_index, bool have) {
-  double Sl = 0.0, Sx = 0.0, Sy = 0.0, Sn = 0.0;
-  double myl = 0.0, myx = 0.0, myy = 0.0, myn = 0.0;
+                                                     int rn, int out_index, bool have) {
+  double Sl = rl, Sx = rx, Sy = ry;
+  int Sn = rn;
 #pragma unroll
-  for (int k = 0; k < FARMS_NSCALES; k++) {
-    Sn += __shfl_sync(0xffffffffu, rn, k, 16);
-    Sl += __shfl_sync(0xffffffffu, rl, k, 16);
-    Sx += __shfl_sync(0xffffffffu, rx, k, 16);
-    Sy += __shfl_sync(0xffffffffu, ry, k, 16);
-    if (sub == k) {
-      myl = Sl; myx = Sx; myy = Sy; myn = Sn;
+  for (int o = 1; o < 16; o <<= 1) {
+    const double pl = __shfl_up_sync(0xffffffffu, Sl, o, 16), px = __shfl_up_sync(0xffffffffu, Sx, o, 16),
+                 py = __shfl_up_sync(0xffffffffu, Sy, o, 16);
+    const int pn = __shfl_up_sync(0xffffffffu, Sn, o, 16);
+    if (sub >= o) {
+      Sl += pl;
+      Sx += px;
+      Sy += py;
+      Sn += pn;
     }
   }
-  const double mean = (sub < FARMS_NSCALES && myn > 0.0) ? myl / myn : 0.0;
-  double best = 0.0, bn = 0.0;
-  int bk = -1;
+  const int nprev = __shfl_up_sync(0xffffffffu, Sn, 1, 16);
+  const bool scale_lane = sub < FARMS_NSCALES && Sn > 0;
+  const float mean = scale_lane ? __fdiv_rn((float)Sl, (float)Sn) : 0.f;
+  const bool competes = scale_lane && (sub == 0 || Sn != nprev);
+  // first maximum over the competing lanes (strict '>' from 0, :1047-1059)
+  float best = competes ? mean : 0.f;
+  int bk = (competes && mean > 0.f) ? sub : 99;
 #pragma unroll
-  for (int k = 0; k < FARMS_NSCALES; k++) {
-    const double mk = __shfl_sync(0xffffffffu, mean, k, 16);
-    const double nk = __shfl_sync(0xffffffffu, myn, k, 16);
-    if (mk > best) {
-      best = mk;
-      bk = k;
-      bn = nk;
+  for (int o = 8; o; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o, 16);
+    const int ok = __shfl_xor_sync(0xffffffffu, bk, o, 16);
+    if (ob > best || (ob == best && ok < bk)) {
+      best = ob;
+      bk = ok;
     }
   }
+  const bool found = bk < FARMS_NSCALES;
+  const int srcl = found ? bk : 0;
+  const int bn = __shfl_sync(0xffffffffu, Sn, srcl, 16);
   // is any other scale (with a different contributor set) within the FP32 noise of the winner?
-  const bool rival = sub < FARMS_NSCALES && myn != bn && fabs(mean - best) <= (double)TK_TIE_TOL * best;
+  const bool rival = scale_lane && Sn != bn && fabsf(mean - best) <= TK_TIE_TOL * best;
   const unsigned seg = 0xffffu << (threadIdx.x & 16);
   const bool any_rival = (__ballot_sync(0xffffffffu, rival) & seg) != 0u;
-  const int srcl = bk < 0 ? 0 : bk;
-  const double wx = __shfl_sync(0xffffffffu, myx, srcl, 16), wy = __shfl_sync(0xffffffffu, myy, srcl, 16),
-               wn = __shfl_sync(0xffffffffu, myn, srcl, 16);
-  bool safe = have && bk >= 0 && !any_rival && best > 1e-30 && best < 1e30;
+  const double wx = __shfl_sync(0xffffffffu, Sx, srcl, 16), wy = __shfl_sync(0xffffffffu, Sy, srcl, 16);
+  bool safe = have && found && !any_rival && best > 1e-30f && best < 1e30f;
   // mean vector much shorter than the mean length: the FP32 sums cancelled, let the exact path do it
-  const double bl = best * wn;
+  const double bl = (double)best * (double)bn;
   safe = safe && (wx * wx + wy * wy) > 1e-4 * bl * bl;
   if (sub == 0 && safe) {
     // k_pool_finish divides by the count and takes sqrt / atan2 (src/vFlow.cpp:365-366)
     A.global_r[out_index] = wx;
     A.global_theta[out_index] = wy;
-    A.fin[out_index] = (uint32_t)wn | ((uint32_t)bk << 16);
+    A.fin[out_index] = (uint32_t)bn | ((uint32_t)bk << 16);
   }
   return safe;
 }
@@ -721,20 +732,30 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
             }
           }
           __syncwarp();
-          // sub-lane k < 11 of each half combines ring k's 16 per-lane partials in FP64
-          double rl = 0.0, rx = 0.0, ry = 0.0, rn = 0.0;
+          // sub-lane k < 11 of each half combines ring k's 16 per-lane partials: four at a time in FP32, the four
+          // group sums in FP64 (the counts are exact either way)
+          double rl = 0.0, rx = 0.0, ry = 0.0;
+          float rnf = 0.f;
           if (sub < FARMS_NSCALES) {
-#pragma unroll 8
-            for (int q = 0; q < 16; q++) {
-              const float4 v = S.acc[warp][sub][(half << 4) | ((q + sub) & 15)];
-              rl += (double)v.x;
-              rx += (double)v.y;
-              ry += (double)v.z;
-              rn += (double)v.w;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; q4++) {
+              float4 g = S.acc[warp][sub][(half << 4) | ((4 * q4 + sub) & 15)];
+#pragma unroll
+              for (int q = 1; q < 4; q++) {
+                const float4 v = S.acc[warp][sub][(half << 4) | ((4 * q4 + q + sub) & 15)];
+                g.x += v.x;
+                g.y += v.y;
+                g.z += v.z;
+                g.w += v.w;
+              }
+              rl += (double)g.x;
+              rx += (double)g.y;
+              ry += (double)g.z;
+              rnf += g.w;
             }
           }
           __syncwarp();
-          const bool fin = finish_event_checked(A, sub, rl, rx, ry, rn, (int)ii - A.h, have);
+          const bool fin = finish_event_checked(A, sub, rl, rx, ry, (int)rnf, (int)ii - A.h, have);
 
           if (sub == 0 && fin) A.done[tpos] = 1;
           // ---- undecided targets (a rival scale within the FP32 noise, cancelling vectors): pool them again
