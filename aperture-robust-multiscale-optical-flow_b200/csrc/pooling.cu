@@ -671,30 +671,63 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
 
           }
         __syncthreads();
-        // tasks = pairs of targets of the same slab (both halves of a warp then share their loop bounds)
-        uint32_t tstart[NSL + 1];
-        tstart[0] = 0;
+        // Tasks: first pairs of targets of the same slab (lanes 0-15 pool one event, lanes 16-31 the next; both
+        // halves share their loop bounds), then "solo" targets pooled by the two halves together, each half taking
+        // every other 64-record trip (half the time of a pair task).  The odd target of a slab is a solo, and so
+        // are the pairs that would not divide evenly among the warps when they are at most half a wave: the
+        // round then ends half a task later instead of a whole one.
+        // (Rounds of many slabs -- the sparse-stream variant -- keep the plain pairing: there an odd target shares
+        // its warp with an idle half.)
+        constexpr bool SOLOS = NSL <= 2;
+        uint32_t pstart[NSL + 1], sstart[NSL + 1], npair[NSL];
+        uint32_t P = 0;
 #pragma unroll
-        for (int w = 0; w < NSL; w++) tstart[w + 1] = tstart[w] + ((S.ntg[w] + 1) >> 1);
-        const uint32_t tasks = tstart[NSL];
+        for (int w = 0; w < NSL; w++) {
+          npair[w] = SOLOS ? S.ntg[w] >> 1 : (S.ntg[w] + 1) >> 1;
+          P += npair[w];
+        }
+        uint32_t extra = SOLOS ? P % WARPS : 0u;
+        if (extra > WARPS / 2) extra = 0;
+#pragma unroll
+        for (int w = NSL - 1; w >= 0; w--) {
+          const uint32_t take = min(extra, npair[w]);
+          npair[w] -= take;
+          extra -= take;
+        }
+        pstart[0] = sstart[0] = 0;
+#pragma unroll
+        for (int w = 0; w < NSL; w++) {
+          pstart[w + 1] = pstart[w] + npair[w];
+          sstart[w + 1] = sstart[w] + (SOLOS ? S.ntg[w] - 2 * npair[w] : 0u);
+        }
+        const uint32_t tasks_p = pstart[NSL], tasks = tasks_p + sstart[NSL];
 
-        // ---- two targets per warp: lanes 0-15 pool one event, lanes 16-31 the next ----
         for (;;) {
           uint32_t k = 0;
           if (lane == 0) k = atomicAdd(&S.tnext, 1u);
           k = __shfl_sync(0xffffffffu, k, 0);
           if (k >= tasks) break;
+          const bool solo = k >= tasks_p;
           int w = 0;
+          uint32_t kk;
+          if (!solo) {
 #pragma unroll
-          for (int q = 1; q < NSL; q++) w += (k >= tstart[q]) ? 1 : 0;
-          const uint32_t kk = (k - tstart[w]) * 2 + half, nt = S.ntg[w];
-          const bool have = kk < nt;
-          const uint32_t tpos = S.tlist[w][have ? kk : nt - 1];
+            for (int q = 1; q < NSL; q++) w += (k >= pstart[q]) ? 1 : 0;
+            kk = (k - pstart[w]) * 2 + half;
+          } else {
+            const uint32_t j = k - tasks_p;
+#pragma unroll
+            for (int q = 1; q < NSL; q++) w += (j >= sstart[q]) ? 1 : 0;
+            kk = 2 * (pstart[w + 1] - pstart[w]) + (j - sstart[w]);
+          }
+          const uint32_t nt = S.ntg[w];
+          const bool have = solo ? half == 0 : kk < nt;  // this half owns a target's result
+          const uint32_t tpos = S.tlist[w][kk < nt ? kk : nt - 1];
           const uint4 r = A.rec[tpos];
           const int xi = (int)(r.x & 0xffffu), yi = (int)(r.x >> 16);
           const uint32_t ii = r.z;
           const int jlo = max(0, yi - FARMS_MAX_WINDOW), jhi = min(yi + FARMS_MAX_WINDOW, W - 1);  // :1000 (sic)
-          const bool rows_ok = have && jhi >= jlo;  // jhi < jlo when W < H: no cell qualifies
+          const bool rows_ok = jhi >= jlo;  // jhi < jlo when W < H: no cell qualifies
           const uint32_t jspan = rows_ok ? (uint32_t)(jhi - jlo) : 0u;
           const int ylo = rows_ok ? jlo : 0x7fff0000;  // makes (cy - ylo) huge => fails
           const int xoff = FARMS_MAX_WINDOW - xi;
@@ -705,7 +738,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
             const int slot = s % (4 + NSL);
             const int n = S.count[slot];
             ncand += (sub == 0 && have) ? n : 0;
-            for (int q0 = sub; q0 < n; q0 += 64) {
+            for (int q0 = sub + (solo ? 64 * half : 0); q0 < n; q0 += solo ? 128 : 64) {
               uint4 c[4];
 #pragma unroll
               for (int u = 0; u < 4; u++) c[u] = S.ra[slot][q0 + 16 * u];  // padded: no bounds check
@@ -755,6 +788,12 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
             }
           }
           __syncwarp();
+          if (solo) {  // the two halves pooled disjoint trips of the same target
+            rl += __shfl_xor_sync(0xffffffffu, rl, 16);
+            rx += __shfl_xor_sync(0xffffffffu, rx, 16);
+            ry += __shfl_xor_sync(0xffffffffu, ry, 16);
+            rnf += __shfl_xor_sync(0xffffffffu, rnf, 16);
+          }
           const bool fin = finish_event_checked(A, sub, rl, rx, ry, (int)rnf, (int)ii - A.h, have);
 
           if (sub == 0 && fin) A.done[tpos] = 1;
