@@ -84,7 +84,8 @@ struct farms_ctx {
   bool d2h_pending[2] = {false, false};
   farms_timings tm{};
 
-  uint2 *sae = nullptr;
+  uint2 *sae = nullptr, *sae2 = nullptr;  // surface of active events; second copy for the two-stream plane fit
+  cudaStream_t fit_stream = nullptr;
   WorkSet ws[2];
   // halo store
   uint16_t *hx = nullptr, *hy = nullptr;
@@ -257,19 +258,34 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   if (((int *)c->h_small)[0]) return fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
 
   // ---- K3 plane fit, chunk by chunk against the chunk-end SAE snapshot ----
+  // Two surfaces and two streams: chunk k works on surface k mod 2 in stream k mod 2, so neighbouring chunks
+  // overlap (their kernels are short: launch gaps and tails would otherwise idle the GPU).  A surface skipped
+  // chunk k-1, so its advance step applies the chunks k-1 and k together.
   const size_t FIT_CHUNK = (size_t)c->fit_chunk;
-  if ((rc = ensure(c, c->fit_scratch, plane_fit_scratch_bytes(c->r, FIT_CHUNK)))) return rc;
+  const size_t scratch_bytes = (plane_fit_scratch_bytes(c->r, FIT_CHUNK) + 255) & ~(size_t)255;
+  if ((rc = ensure(c, c->fit_scratch, 2 * scratch_bytes))) return rc;
   FitParams fp{c->W, c->H, c->r, c->P, c->min_inl};
   FitOut fo{w.vx, w.vy, w.len, w.theta, w.lcx, w.lcy, w.valid, w.bw, w.inl, w.det};
-  for (size_t c0 = 0; c0 < m; c0 += FIT_CHUNK) {
+  CU(cudaMemcpyAsync(c->sae2, c->sae, c->npx * sizeof(uint2), cudaMemcpyDeviceToDevice, s));
+  CU(cudaEventRecord(c->ev_c0, s));
+  CU(cudaStreamWaitEvent(c->fit_stream, c->ev_c0, 0));
+  size_t prev_c0 = 0, nchunks = 0;
+  for (size_t c0 = 0; c0 < m; c0 += FIT_CHUNK, nchunks++) {
     const size_t c1 = std::min(m, c0 + FIT_CHUNK);
-    launch_sae_advance(c->sae, w.pixkeep, w.et, w.nextp, (int)c0, (int)c1, s);
+    const bool odd = (nchunks & 1) != 0;
+    cudaStream_t st = odd ? c->fit_stream : s;
+    uint2 *surf = odd ? c->sae2 : c->sae;
+    launch_sae_advance(surf, w.pixkeep, w.et, w.nextp, (int)(nchunks ? prev_c0 : c0), (int)c1, st);
     *L += 1;
     if (c1 > h) {
-      *L += launch_plane_fit(c->sae, w.prevp, w.ex, w.ey, w.et, (int)std::max(c0, h), (int)c1, fp, fo, c->d_counters,
-                             c->fit_scratch.p, s);
+      *L += launch_plane_fit(surf, w.prevp, w.ex, w.ey, w.et, (int)std::max(c0, h), (int)c1, fp, fo, c->d_counters,
+                             (char *)c->fit_scratch.p + (odd ? scratch_bytes : 0), st);
     }
+    prev_c0 = c0;
   }
+  CU(cudaEventRecord(c->ev_c1, c->fit_stream));
+  CU(cudaStreamWaitEvent(s, c->ev_c1, 0));
+  if (nchunks && !(nchunks & 1)) std::swap(c->sae, c->sae2);  // the last chunk ran on the second surface
   launch_sae_finalize(c->sae, w.pixkeep, w.nextp, (int)m, s);
   *L += 1;
   CU(cudaEventRecord(c->ev[EV_FIT], s));
@@ -542,6 +558,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   if (const char *e = getenv("FARMS_POOL_IMPL")) c->pool_impl = strcmp(e, "bits") == 0 ? 2 : strcmp(e, "tile1") == 0 ? 3 : 1;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&c->fit_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   for (int i = 0; i < EV_COUNT; i++)
     if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(FARMS_ERR_CUDA);
@@ -553,6 +570,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   }
   bool ok = true;
   ok &= cudaMalloc((void **)&c->sae, c->npx * sizeof(uint2)) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->sae2, c->npx * sizeof(uint2)) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->hx, HALO_CAP * 2) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->hy, HALO_CAP * 2) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->ht, HALO_CAP * 4) == cudaSuccess;
@@ -579,7 +597,7 @@ void farms_destroy(farms_ctx *c) {
   cudaDeviceSynchronize();
   free_owned(c->ws[0]);
   free_owned(c->ws[1]);
-  void *ps[] = {c->sae, c->hx, c->hy, c->ht, c->hm, c->hlen, c->hlcx, c->hlcy, c->d_err, c->d_counters, c->d_work,
+  void *ps[] = {c->sae, c->sae2, c->hx, c->hy, c->ht, c->hm, c->hlen, c->hlcx, c->hlcy, c->d_err, c->d_counters, c->d_work,
                 c->d_small, c->in_x[0], c->in_y[0], c->in_t[0], c->in_x[1], c->in_y[1], c->in_t[1], c->sort_temp.p,
                 c->scan_temp.p, c->cell_start.p, c->fit_scratch.p, c->surf_tmp.p, c->item_ovf.p};
   for (void *p : ps)
@@ -592,6 +610,7 @@ void farms_destroy(farms_ctx *c) {
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
   if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  if (c->fit_stream) cudaStreamDestroy(c->fit_stream);
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
