@@ -25,7 +25,7 @@ constexpr uint64_t DEFAULT_MAX_BATCH = 16ull << 20;
 constexpr uint32_t DEFAULT_SLACK_US = 1000;
 constexpr size_t HALO_CAP = 8ull << 20;       // events carried across a batch boundary at most
 #ifndef FARMS_FIT_CHUNK_LOG2
-#define FARMS_FIT_CHUNK_LOG2 17
+#define FARMS_FIT_CHUNK_LOG2 16
 #endif
 constexpr int FIT_CHUNK_MAX = 1 << FARMS_FIT_CHUNK_LOG2;  // events per SAE snapshot at most
 constexpr int FIT_CHUNK_MIN = 1 << 13;
@@ -64,9 +64,10 @@ struct farms_ctx {
   size_t npx = 0;
   int num_sms = 148;
   // Events per SAE snapshot.  A fit thread walks back one history link for every footprint cell that was hit
-  // again later in its chunk, so the chunk is kept to about a third of an event per pixel: 2^17 events at
-  // 1280x720, 2^15 at 346x260 (measured there: 2^13 73 ms, 2^14 46, 2^15 39, 2^16 49, 2^17 66 ms per 20 M events;
-  // small chunks are launch-bound, large ones walk ~100 dependent history links per event).
+  // again later in its chunk, so the chunk is kept to about a sixth of an event per pixel, at most 2^16 events:
+  // 2^16 at 1280x720 (measured with the two-stream overlap: 2^15 11.3 ms, 2^16 10.1, 2^17 10.7 per 20 M events),
+  // 2^14 at 346x260 (2^13 38.9 ms, 2^14 31.7, 2^15 33.4; without the overlap 2^17 took 66 ms).  Small chunks are
+  // launch-bound, large ones walk many dependent history links per event.
   int fit_chunk = FIT_CHUNK_MAX;
   int pool_impl = 1;  // 1 = staged-list fast path (k_pool_tile), 2 = bit-table variant (FARMS_POOL_IMPL=bits, A/B runs)
   cudaStream_t stream = nullptr;
@@ -553,7 +554,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   if (prop.major < 10) return bail(FARMS_ERR_CUDA);  // built for sm_100a only
   c->num_sms = prop.multiProcessorCount;
   c->fit_chunk = FIT_CHUNK_MIN;
-  while (c->fit_chunk < FIT_CHUNK_MAX && (size_t)c->fit_chunk * 3 < c->npx) c->fit_chunk *= 2;
+  while (c->fit_chunk < FIT_CHUNK_MAX && (size_t)c->fit_chunk * 6 < c->npx) c->fit_chunk *= 2;
   if (const char *e = getenv("FARMS_FIT_CHUNK")) c->fit_chunk = std::max(1024, atoi(e));  // tuning runs
   if (const char *e = getenv("FARMS_POOL_IMPL")) c->pool_impl = strcmp(e, "bits") == 0 ? 2 : strcmp(e, "tile1") == 0 ? 3 : 1;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
