@@ -12,13 +12,17 @@
 // between consecutive scales, and the scale sums are prefix sums over rings.  An empty ring adds exactly
 // nothing, so exact ties resolve to the smaller scale like the reference's strict '>' (src/vFlow.cpp:1054).
 //
-// Two kernels share that definition:
+// The kernels that share that definition:
 //   k_pool_tile  -- the fast path.  A CTA owns a 32x32-pixel tile for a run of time slabs and keeps the flow
-//                   events of the (32+100)^2 region of the last <= 5 slabs staged in shared memory; every
-//                   warp pools one event of the tile against the staged set.  Needs sorted timestamps
-//                   (so that the age test folds into an index bound) and windows that stay inside rows < H.
-//   k_pool_any   -- the general path straight from the global index: unsorted timestamps, windows whose
-//                   second coordinate runs past H (the reference's width-1 bound, below), overflowed tiles.
+//                   events of the (32+100)^2 region of the slabs its current round's windows span staged in
+//                   shared memory; every half-warp pools one event of the tile against the staged set with FP32
+//                   partial sums, and pools it again exactly (FP64) when the scale decision is not clear-cut.
+//                   Needs sorted timestamps (so that the age test folds into an index bound) and windows that
+//                   stay inside rows < 2H.  A flagged second pass with larger slots takes the rounds whose
+//                   staging overflowed; k_pool_finish turns the sums it leaves into globalR / globalTheta.
+//   k_pool_any   -- the general, exact path straight from the global index: unsorted timestamps, windows whose
+//                   second coordinate runs past 2H (the reference's width-1 bound, below), whatever is left.
+//   k_pool_bits  -- a measured alternative to k_pool_tile built on prefix bit tables (FARMS_POOL_IMPL=bits).
 //
 // Flat-index rule: the reference bounds the window's second coordinate by width-1
 // (src/vFlow.cpp:1000, 1113) and indexes _data[i*H + j] unchecked (include/EventMatrix.h:32-34), so a
@@ -283,10 +287,11 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
 // fast path: owner tiles with shared-memory staging, FP32 ring partials, exact decisions
 // ------------------------------------------------------------------------------------------------
 // Ring partial sums are kept in FP32 (half the shared memory of FP64 => twice the resident warps) and
-// combined in FP64.  That perturbs a scale's mean by < 1e-5 relative, so an event is only finished here when
+// combined in FP64.  That perturbs a scale's mean by < 1e-5 relative, so an event is only finished from them when
 // its arg-max over scales is decided by a margin > 2e-5 and its mean vector is not a cancellation residue;
-// everything else (measured: well under 1 % of events) is left to k_pool_any, which is exact.  Scales whose
-// extra rings are empty have bit-identical sums in both arithmetics, so exact ties behave like the reference.
+// everything else (measured: about 2 % of events) is pooled again in FP64 by the same half-warp.  Scales whose
+// extra rings are empty hold the same contributors (equal counts) and never compete, so exact ties behave like
+// the reference's strict '>'.
 constexpr int OT_SHIFT = 5, OT = 1 << OT_SHIFT;  // owner tile edge (pixels)
 // NSL (template parameter): consecutive slabs pooled per round (more events per round => fewer, fuller waves).
 // A 500-us window touches <= 5 slabs, so a round's windows span <= 4 + NSL staged slabs (the slot ring).
