@@ -294,10 +294,13 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
 // the reference's strict '>'.
 constexpr int OT_SHIFT = 5, OT = 1 << OT_SHIFT;  // owner tile edge (pixels)
 // NSL (template parameter): consecutive slabs pooled per round (more events per round => fewer, fuller waves).
-// A 500-us window touches <= 5 slabs, so a round's windows span <= 4 + NSL staged slabs (the slot ring).
+// A 500-us window reaches back TK_LB slabs at most, so a round's windows span <= TK_LB + NSL staged slabs (the slot
+// ring).
+constexpr int TK_LB = FARMS_SLAB_LOOKBACK;
+constexpr int TK_OVF_SHIFT = FARMS_SLAB_SHIFT >= 7 ? 1 : 2;  // slabs per bit of the overflow bitmap (32 bits / item)
 constexpr int TK_PAD = 64;     // the pooling loop reads 4 x 16 records at a time without bounds checks
 #ifndef FARMS_TK_SEG
-#define FARMS_TK_SEG 64
+#define FARMS_TK_SEG (32 << (FARMS_SLAB_SHIFT >= 7 ? 1 : 2))
 #endif
 constexpr int TK_SEG = FARMS_TK_SEG;  // slabs per work item
 constexpr int TK_MAXT = 128;   // targets handled per round and slab
@@ -308,18 +311,18 @@ template <int WARPS, int CAP, int NSL>
 struct TileSmem {
   // {x | y<<16 (logical window coordinates), idx, end - idx, |flow|cos as f32} and |flow|sin; |flow| itself is
   // recomputed from the two (4 bytes per staged record buy 23 % more records per slot)
-  uint4 ra[(4 + NSL)][CAP + TK_PAD];
-  float rb[(4 + NSL)][CAP];
+  uint4 ra[(TK_LB + NSL)][CAP + TK_PAD];
+  float rb[(TK_LB + NSL)][CAP];
   float4 acc[WARPS][FARMS_NSCALES][32];   // per-lane ring partials: len, lcx, lcy, count
   uint32_t tlist[NSL][TK_MAXT];
   // staging pass: run descriptors of all slabs being staged (start in the index, flat offset, slab | aliased << 7)
-  uint32_t run_s[(4 + NSL) * TK_MAXRUN], run_o[(4 + NSL) * TK_MAXRUN + 1];
-  uint8_t run_info[(4 + NSL) * TK_MAXRUN];
-  uint32_t slab_f[(4 + NSL) + 1], slab_pre[(4 + NSL) + 1];  // per staged slab: first flat position, passes before it
+  uint32_t run_s[(TK_LB + NSL) * TK_MAXRUN], run_o[(TK_LB + NSL) * TK_MAXRUN + 1];
+  uint8_t run_info[(TK_LB + NSL) * TK_MAXRUN];
+  uint32_t slab_f[(TK_LB + NSL) + 1], slab_pre[(TK_LB + NSL) + 1];  // per staged slab: first flat position, passes before it
   uint32_t wcount[WARPS];
-  int tag[(4 + NSL)];
-  int count[(4 + NSL)];
-  int overflow[(4 + NSL)];
+  int tag[(TK_LB + NSL)];
+  int count[(TK_LB + NSL)];
+  int overflow[(TK_LB + NSL)];
   int dlo[NSL], dhi[NSL], ovf[NSL];  // per target slab of the round: staged slabs its windows span
   unsigned int ntg[NSL], tnext, item;
 };
@@ -337,7 +340,7 @@ struct Region {  // pixels an owner tile can reach, as physical rectangles
 // no special case.
 template <class SM, int WARPS, int CAP, int NSL>
 __device__ void stage_slabs(const PoolArgs &A, SM &S, int s0, int s1, const Region &R, uint32_t i_round) {
-  constexpr int THREADS = WARPS * 32, RING = 4 + NSL;
+  constexpr int THREADS = WARPS * 32, RING = TK_LB + NSL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ts = A.g.tile_shift, nty = A.g.nty, NT = A.g.ntx * A.g.nty, H = A.g.H;
   const int tx0 = R.rx0 >> ts, tx1 = R.rx1 >> ts, ty0 = R.ry0 >> ts, ty1 = R.ry1 >> ts;
@@ -570,7 +573,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
   for (;;) {
     __syncthreads();
     if (tid == 0) S.item = atomicAdd(A.work_counter, 1u);
-    if (tid < (4 + NSL)) S.tag[tid] = -1;
+    if (tid < (TK_LB + NSL)) S.tag[tid] = -1;
     __syncthreads();
     const unsigned int item = S.item;
     if (item >= nitems) break;
@@ -619,8 +622,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
       if (nraw_all == 0) continue;  // uniform across the CTA
       if (SECOND) {  // only rounds the first pass flagged do any work here
         const uint32_t bits = A.item_ovf[item];
-        const int b0 = (d - d_begin) >> 1, nb2 = (nd + 1) >> 1;
-        if (((bits >> b0) & ((1u << nb2) - 1u)) == 0u) continue;
+        const int b0 = (d - d_begin) >> TK_OVF_SHIFT, b1 = (d + nd - 1 - d_begin) >> TK_OVF_SHIFT;
+        if (((bits >> b0) & ((2u << (b1 - b0)) - 1u)) == 0u) continue;
       }
 
       // ---- make sure the slabs of all windows of the round are staged ----
@@ -631,7 +634,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
         const uint32_t lo_id =
             (t_first >= (uint32_t)(FARMS_KILL_OLD_FLOW_TIME - 1) ? t_first - (FARMS_KILL_OLD_FLOW_TIME - 1) : 0u) >> FARMS_SLAB_SHIFT;
         int l = dd;
-        while (l > 0 && dd - l < 4 && A.slab_ids[l - 1] >= lo_id) l--;
+        while (l > 0 && dd - l < TK_LB && A.slab_ids[l - 1] >= lo_id) l--;
         S.dlo[tid] = l;
         S.dhi[tid] = dd;
       }
@@ -647,14 +650,14 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
       }
       // staged slabs are a contiguous range ending at the last staged slab, so what is missing is a suffix
       int s_new = s_first;
-      while (s_new <= s_last && S.tag[s_new % (4 + NSL)] == s_new) s_new++;  // uniform: tags are read after a barrier
+      while (s_new <= s_last && S.tag[s_new % (TK_LB + NSL)] == s_new) s_new++;  // uniform: tags are read after a barrier
       if (s_new <= s_last) stage_slabs<SM, WARPS, CAP, NSL>(A, S, s_new, s_last, R, i_round);
       __syncthreads();
       if (tid < NSL) {
         int o = 0;
-        for (int s = S.dlo[tid]; s <= S.dhi[tid]; s++) o |= S.overflow[s % (4 + NSL)];
+        for (int s = S.dlo[tid]; s <= S.dhi[tid]; s++) o |= S.overflow[s % (TK_LB + NSL)];
         S.ovf[tid] = o;
-        if (!SECOND && o && nraw[tid]) atomicOr(&A.item_ovf[item], 1u << ((d + tid - d_begin) >> 1));
+        if (!SECOND && o && nraw[tid]) atomicOr(&A.item_ovf[item], 1u << ((d + tid - d_begin) >> TK_OVF_SHIFT));
       }
 
       for (uint32_t t0 = 0; t0 < nmax; t0 += TK_MAXT) {
@@ -683,7 +686,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
         // round then ends half a task later instead of a whole one.
         // (Rounds of many slabs -- the sparse-stream variant -- keep the plain pairing: there an odd target shares
         // its warp with an idle half.)
-        constexpr bool SOLOS = NSL <= 2;
+        constexpr bool SOLOS = (NSL << FARMS_SLAB_SHIFT) <= 256;
         uint32_t pstart[NSL + 1], sstart[NSL + 1], npair[NSL];
         uint32_t P = 0;
 #pragma unroll
@@ -740,7 +743,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
           for (int q = 0; q < FARMS_NSCALES; q++) S.acc[warp][q][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
           const int sl = S.dlo[w], sh = S.dhi[w];
           for (int s = sl; s <= sh; s++) {
-            const int slot = s % (4 + NSL);
+            const int slot = s % (TK_LB + NSL);
             const int n = S.count[slot];
             ncand += (sub == 0 && have) ? n : 0;
             for (int q0 = sub + (solo ? 64 * half : 0); q0 < n; q0 += solo ? 128 : 64) {
@@ -814,7 +817,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
 #pragma unroll
               for (int q = 0; q < FARMS_NSCALES; q++) dacc[q * 16 + sub] = make_double4(0.0, 0.0, 0.0, 0.0);
               for (int s = sl; s <= sh; s++) {
-                const int slot = s % (4 + NSL);
+                const int slot = s % (TK_LB + NSL);
                 const int n = S.count[slot];
                 for (int q0 = sub; q0 < n; q0 += 16) {
                   const uint4 c = S.ra[slot][q0];
@@ -861,6 +864,7 @@ template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND>
 void launch_tile(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
   PoolArgs A = A0;
   using SM = TileSmem<WARPS, CAP, NSL>;
+  static_assert(sizeof(SM) <= (CTAS == 2 ? 115712 : 232448), "shared memory of the tile kernel: 227 KB per CTA, 228 KB per SM");
   auto kern = k_pool_tile<WARPS, CAP, NSL, CTAS, SECOND>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -899,8 +903,8 @@ constexpr int BP_PITCH = BP_LW * 8 + 4;     // words per table row (+4: conflict
 constexpr int BP_ROWQ = BP_PITCH / 4;       // uint4 per row
 constexpr int BP_NROW = OT + 2 * FARMS_MAX_WINDOW + 1;
 constexpr int BP_MAXQ = 64;                 // queries per round
-constexpr int BP_NDMAX = 8;                 // query slabs per round at most
-constexpr int BP_MAXSLAB = 4 + BP_NDMAX;    // + look-back slabs (a 500-us window touches <= 5 slabs)
+constexpr int BP_NDMAX = TK_LB > 4 ? 4 : 8;  // query slabs per round at most
+constexpr int BP_MAXSLAB = TK_LB + BP_NDMAX;  // + look-back slabs
 constexpr int BP_RUNS_PER_SLAB = 20;        // <= 10 tile columns for rows < H plus <= 10 aliased
 constexpr int BP_MAXRUNS = 256;
 static_assert(BP_MAXSLAB * BP_RUNS_PER_SLAB + 2 * BP_NDMAX <= BP_THREADS, "one thread per run descriptor");
@@ -929,7 +933,7 @@ __device__ __forceinline__ int slab_lookback(const PoolArgs &A, int dd) {
   const uint32_t lo_id =
       (t_first >= (uint32_t)(FARMS_KILL_OLD_FLOW_TIME - 1) ? t_first - (FARMS_KILL_OLD_FLOW_TIME - 1) : 0u) >> FARMS_SLAB_SHIFT;
   int l = dd;
-  while (l > 0 && dd - l < 4 && A.slab_ids[l - 1] >= lo_id) l--;
+  while (l > 0 && dd - l < TK_LB && A.slab_ids[l - 1] >= lo_id) l--;
   return l;
 }
 
@@ -1474,18 +1478,33 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
   if (fast && g.tile_shift == 4) {
     A.work_counter = work_counter;
     if (fast == 2) launch_bits(A, nslabs, num_sms, s);  // bit-table variant: 8 warps, 2 CTAs per SM, ~110 KB each
+#if FARMS_SLAB_SHIFT >= 7
     else if (fast == 3) launch_tile<16, 768, 4, 1, false>(A, nslabs, num_sms, s);  // 16 warps, 1 CTA per SM, ~222 KB
+#else
+    else if (fast == 3) launch_tile<16, 368, 8, 1, false>(A, nslabs, num_sms, s);
+#endif
     else {
       // flow events a slab holds inside one (32+100)^2 region, from the batch average
       const double per_region = flow_per_slab * 17424.0 / ((double)g.W * (double)g.H);
+#if FARMS_SLAB_SHIFT >= 7
       if (per_region < 110.0)  // sparse stream: 8 slabs per round keep the round's task list full (160-record slots)
         launch_tile<8, 160, 8, 2, false>(A, nslabs, num_sms, s);
       else
         launch_tile<8, 512, 2, 2, false>(A, nslabs, num_sms, s);  // 8 warps, 2 CTAs per SM, ~112 KB each
+#else
+      if (per_region < 55.0)  // sparse stream: 8 slabs per round keep the round's task list full (144-record slots)
+        launch_tile<8, 144, 8, 2, false>(A, nslabs, num_sms, s);
+      else
+        launch_tile<8, 216, 4, 2, false>(A, nslabs, num_sms, s);  // 8 warps, 2 CTAs per SM, ~112 KB each
+#endif
       // rounds whose staging overflowed those slots (locally dense scenes) get a second chance with 640-record
       // slots before the general kernel takes what is left
       A.work_counter = work_counter + 2;
+#if FARMS_SLAB_SHIFT >= 7
       launch_tile<16, 768, 4, 1, true>(A, nslabs, num_sms, s);
+#else
+      launch_tile<16, 368, 8, 1, true>(A, nslabs, num_sms, s);
+#endif
       launches++;
     }
     const size_t nout = m - (size_t)h;
