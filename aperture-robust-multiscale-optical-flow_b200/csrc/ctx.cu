@@ -187,9 +187,15 @@ __global__ void k_tail_start(const uint32_t *__restrict__ em, uint32_t m, uint32
   out[1] = last;
 }
 
-__global__ void k_nslabs(const uint32_t *__restrict__ em, const uint32_t *__restrict__ excl, uint32_t m, uint32_t *out) {
-  const bool first = m == 1 || (em[m - 2] >> FARMS_SLAB_SHIFT) != (em[m - 1] >> FARMS_SLAB_SHIFT);
+__global__ void k_nslabs(const uint32_t *__restrict__ em, const uint32_t *__restrict__ excl, uint32_t m, int slab_shift,
+                         uint32_t *out) {
+  const bool first = m == 1 || (em[m - 2] >> slab_shift) != (em[m - 1] >> slab_shift);
   out[0] = excl[m - 1] + ((m > 1 && first) ? 1u : 0u) + 1u;
+}
+
+__global__ void k_time_span(const uint32_t *__restrict__ em, uint32_t m, uint32_t *out) {
+  out[0] = em[0];
+  out[1] = em[m - 1];
 }
 
 // Small device->host read-backs (error flag, slab count, tail position) are written straight into pinned host
@@ -292,16 +298,14 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaEventRecord(c->ev[EV_FIT], s));
 
   // ---- K4a pooling index: dense time slabs x tiles ----
-  CU(cudaMemsetAsync(c->d_small, 0, 16, s));
-  launch_slab_flags(w.em, w.et, m, w.flags, c->d_small + 1, s);
-  exclusive_scan_u32(w.flags, w.flags, m, c->scan_temp.p, s, L);
-  k_nslabs<<<1, 1, 0, s>>>(w.em, w.flags, (uint32_t)m, c->d_small);
-  *L += 2;
-  k_publish<<<1, 32, 0, s>>>(c->h_small, c->d_small, 2);
+  // Slab length from the density of flow events: the shortest of 128 us, 256 us, ... that puts about 100 flow
+  // events of a (32+100)^2 tile region into a slab (shorter slabs cut fewer useless candidates than their fixed
+  // cost per slab and round; a sparse stream would otherwise spend its time on near-empty slabs).
+  k_time_span<<<1, 1, 0, s>>>(w.em, (uint32_t)m, c->d_small + 2);
+  k_publish<<<1, 32, 0, s>>>(c->h_small + 4, c->d_small + 2, 2);
   k_publish<<<1, 32, 0, s>>>(c->h_small + 2, (const uint32_t *)c->d_counters, 2);
+  *L += 3;
   CU(cudaStreamSynchronize(s));
-  const size_t nslabs = c->h_small[0];
-  const int monotone = c->h_small[1] == 0;
   // flow events of this batch's new part (the fit ran above); the halo is assumed to have the same density
   const unsigned long long valid_total = *(const unsigned long long *)(c->h_small + 2);
   const double flow_frac = n ? (double)(valid_total - c->valid_seen) / (double)n : 0.0;
@@ -309,6 +313,22 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   PoolGeom g{};
   g.W = c->W;
   g.H = c->H;
+  g.slab_shift = FARMS_SLAB_SHIFT_MIN;
+  {
+    const double span_us = (double)(c->h_small[5] - c->h_small[4]) + 1.0;
+    const double per_region_us = flow_frac * (double)m * (132.0 * 132.0 / (double)c->npx) / span_us;
+    static const double target = getenv("FARMS_SLAB_TARGET") ? atof(getenv("FARMS_SLAB_TARGET")) : 100.0;  // tuning runs
+    while (g.slab_shift < FARMS_SLAB_SHIFT_MAX && per_region_us * (double)(1u << g.slab_shift) < target) g.slab_shift++;
+  }
+  CU(cudaMemsetAsync(c->d_small, 0, 8, s));
+  launch_slab_flags(w.em, w.et, m, g.slab_shift, w.flags, c->d_small + 1, s);
+  exclusive_scan_u32(w.flags, w.flags, m, c->scan_temp.p, s, L);
+  k_nslabs<<<1, 1, 0, s>>>(w.em, w.flags, (uint32_t)m, g.slab_shift, c->d_small);
+  *L += 2;
+  k_publish<<<1, 32, 0, s>>>(c->h_small, c->d_small, 2);
+  CU(cudaStreamSynchronize(s));
+  const size_t nslabs = c->h_small[0];
+  const int monotone = c->h_small[1] == 0;
   g.tile_shift = 4;
   for (;;) {
     g.ntx = (c->W + (1 << g.tile_shift) - 1) >> g.tile_shift;

@@ -23,12 +23,13 @@
 #define FARMS_WINDOW_JUMP 5           // src/vFlow.cpp:73
 #define FARMS_MAX_WINDOW 50           // src/vFlow.cpp:74
 #define FARMS_NSCALES 11
-#ifndef FARMS_SLAB_SHIFT
-#define FARMS_SLAB_SHIFT 7            // pooling time slabs of 128 us (6 = 64 us also builds and passes the parity
-                                      // tests; measured slower: pooling 45.7 against 38.0 ms per 20 M events)
-#endif
-// dense slabs a 500-us window can reach back from the slab of its event: ceil(499 / slab length)
-#define FARMS_SLAB_LOOKBACK ((FARMS_KILL_OLD_FLOW_TIME - 1 + (1 << FARMS_SLAB_SHIFT) - 1) >> FARMS_SLAB_SHIFT)
+// Pooling time slabs are 2^slab_shift us long (PoolGeom::slab_shift, chosen per batch from the density of flow
+// events): 128 us for dense streams (64 us measured slower: 45.7 against 38.0 ms per 20 M events at 1280x720),
+// longer for sparse ones so that a slab of one tile region holds ~100+ records.
+#define FARMS_SLAB_SHIFT_MIN 7
+#define FARMS_SLAB_SHIFT_MAX 14
+// dense slabs a 500-us window can reach back from the slab of its event, at most: ceil(499 / 128)
+#define FARMS_SLAB_LOOKBACK 4
 
 struct FitParams {
   int W, H, r, P, min_inl;
@@ -47,6 +48,7 @@ struct PoolGeom {
   int W, H;
   int tile_shift;     // tiles of (1<<tile_shift)^2 pixels
   int ntx, nty;       // tiles per axis; tile id = tx*nty + ty (y fastest, like the pixel layout)
+  int slab_shift;     // time slabs of 2^slab_shift us
 };
 
 // ---- sort.cu ----
@@ -71,7 +73,7 @@ void launch_halo_keys(const uint16_t *ex, const uint16_t *ey, size_t h, int H, u
                       cudaStream_t s);
 void launch_links(const uint32_t *skeys, const uint32_t *svals, const uint32_t *et, const uint2 *sae, size_t m,
                   int2 *prevp, int32_t *nextp, cudaStream_t s);
-void launch_slab_flags(const uint32_t *em, const uint32_t *et, size_t m, uint32_t *flags, uint32_t *nonmono,
+void launch_slab_flags(const uint32_t *em, const uint32_t *et, size_t m, int slab_shift, uint32_t *flags, uint32_t *nonmono,
                        cudaStream_t s);
 void launch_slice_surface(const uint16_t *x, const uint16_t *y, const uint64_t *t, size_t n, uint64_t t0, int H,
                           unsigned long long *packed, cudaStream_t s);

@@ -60,12 +60,12 @@ __global__ void k_links(const uint32_t *__restrict__ skeys, const uint32_t *__re
 }
 
 // flags[j] = 1 where a new time slab starts; *nonmono != 0 if any timestamp runs backwards.
-__global__ void k_slab_flags(const uint32_t *__restrict__ em, const uint32_t *__restrict__ et, size_t m,
+__global__ void k_slab_flags(const uint32_t *__restrict__ em, const uint32_t *__restrict__ et, size_t m, int slab_shift,
                              uint32_t *__restrict__ flags, uint32_t *__restrict__ nonmono) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool bad = false;
   if (j < m) {
-    flags[j] = (j > 0 && (em[j] >> FARMS_SLAB_SHIFT) != (em[j - 1] >> FARMS_SLAB_SHIFT)) ? 1u : 0u;
+    flags[j] = (j > 0 && (em[j] >> slab_shift) != (em[j - 1] >> slab_shift)) ? 1u : 0u;
     bad = em[j] != et[j];
   }
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(nonmono, 1u);
@@ -123,9 +123,9 @@ void launch_links(const uint32_t *skeys, const uint32_t *svals, const uint32_t *
                   int2 *prevp, int32_t *nextp, cudaStream_t s) {
   if (m) k_links<<<nb(m, 256), 256, 0, s>>>(skeys, svals, et, sae, m, prevp, nextp);
 }
-void launch_slab_flags(const uint32_t *em, const uint32_t *et, size_t m, uint32_t *flags, uint32_t *nonmono,
+void launch_slab_flags(const uint32_t *em, const uint32_t *et, size_t m, int slab_shift, uint32_t *flags, uint32_t *nonmono,
                        cudaStream_t s) {
-  if (m) k_slab_flags<<<nb(m, 256), 256, 0, s>>>(em, et, m, flags, nonmono);
+  if (m) k_slab_flags<<<nb(m, 256), 256, 0, s>>>(em, et, m, slab_shift, flags, nonmono);
 }
 void launch_slice_surface(const uint16_t *x, const uint16_t *y, const uint64_t *t, size_t n, uint64_t t0, int H,
                           unsigned long long *packed, cudaStream_t s) {

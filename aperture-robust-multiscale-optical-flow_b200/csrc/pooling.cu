@@ -47,8 +47,8 @@ __global__ void k_cell_keys(const uint16_t *__restrict__ ex, const uint16_t *__r
                             uint32_t *__restrict__ slab_ids, uint32_t *__restrict__ slab_first) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
-  const uint32_t sid = em[j] >> FARMS_SLAB_SHIFT;
-  const bool first = j == 0 || (em[j - 1] >> FARMS_SLAB_SHIFT) != sid;
+  const uint32_t sid = em[j] >> g.slab_shift;
+  const bool first = j == 0 || (em[j - 1] >> g.slab_shift) != sid;
   const uint32_t dense = excl[j] + ((j > 0 && first) ? 1u : 0u);
   if (first) {
     slab_ids[dense] = sid;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
       }
       // time slabs that can hold an event with |ti - tj| < 500 and index <= ii
       const uint32_t lo_id = (ti >= (uint32_t)(FARMS_KILL_OLD_FLOW_TIME - 1) ? ti - (FARMS_KILL_OLD_FLOW_TIME - 1) : 0u) >>
-                             FARMS_SLAB_SHIFT;
+                             A.g.slab_shift;
       int dlo = dhi;
       while (dlo > 0 && A.slab_ids[dlo - 1] >= lo_id) dlo--;
 
@@ -297,10 +297,10 @@ constexpr int OT_SHIFT = 5, OT = 1 << OT_SHIFT;  // owner tile edge (pixels)
 // A 500-us window reaches back TK_LB slabs at most, so a round's windows span <= TK_LB + NSL staged slabs (the slot
 // ring).
 constexpr int TK_LB = FARMS_SLAB_LOOKBACK;
-constexpr int TK_OVF_SHIFT = FARMS_SLAB_SHIFT >= 7 ? 1 : 2;  // slabs per bit of the overflow bitmap (32 bits / item)
+constexpr int TK_OVF_SHIFT = 1;  // slabs per bit of the overflow bitmap, as a shift (32 bits per item of 64 slabs)
 constexpr int TK_PAD = 64;     // the pooling loop reads 4 x 16 records at a time without bounds checks
 #ifndef FARMS_TK_SEG
-#define FARMS_TK_SEG (32 << (FARMS_SLAB_SHIFT >= 7 ? 1 : 2))
+#define FARMS_TK_SEG 64
 #endif
 constexpr int TK_SEG = FARMS_TK_SEG;  // slabs per work item
 constexpr int TK_MAXT = 128;   // targets handled per round and slab
@@ -630,9 +630,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
       __syncthreads();  // the previous round is done with S.dlo / S.dhi / S.ovf
       if (tid < NSL) {
         const int dd = min(d + tid, d_end - 1);
-        const uint32_t t_first = A.slab_ids[dd] << FARMS_SLAB_SHIFT;
+        const uint32_t t_first = A.slab_ids[dd] << A.g.slab_shift;
         const uint32_t lo_id =
-            (t_first >= (uint32_t)(FARMS_KILL_OLD_FLOW_TIME - 1) ? t_first - (FARMS_KILL_OLD_FLOW_TIME - 1) : 0u) >> FARMS_SLAB_SHIFT;
+            (t_first >= (uint32_t)(FARMS_KILL_OLD_FLOW_TIME - 1) ? t_first - (FARMS_KILL_OLD_FLOW_TIME - 1) : 0u) >> A.g.slab_shift;
         int l = dd;
         while (l > 0 && dd - l < TK_LB && A.slab_ids[l - 1] >= lo_id) l--;
         S.dlo[tid] = l;
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
         // round then ends half a task later instead of a whole one.
         // (Rounds of many slabs -- the sparse-stream variant -- keep the plain pairing: there an odd target shares
         // its warp with an idle half.)
-        constexpr bool SOLOS = (NSL << FARMS_SLAB_SHIFT) <= 256;
+        constexpr bool SOLOS = NSL <= 2;
         uint32_t pstart[NSL + 1], sstart[NSL + 1], npair[NSL];
         uint32_t P = 0;
 #pragma unroll
@@ -903,7 +903,7 @@ constexpr int BP_PITCH = BP_LW * 8 + 4;     // words per table row (+4: conflict
 constexpr int BP_ROWQ = BP_PITCH / 4;       // uint4 per row
 constexpr int BP_NROW = OT + 2 * FARMS_MAX_WINDOW + 1;
 constexpr int BP_MAXQ = 64;                 // queries per round
-constexpr int BP_NDMAX = TK_LB > 4 ? 4 : 8;  // query slabs per round at most
+constexpr int BP_NDMAX = 8;  // query slabs per round at most
 constexpr int BP_MAXSLAB = TK_LB + BP_NDMAX;  // + look-back slabs
 constexpr int BP_RUNS_PER_SLAB = 20;        // <= 10 tile columns for rows < H plus <= 10 aliased
 constexpr int BP_MAXRUNS = 256;
@@ -929,9 +929,9 @@ struct BitsSmem {
 
 // first dense slab a query of dense slab dd can need (|dt| < 500 us, at most 4 slabs back)
 __device__ __forceinline__ int slab_lookback(const PoolArgs &A, int dd) {
-  const uint32_t t_first = A.slab_ids[dd] << FARMS_SLAB_SHIFT;
+  const uint32_t t_first = A.slab_ids[dd] << A.g.slab_shift;
   const uint32_t lo_id =
-      (t_first >= (uint32_t)(FARMS_KILL_OLD_FLOW_TIME - 1) ? t_first - (FARMS_KILL_OLD_FLOW_TIME - 1) : 0u) >> FARMS_SLAB_SHIFT;
+      (t_first >= (uint32_t)(FARMS_KILL_OLD_FLOW_TIME - 1) ? t_first - (FARMS_KILL_OLD_FLOW_TIME - 1) : 0u) >> A.g.slab_shift;
   int l = dd;
   while (l > 0 && dd - l < TK_LB && A.slab_ids[l - 1] >= lo_id) l--;
   return l;
@@ -1478,33 +1478,18 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
   if (fast && g.tile_shift == 4) {
     A.work_counter = work_counter;
     if (fast == 2) launch_bits(A, nslabs, num_sms, s);  // bit-table variant: 8 warps, 2 CTAs per SM, ~110 KB each
-#if FARMS_SLAB_SHIFT >= 7
     else if (fast == 3) launch_tile<16, 768, 4, 1, false>(A, nslabs, num_sms, s);  // 16 warps, 1 CTA per SM, ~222 KB
-#else
-    else if (fast == 3) launch_tile<16, 368, 8, 1, false>(A, nslabs, num_sms, s);
-#endif
     else {
       // flow events a slab holds inside one (32+100)^2 region, from the batch average
       const double per_region = flow_per_slab * 17424.0 / ((double)g.W * (double)g.H);
-#if FARMS_SLAB_SHIFT >= 7
-      if (per_region < 110.0)  // sparse stream: 8 slabs per round keep the round's task list full (160-record slots)
-        launch_tile<8, 160, 8, 2, false>(A, nslabs, num_sms, s);
+      if (per_region < 200.0)  // thin slabs: 4 per round keep the round's task list full (320-record slots)
+        launch_tile<8, 320, 4, 2, false>(A, nslabs, num_sms, s);
       else
         launch_tile<8, 512, 2, 2, false>(A, nslabs, num_sms, s);  // 8 warps, 2 CTAs per SM, ~112 KB each
-#else
-      if (per_region < 55.0)  // sparse stream: 8 slabs per round keep the round's task list full (144-record slots)
-        launch_tile<8, 144, 8, 2, false>(A, nslabs, num_sms, s);
-      else
-        launch_tile<8, 216, 4, 2, false>(A, nslabs, num_sms, s);  // 8 warps, 2 CTAs per SM, ~112 KB each
-#endif
       // rounds whose staging overflowed those slots (locally dense scenes) get a second chance with 640-record
       // slots before the general kernel takes what is left
       A.work_counter = work_counter + 2;
-#if FARMS_SLAB_SHIFT >= 7
       launch_tile<16, 768, 4, 1, true>(A, nslabs, num_sms, s);
-#else
-      launch_tile<16, 368, 8, 1, true>(A, nslabs, num_sms, s);
-#endif
       launches++;
     }
     const size_t nout = m - (size_t)h;
