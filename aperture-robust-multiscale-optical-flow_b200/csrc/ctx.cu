@@ -298,7 +298,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaEventRecord(c->ev[EV_FIT], s));
 
   // ---- K4a pooling index: dense time slabs x tiles ----
-  // Slab length from the density of flow events: the shortest of 128 us, 256 us, ... that puts about 100 flow
+  // Slab length from the density of flow events: the shortest of 128 us, 256 us, ... that puts at least 70 flow
   // events of a (32+100)^2 tile region into a slab (shorter slabs cut fewer useless candidates than their fixed
   // cost per slab and round; a sparse stream would otherwise spend its time on near-empty slabs).
   k_time_span<<<1, 1, 0, s>>>(w.em, (uint32_t)m, c->d_small + 2);
@@ -317,7 +317,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   {
     const double span_us = (double)(c->h_small[5] - c->h_small[4]) + 1.0;
     const double per_region_us = flow_frac * (double)m * (132.0 * 132.0 / (double)c->npx) / span_us;
-    static const double target = getenv("FARMS_SLAB_TARGET") ? atof(getenv("FARMS_SLAB_TARGET")) : 100.0;  // tuning runs
+    static const double target = getenv("FARMS_SLAB_TARGET") ? atof(getenv("FARMS_SLAB_TARGET")) : 70.0;  // tuning runs
     while (g.slab_shift < FARMS_SLAB_SHIFT_MAX && per_region_us * (double)(1u << g.slab_shift) < target) g.slab_shift++;
   }
   CU(cudaMemsetAsync(c->d_small, 0, 8, s));
