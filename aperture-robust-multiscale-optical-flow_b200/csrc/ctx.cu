@@ -721,6 +721,49 @@ int farms_slice_surface(farms_ctx *c, const uint16_t *d_x, const uint16_t *d_y, 
   return FARMS_OK;
 }
 
+int farms_slice_surface_host(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t n,
+                             uint64_t t0, uint32_t *last_t, uint8_t *hit) {
+  if (!c || !last_t || !hit || (n && (!x || !y || !t))) return FARMS_ERR_ARG;
+  CU(cudaSetDevice(c->cfg.device));
+  uint16_t *dx = nullptr, *dy = nullptr;
+  uint64_t *dt = nullptr;
+  uint32_t *dl = nullptr;
+  uint8_t *dh = nullptr;
+  const size_t cap = (size_t)std::max<uint64_t>(n, 1);
+  bool ok = cudaMalloc((void **)&dx, cap * 2) == cudaSuccess && cudaMalloc((void **)&dy, cap * 2) == cudaSuccess &&
+            cudaMalloc((void **)&dt, cap * 8) == cudaSuccess && cudaMalloc((void **)&dl, c->npx * 4) == cudaSuccess &&
+            cudaMalloc((void **)&dh, c->npx) == cudaSuccess;
+  int rc = ok ? FARMS_OK : fail(c, FARMS_ERR_NOMEM, "out of device memory for a %llu-event slice", (unsigned long long)n);
+  if (ok && n) {
+    ok = cudaMemcpy(dx, x, n * 2, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(dy, y, n * 2, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(dt, t, n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) rc = fail(c, FARMS_ERR_CUDA, "upload of the slice failed");
+  }
+  if (rc == FARMS_OK) rc = farms_slice_surface(c, dx, dy, dt, n, t0, dl, dh);
+  if (rc == FARMS_OK && (cudaMemcpy(last_t, dl, c->npx * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                         cudaMemcpy(hit, dh, c->npx, cudaMemcpyDeviceToHost) != cudaSuccess))
+    rc = fail(c, FARMS_ERR_CUDA, "download of the surface failed");
+  cudaFree(dx); cudaFree(dy); cudaFree(dt); cudaFree(dl); cudaFree(dh);
+  return rc;
+}
+
+int farms_state_fold_host(farms_ctx *c, const uint32_t *last_t, const uint8_t *hit) {
+  if (!c || !last_t || !hit) return FARMS_ERR_ARG;
+  CU(cudaSetDevice(c->cfg.device));
+  uint32_t *dl = nullptr;
+  uint8_t *dh = nullptr;
+  int rc = FARMS_OK;
+  if (cudaMalloc((void **)&dl, c->npx * 4) != cudaSuccess || cudaMalloc((void **)&dh, c->npx) != cudaSuccess)
+    rc = fail(c, FARMS_ERR_NOMEM, "out of device memory for a surface");
+  else if (cudaMemcpy(dl, last_t, c->npx * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+           cudaMemcpy(dh, hit, c->npx, cudaMemcpyHostToDevice) != cudaSuccess)
+    rc = fail(c, FARMS_ERR_CUDA, "upload of the surface failed");
+  if (rc == FARMS_OK) rc = farms_state_fold(c, dl, dh);
+  cudaFree(dl); cudaFree(dh);
+  return rc;
+}
+
 int farms_pack4_f32(farms_ctx *c, const double *d_a, const double *d_b, const double *d_c, const double *d_d,
                     uint64_t n, float *d_out4) {
   if (!c || (n && (!d_a || !d_b || !d_c || !d_d || !d_out4))) return FARMS_ERR_ARG;

@@ -16,7 +16,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "farms_b200.h"
@@ -31,6 +33,7 @@ struct Options {
   bool serial = true, verbose = false;
   bool fast = false;  // --fast 1: FP32 ring partials in the pooling kernel (about 1e-7 relative on columns 5-6)
   bool binary = false;  // --binary 1: <filename>.evb in, <filename>_FARMSOut_.bin out (include/farms_textio.h)
+  int gpus = 1;         // --gpus N: time-slice the recording over devices device .. device+N-1 (one host thread each)
 };
 
 void usage() {
@@ -49,7 +52,8 @@ void usage() {
       "  --v arg               set verbose to 1 for full debug mode\n"
       "  --device arg          CUDA device ordinal (extension)\n"
       "  --fast arg            1 = fastest pooling kernel, columns 5-6 accurate to ~1e-7 (extension)\n"
-      "  --binary arg          1 = binary side-format: <filename>.evb in, <filename>_FARMSOut_.bin out (extension)\n");
+      "  --binary arg          1 = binary side-format: <filename>.evb in, <filename>_FARMSOut_.bin out (extension)\n"
+      "  --gpus arg            time-slice the recording over this many GPUs, device .. device+N-1 (extension)\n");
 }
 
 bool parse_int(const std::string &s, int &out) {
@@ -83,7 +87,7 @@ int parse_args(int argc, char **argv, Options &o) {
       return 2;
     }
     static const char *known[] = {"filename", "height", "width", "filtersize", "inlierCheck", "numEvents",
-                                  "numevents", "NUMEVENTS", "SERIAL", "v", "device", "fast", "binary"};
+                                  "numevents", "NUMEVENTS", "SERIAL", "v", "device", "fast", "binary", "gpus"};
     bool ok = false;
     for (const char *k : known) ok |= name == k;
     if (!ok) {
@@ -118,6 +122,7 @@ int parse_args(int argc, char **argv, Options &o) {
     else if (name == "device") { o.device = iv; }
     else if (name == "fast") { o.fast = iv == 1; }
     else if (name == "binary") { o.binary = iv == 1; }
+    else if (name == "gpus") { o.gpus = iv < 1 ? 1 : iv; }
   }
   // the reference honours the spellings in the order numEvents, numevents, NUMEVENTS (src/main.cpp:131-151)
   // and converts the int to unsigned long
@@ -128,6 +133,113 @@ int parse_args(int argc, char **argv, Options &o) {
       break;
     }
   return 0;
+}
+
+// ---- single-process multi-GPU run: the recording is cut into equal time slices, one per GPU.
+// GPU g owns the events of stream time [g*D, (g+1)*D), also processes the 499-us causal halo in front of them
+// (pooling admits |dt| < 500 us, src/vFlow.cpp:1002) and rebuilds the surface of active events at its halo start
+// from the "last event per pixel" surfaces of the earlier slices (the surface never forgets, src/vFlow.cpp:267):
+// slice r contributes the events of [r*D - 499, (r+1)*D - 499), which tile the time axis; later slices win.
+struct SliceOut {
+  std::vector<uint32_t> t_rel;
+  std::vector<double> gr, gth, vx, vy, lr, lth;
+  std::vector<uint8_t> scale;
+};
+
+int run_sliced(const Options &o, const farms_config &base, const farms_events &ev, const farms_out &out,
+               farms_timings &tm_sum, uint64_t &events_done, std::string &err) {
+  const size_t n = (size_t)ev.n;
+  const int G = o.gpus;
+  for (size_t i = 1; i < n; i++)
+    if (ev.t[i] < ev.t[i - 1]) {
+      err = "--gpus needs non-decreasing timestamps (time slices); run this recording on one GPU";
+      return 1;
+    }
+  const uint64_t t0 = ev.t[0], span = ev.t[n - 1] - t0 + 1, D = (span + G - 1) / G, HALO = 499;
+  auto first_at = [&](uint64_t ts) {  // first event with stream time >= ts
+    return (size_t)(std::lower_bound(ev.t, ev.t + n, t0 + ts) - ev.t);
+  };
+  const bool same_device = std::getenv("FARMS_CLI_SAME_DEVICE") != nullptr;  // tests on a one-GPU box
+  const size_t npx = (size_t)o.width * o.height;
+  std::vector<farms_ctx *> ctx(G, nullptr);
+  std::vector<std::vector<uint32_t>> surf_t(G);
+  std::vector<std::vector<uint8_t>> surf_hit(G);
+  std::vector<int> rc(G, FARMS_OK);
+  std::vector<std::string> msg(G);
+  std::vector<SliceOut> so(G);
+  std::vector<size_t> lo(G), begin(G), end(G);
+  auto each_gpu = [&](auto fn) {
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++) th.emplace_back([&, g] { fn(g); });
+    for (auto &t : th) t.join();
+    for (int g = 0; g < G; g++)
+      if (rc[g] != FARMS_OK) {
+        err = "GPU slice " + std::to_string(g) + ": " + msg[g];
+        return 1;
+      }
+    return 0;
+  };
+  // phase 1: contexts, and every slice's share of the surface exchange
+  int bad = each_gpu([&](int g) {
+    farms_config cfg = base;
+    cfg.device = same_device ? base.device : base.device + g;
+    rc[g] = farms_create(&ctx[g], &cfg);
+    if (rc[g] != FARMS_OK) { msg[g] = "farms_create failed (device " + std::to_string(cfg.device) + ")"; return; }
+    farms_set_t0(ctx[g], t0);
+    begin[g] = first_at((uint64_t)g * D);
+    end[g] = g == G - 1 ? n : first_at((uint64_t)(g + 1) * D);
+    lo[g] = g == 0 ? 0 : first_at((uint64_t)g * D - std::min<uint64_t>(HALO, (uint64_t)g * D));
+    if (g < G - 1) {
+      const size_t s0 = lo[g], s1 = first_at((uint64_t)(g + 1) * D - std::min<uint64_t>(HALO, (uint64_t)(g + 1) * D));
+      surf_t[g].resize(npx);
+      surf_hit[g].resize(npx);
+      rc[g] = farms_slice_surface_host(ctx[g], ev.x + s0, ev.y + s0, ev.t + s0, s1 > s0 ? s1 - s0 : 0, t0,
+                                       surf_t[g].data(), surf_hit[g].data());
+      if (rc[g] != FARMS_OK) msg[g] = farms_last_error(ctx[g]);
+    }
+  });
+  // phase 2: fold the earlier slices' surfaces in order, then process halo + owned events
+  if (!bad) bad = each_gpu([&](int g) {
+    for (int r = 0; r < g && rc[g] == FARMS_OK; r++)
+      rc[g] = farms_state_fold_host(ctx[g], surf_t[r].data(), surf_hit[r].data());
+    if (rc[g] != FARMS_OK) { msg[g] = farms_last_error(ctx[g]); return; }
+    const size_t m = end[g] - lo[g];
+    SliceOut &q = so[g];
+    q.t_rel.resize(m); q.gr.resize(m); q.gth.resize(m); q.vx.resize(m); q.vy.resize(m); q.lr.resize(m);
+    q.lth.resize(m); q.scale.resize(m);
+    farms_out fo;
+    std::memset(&fo, 0, sizeof fo);
+    fo.t_rel = q.t_rel.data(); fo.global_r = q.gr.data(); fo.global_theta = q.gth.data(); fo.vx = q.vx.data();
+    fo.vy = q.vy.data(); fo.local_r = q.lr.data(); fo.local_theta = q.lth.data(); fo.scale = q.scale.data();
+    if (m) rc[g] = farms_process_host(ctx[g], ev.x + lo[g], ev.y + lo[g], ev.t + lo[g], nullptr, m, &fo);
+    if (rc[g] != FARMS_OK) msg[g] = farms_last_error(ctx[g]);
+  });
+  std::memset(&tm_sum, 0, sizeof tm_sum);
+  events_done = 0;
+  for (int g = 0; g < G; g++) {
+    if (!bad && ctx[g]) {
+      const size_t skip = begin[g] - lo[g], cnt = end[g] - begin[g], at = begin[g];
+      const SliceOut &q = so[g];
+      std::copy_n(q.t_rel.begin() + skip, cnt, out.t_rel + at);
+      std::copy_n(q.gr.begin() + skip, cnt, out.global_r + at);
+      std::copy_n(q.gth.begin() + skip, cnt, out.global_theta + at);
+      std::copy_n(q.vx.begin() + skip, cnt, out.vx + at);
+      std::copy_n(q.vy.begin() + skip, cnt, out.vy + at);
+      std::copy_n(q.lr.begin() + skip, cnt, out.local_r + at);
+      std::copy_n(q.lth.begin() + skip, cnt, out.local_theta + at);
+      std::copy_n(q.scale.begin() + skip, cnt, out.scale + at);
+      farms_timings tm;
+      farms_get_timings(ctx[g], &tm);
+      tm_sum.total_ms = std::max(tm_sum.total_ms, tm.total_ms);
+      tm_sum.ingest_ms += tm.ingest_ms; tm_sum.index_ms += tm.index_ms; tm_sum.fit_ms += tm.fit_ms;
+      tm_sum.bin_ms += tm.bin_ms; tm_sum.pool_ms += tm.pool_ms;
+      tm_sum.valid_events += tm.valid_events;  // includes the halo events of every slice
+      tm_sum.events += cnt;
+      events_done += cnt;
+    }
+    if (ctx[g]) farms_destroy(ctx[g]);
+  }
+  return bad;
 }
 
 }  // namespace
@@ -181,8 +293,21 @@ int main(int argc, char **argv) {
   out.t_rel = t_rel.data(); out.global_r = gr.data(); out.global_theta = gth.data(); out.vx = vx.data();
   out.vy = vy.data(); out.local_r = lr.data(); out.local_theta = lth.data(); out.scale = scale.data();
 
+  farms_timings tm_sliced;
+  uint64_t sliced_events = 0;
   const auto a = std::chrono::system_clock::now();
-  rc = farms_process_host(ctx, ev.x, ev.y, ev.t, nullptr, n, &out);
+  if (o.gpus > 1) {
+    std::string serr;
+    if (run_sliced(o, cfg, ev, out, tm_sliced, sliced_events, serr)) {
+      std::fprintf(stderr, "error: %s\n", serr.c_str());
+      farms_text_free(&ev);
+      farms_destroy(ctx);
+      return 1;
+    }
+    rc = FARMS_OK;
+  } else {
+    rc = farms_process_host(ctx, ev.x, ev.y, ev.t, nullptr, n, &out);
+  }
   const auto b = std::chrono::system_clock::now();
   if (rc != FARMS_OK) {
     std::fprintf(stderr, "error: %s\n", farms_last_error(ctx));
@@ -208,10 +333,12 @@ int main(int argc, char **argv) {
 
   farms_timings tm;
   farms_get_timings(ctx, &tm);
+  if (o.gpus > 1) tm = tm_sliced;  // slowest slice's device time, stage times summed over the slices
+  const uint64_t events_done = o.gpus > 1 ? sliced_events : farms_num_events(ctx);
   // same line as src/main.cpp:209, but with real (not integer-divided) seconds
   const double sec = (double)usec / 1e6;
   std::printf("[Benchmark Main] : Processing time   : %ld usec %g sec  with rate of : %g events/sec\n", usec, sec,
-              sec > 0 ? ((double)farms_num_events(ctx) - 1) / sec : 0.0);
+              sec > 0 ? ((double)events_done - 1) / sec : 0.0);
   std::printf("[farms_b200] device %.3f ms (ingest %.3f, index %.3f, fit %.3f, bin %.3f, pool %.3f), valid %llu of %llu\n",
               tm.total_ms, tm.ingest_ms, tm.index_ms, tm.fit_ms, tm.bin_ms, tm.pool_ms,
               (unsigned long long)tm.valid_events, (unsigned long long)tm.events);

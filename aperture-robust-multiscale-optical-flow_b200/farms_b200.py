@@ -21,6 +21,7 @@ EXPORTS = [
     "farms_abi_version", "farms_create", "farms_destroy", "farms_reset", "farms_last_error", "farms_normalize_filtersize", "farms_get_params",
     "farms_process_host", "farms_process_device", "farms_num_events", "farms_get_timings", "farms_set_t0",
     "farms_state_export", "farms_state_fold", "farms_slice_surface", "farms_pack4_f32",
+    "farms_slice_surface_host", "farms_state_fold_host",
 ]
 
 

@@ -146,6 +146,13 @@ int farms_state_fold(farms_ctx *ctx, const uint32_t *d_last_t, const uint8_t *d_
 int farms_slice_surface(farms_ctx *ctx, const uint16_t *d_x, const uint16_t *d_y, const uint64_t *d_t,
                         uint64_t n, uint64_t t0, uint32_t *d_last_t, uint8_t *d_hit);
 
+/* The same two steps with HOST arrays (width*height entries each), for callers without CUDA of their own -- the
+ * FARMS_Flow command line uses them for its single-process multi-GPU mode (one host thread and one context per
+ * GPU, surfaces handed over through host memory). */
+int farms_slice_surface_host(farms_ctx *ctx, const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t n,
+                             uint64_t t0, uint32_t *last_t, uint8_t *hit);
+int farms_state_fold_host(farms_ctx *ctx, const uint32_t *last_t, const uint8_t *hit);
+
 /* K5 helper for the final gather of a time-sliced run: interleave four f64 device columns (normally globalR,
  * globalTheta, localR, localTheta -- the README's 8-column contract minus the echoed x y t p) into one
  * float4-per-event device buffer that goes over NVLink in a single NCCL gather. */

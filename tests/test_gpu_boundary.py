@@ -222,3 +222,28 @@ def test_cli_binary_side_format_carries_the_same_columns_as_the_text_files(tmp_p
     assert np.array_equal(cols["x"], x16[:n]) and np.array_equal(cols["y"], y16[:n]) and np.array_equal(cols["p"], p8[:n])
     for k in ("t_rel", "scale", "global_r", "global_theta", "vx", "vy", "local_r", "local_theta"):
         assert np.array_equal(cols[k], ref[k], equal_nan=True), k
+
+
+def test_cli_time_sliced_over_several_contexts_equals_one_run(tmp_path, monkeypatch):
+    """FARMS_Flow --gpus 3 (single process, one host thread and one context per slice; here all on device 0):
+    the surface hand-over and the 499-us halo make the sliced run equal to the plain one."""
+    from helpers import synth_stream
+    s, x, y, t, p = synth_stream(3, 120000, 0)
+    base1, base3 = str(tmp_path / "one"), str(tmp_path / "three")
+    arr = np.stack([x.astype(np.int64), y.astype(np.int64), t.astype(np.int64), p.astype(np.int64)], 1)
+    for b in (base1, base3):
+        np.savetxt(b + ".txt", arr, fmt="%d")
+    common = ["--width", str(s.width), "--height", str(s.height), "--filtersize", str(s.filtersize)]
+    r1 = subprocess.run([CLI] + common + ["--filename", base1], capture_output=True, text=True)
+    assert r1.returncode == 0, r1.stderr
+    monkeypatch.setenv("FARMS_CLI_SAME_DEVICE", "1")
+    r3 = subprocess.run([CLI] + common + ["--filename", base3, "--gpus", "3"], capture_output=True, text=True)
+    assert r3.returncode == 0, r3.stderr
+    a = np.loadtxt(base1 + "_FARMSOut_batch.txt")
+    b = np.loadtxt(base3 + "_FARMSOut_batch.txt")
+    assert a.shape == b.shape == (len(x), 11)
+    assert np.array_equal(a[:, [0, 1, 2, 3, 10]], b[:, [0, 1, 2, 3, 10]])      # x y t p scale
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    m = ~np.isnan(a)
+    assert np.allclose(a[m], b[m], rtol=2e-6, atol=0)                             # 6 printed digits
+    assert (a[:, 8] > 0).sum() > 10000
