@@ -120,14 +120,15 @@ def test_fast_pooling_equals_exact_pooling_on_long_dense_streams(config, n, star
     assert np.array_equal(fast["global_r"][~v], exact["global_r"][~v])
 
 
-def test_bit_table_pooling_variant_matches_oracle_and_exact_kernel(monkeypatch):
+@pytest.mark.parametrize("impl", ["bits", "tile1"])
+def test_alternative_pooling_kernels_match_oracle_and_exact_kernel(monkeypatch, impl):
     """k_pool_bits (FARMS_POOL_IMPL=bits: prefix bit tables over the staged records, a measured alternative to the
-    default staged-list kernel) obeys the same contract: oracle parity on a short stream, and the same scale as
-    the exact FP64 kernel on a long dense one."""
+    default staged-list kernel) and the one-CTA-per-SM instantiation of k_pool_tile (tile1) obey the same contract:
+    oracle parity on a short stream, and the same scale as the exact FP64 kernel on a long dense one."""
     import farms_b200
-    monkeypatch.setenv("FARMS_POOL_IMPL", "bits")
+    monkeypatch.setenv("FARMS_POOL_IMPL", impl)
     s, x, y, t, ref, f = _run_case(4, 120000, 0, None)
-    rep = compare(f.process(x, y, t), ref, "cfg4 bit-table pooling")
+    rep = compare(f.process(x, y, t), ref, f"cfg4 pooling variant {impl}")
     assert_parity(rep)
     s, x, y, t, p = synth_stream(4, 2_000_000, 2000)
     fast = farms_b200.Farms(s.width, s.height, s.filtersize, 5).process(x, y, t)
