@@ -29,6 +29,7 @@ constexpr size_t HALO_CAP = 8ull << 20;       // events carried across a batch b
 #endif
 constexpr int FIT_CHUNK_MAX = 1 << FARMS_FIT_CHUNK_LOG2;  // events per SAE snapshot at most
 constexpr int FIT_CHUNK_MIN = 1 << 13;
+constexpr int FIT_WAYS = 4;  // plane-fit chunks in flight
 constexpr size_t CSR_BUDGET = 96ull << 20;    // max (slab, tile) cells of the pooling index per batch
 
 enum { EV_START, EV_H2D, EV_INGEST, EV_INDEX, EV_FIT, EV_BIN, EV_POOL, EV_END, EV_COUNT };
@@ -85,8 +86,11 @@ struct farms_ctx {
   bool d2h_pending[2] = {false, false};
   farms_timings tm{};
 
-  uint2 *sae = nullptr, *sae2 = nullptr;  // surface of active events; second copy for the two-stream plane fit
-  cudaStream_t fit_stream = nullptr;
+  // surface of active events, plus the extra copies and streams of the overlapped plane fit (chunk k works on
+  // surface k mod FIT_WAYS in stream k mod FIT_WAYS; way 0 is `sae` on the main stream)
+  uint2 *sae = nullptr, *sae_x[FIT_WAYS - 1] = {};
+  cudaStream_t fit_streams[FIT_WAYS - 1] = {};
+  cudaEvent_t ev_fit[FIT_WAYS - 1] = {};
   WorkSet ws[2];
   // halo store
   uint16_t *hx = nullptr, *hy = nullptr;
@@ -265,34 +269,41 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   if (((int *)c->h_small)[0]) return fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
 
   // ---- K3 plane fit, chunk by chunk against the chunk-end SAE snapshot ----
-  // Two surfaces and two streams: chunk k works on surface k mod 2 in stream k mod 2, so neighbouring chunks
-  // overlap (their kernels are short: launch gaps and tails would otherwise idle the GPU).  A surface skipped
-  // chunk k-1, so its advance step applies the chunks k-1 and k together.
+  // FIT_WAYS surfaces and streams: chunk k works on surface k mod FIT_WAYS in stream k mod FIT_WAYS, so
+  // neighbouring chunks overlap (their kernels are short: launch gaps and tails would otherwise idle the GPU).
+  // A surface skipped the chunks since its last turn, so its advance step applies them together with chunk k.
   const size_t FIT_CHUNK = (size_t)c->fit_chunk;
   const size_t scratch_bytes = (plane_fit_scratch_bytes(c->r, FIT_CHUNK) + 255) & ~(size_t)255;
-  if ((rc = ensure(c, c->fit_scratch, 2 * scratch_bytes))) return rc;
+  if ((rc = ensure(c, c->fit_scratch, FIT_WAYS * scratch_bytes))) return rc;
   FitParams fp{c->W, c->H, c->r, c->P, c->min_inl};
   FitOut fo{w.vx, w.vy, w.len, w.theta, w.lcx, w.lcy, w.valid, w.bw, w.inl, w.det};
-  CU(cudaMemcpyAsync(c->sae2, c->sae, c->npx * sizeof(uint2), cudaMemcpyDeviceToDevice, s));
+  for (int q = 0; q < FIT_WAYS - 1; q++)
+    CU(cudaMemcpyAsync(c->sae_x[q], c->sae, c->npx * sizeof(uint2), cudaMemcpyDeviceToDevice, s));
   CU(cudaEventRecord(c->ev_c0, s));
-  CU(cudaStreamWaitEvent(c->fit_stream, c->ev_c0, 0));
-  size_t prev_c0 = 0, nchunks = 0;
+  for (int q = 0; q < FIT_WAYS - 1; q++) CU(cudaStreamWaitEvent(c->fit_streams[q], c->ev_c0, 0));
+  size_t nchunks = 0;
   for (size_t c0 = 0; c0 < m; c0 += FIT_CHUNK, nchunks++) {
     const size_t c1 = std::min(m, c0 + FIT_CHUNK);
-    const bool odd = (nchunks & 1) != 0;
-    cudaStream_t st = odd ? c->fit_stream : s;
-    uint2 *surf = odd ? c->sae2 : c->sae;
-    launch_sae_advance(surf, w.pixkeep, w.et, w.nextp, (int)(nchunks ? prev_c0 : c0), (int)c1, st);
+    const int way = (int)(nchunks % FIT_WAYS);
+    cudaStream_t st = way ? c->fit_streams[way - 1] : s;
+    uint2 *surf = way ? c->sae_x[way - 1] : c->sae;
+    // first event this surface has not seen yet: the chunk after its previous turn
+    const size_t from = nchunks >= (size_t)FIT_WAYS ? c0 - (size_t)(FIT_WAYS - 1) * FIT_CHUNK : 0;
+    launch_sae_advance(surf, w.pixkeep, w.et, w.nextp, (int)from, (int)c1, st);
     *L += 1;
     if (c1 > h) {
       *L += launch_plane_fit(surf, w.prevp, w.ex, w.ey, w.et, (int)std::max(c0, h), (int)c1, fp, fo, c->d_counters,
-                             (char *)c->fit_scratch.p + (odd ? scratch_bytes : 0), st);
+                             (char *)c->fit_scratch.p + (size_t)way * scratch_bytes, st);
     }
-    prev_c0 = c0;
   }
-  CU(cudaEventRecord(c->ev_c1, c->fit_stream));
-  CU(cudaStreamWaitEvent(s, c->ev_c1, 0));
-  if (nchunks && !(nchunks & 1)) std::swap(c->sae, c->sae2);  // the last chunk ran on the second surface
+  for (int q = 0; q < FIT_WAYS - 1; q++) {
+    CU(cudaEventRecord(c->ev_fit[q], c->fit_streams[q]));
+    CU(cudaStreamWaitEvent(s, c->ev_fit[q], 0));
+  }
+  if (nchunks) {  // the surface of the last chunk holds the whole batch: it becomes the persistent one
+    const int way = (int)((nchunks - 1) % FIT_WAYS);
+    if (way) std::swap(c->sae, c->sae_x[way - 1]);
+  }
   launch_sae_finalize(c->sae, w.pixkeep, w.nextp, (int)m, s);
   *L += 1;
   CU(cudaEventRecord(c->ev[EV_FIT], s));
@@ -579,7 +590,10 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   if (const char *e = getenv("FARMS_POOL_IMPL")) c->pool_impl = strcmp(e, "bits") == 0 ? 2 : strcmp(e, "tile1") == 0 ? 3 : 1;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
-  if (cudaStreamCreateWithFlags(&c->fit_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+  for (int q = 0; q < FIT_WAYS - 1; q++) {
+    if (cudaStreamCreateWithFlags(&c->fit_streams[q], cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+    if (cudaEventCreateWithFlags(&c->ev_fit[q], cudaEventDisableTiming) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+  }
   if (cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   for (int i = 0; i < EV_COUNT; i++)
     if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(FARMS_ERR_CUDA);
@@ -591,7 +605,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   }
   bool ok = true;
   ok &= cudaMalloc((void **)&c->sae, c->npx * sizeof(uint2)) == cudaSuccess;
-  ok &= cudaMalloc((void **)&c->sae2, c->npx * sizeof(uint2)) == cudaSuccess;
+  for (int q = 0; q < FIT_WAYS - 1; q++) ok &= cudaMalloc((void **)&c->sae_x[q], c->npx * sizeof(uint2)) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->hx, HALO_CAP * 2) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->hy, HALO_CAP * 2) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->ht, HALO_CAP * 4) == cudaSuccess;
@@ -618,7 +632,12 @@ void farms_destroy(farms_ctx *c) {
   cudaDeviceSynchronize();
   free_owned(c->ws[0]);
   free_owned(c->ws[1]);
-  void *ps[] = {c->sae, c->sae2, c->hx, c->hy, c->ht, c->hm, c->hlen, c->hlcx, c->hlcy, c->d_err, c->d_counters, c->d_work,
+  for (int q = 0; q < FIT_WAYS - 1; q++) {
+    if (c->sae_x[q]) cudaFree(c->sae_x[q]);
+    if (c->fit_streams[q]) cudaStreamDestroy(c->fit_streams[q]);
+    if (c->ev_fit[q]) cudaEventDestroy(c->ev_fit[q]);
+  }
+  void *ps[] = {c->sae, c->hx, c->hy, c->ht, c->hm, c->hlen, c->hlcx, c->hlcy, c->d_err, c->d_counters, c->d_work,
                 c->d_small, c->in_x[0], c->in_y[0], c->in_t[0], c->in_x[1], c->in_y[1], c->in_t[1], c->sort_temp.p,
                 c->scan_temp.p, c->cell_start.p, c->fit_scratch.p, c->surf_tmp.p, c->item_ovf.p};
   for (void *p : ps)
@@ -631,7 +650,6 @@ void farms_destroy(farms_ctx *c) {
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
   if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
-  if (c->fit_stream) cudaStreamDestroy(c->fit_stream);
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
