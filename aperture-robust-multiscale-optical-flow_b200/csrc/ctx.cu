@@ -102,7 +102,8 @@ struct farms_ctx {
   // misc
   DevBuf sort_temp, scan_temp, cell_start, fit_scratch, surf_tmp, item_ovf;
   int *d_err = nullptr;
-  unsigned long long *d_counters = nullptr;  // [0] valid events, [1] pool candidates
+  unsigned long long *d_counters = nullptr;  // [0] valid events, [1] pool candidates, [2..4] events per pooling path
+  unsigned pool_kernels = 0;
   unsigned int *d_work = nullptr;
   uint32_t *d_small = nullptr;  // device scratch words
   uint32_t *h_small = nullptr;  // pinned host scratch words
@@ -262,6 +263,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   const uint32_t *skeys = which ? w.keyB : w.keyA, *svals = which ? w.valB : w.valA;
   launch_links(skeys, svals, w.et, c->sae, m, w.prevp, w.nextp, s);
   *L += 1;
+  CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev[EV_INDEX], s));
 
   // range errors are known by now without having stalled the sort
@@ -306,6 +308,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   }
   launch_sae_finalize(c->sae, w.pixkeep, w.nextp, (int)m, s);
   *L += 1;
+  CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev[EV_FIT], s));
 
   // ---- K4a pooling index: dense time slabs x tiles ----
@@ -328,7 +331,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   {
     const double span_us = (double)(c->h_small[5] - c->h_small[4]) + 1.0;
     const double per_region_us = flow_frac * (double)m * (132.0 * 132.0 / (double)c->npx) / span_us;
-    static const double target = getenv("FARMS_SLAB_TARGET") ? atof(getenv("FARMS_SLAB_TARGET")) : 70.0;  // tuning runs
+    const double target = c->cfg.slab_target ? (double)c->cfg.slab_target : 70.0;
     while (g.slab_shift < FARMS_SLAB_SHIFT_MAX && per_region_us * (double)(1u << g.slab_shift) < target) g.slab_shift++;
   }
   CU(cudaMemsetAsync(c->d_small, 0, 8, s));
@@ -358,6 +361,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   launch_build_records(skeys, svals, m, w.ex, w.ey, w.et, w.nextp, w.len, w.lcx, w.lcy, monotone, w.rec,
                        w.pay, (uint32_t *)c->cell_start.p, (uint32_t)ncells, s);
   *L += 2;
+  CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev[EV_BIN], s));
 
   // ---- K4b pooling ----
@@ -375,7 +379,8 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   const int fast = (monotone && !(c->cfg.flags & FARMS_FLAG_GENERIC_POOLING)) ? c->pool_impl : 0;
   *L += launch_pooling(w.rec, w.pay, (const uint32_t *)c->cell_start.p, w.slab_ids, w.slab_first, w.fin, (uint32_t *)c->item_ovf.p, w.done, m, (uint32_t)ncells,
                        (int)h, w.len, w.lcx, w.lcy, (int)nslabs, g, fast, flow_frac * (double)m / (double)nslabs, w.gr, w.gth, w.scale,
-                       c->d_work, c->d_counters + 1, c->num_sms, s);
+                       c->d_work, c->d_counters + 1, c->num_sms, s, &c->pool_kernels);
+  CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev[EV_POOL], s));
 
   // ---- results of the new events ----
@@ -412,7 +417,11 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaStreamSynchronize(s));
   size_t ts = c->h_small[0];
   c->last_M = c->h_small[1];
-  if (m - ts > HALO_CAP) ts = m - HALO_CAP;
+  // more than HALO_CAP events inside the pooling window (+ slack): truncating the halo would silently lose
+  // contributors for the next batch, so this is an error (timestamps in the wrong unit, or a pathological burst)
+  if (m - ts > HALO_CAP)
+    return fail(c, FARMS_ERR_STATE, "%zu events within the last %u us exceed the %zu-event history kept across batches",
+                m - ts, window, HALO_CAP);
   const size_t nh = m - ts;
   CU(cudaMemcpyAsync(c->hx, w.ex + ts, nh * 2, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemcpyAsync(c->hy, w.ey + ts, nh * 2, cudaMemcpyDeviceToDevice, s));
@@ -453,8 +462,9 @@ int process(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *
   const uint64_t maxb = c->cfg.max_batch ? c->cfg.max_batch : DEFAULT_MAX_BATCH;
   farms_timings &tm = c->tm;
   tm = farms_timings{};
-  CU(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), s));
+  CU(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), s));
   c->valid_seen = 0;
+  c->pool_kernels = 0;
   float stage[8] = {0};
   float h2d_ms = 0, d2h_ms = 0;
   CU(cudaEventRecord(c->ev[EV_START], s));
@@ -524,7 +534,7 @@ int process(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *
   CU(cudaStreamSynchronize(s));
   float total = 0;
   CU(cudaEventElapsedTime(&total, c->ev[EV_START], c->ev[EV_END]));
-  unsigned long long counters[2];
+  unsigned long long counters[8];
   CU(cudaMemcpy(counters, c->d_counters, sizeof counters, cudaMemcpyDeviceToHost));
   tm.total_ms = total;
   tm.h2d_ms = h2d_ms;
@@ -537,6 +547,8 @@ int process(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *
   tm.events = n;
   tm.valid_events = counters[0];
   tm.pool_candidates = counters[1];
+  tm.pool_kernels = c->pool_kernels;
+  for (int k = 0; k < 3; k++) tm.pool_events[k] = counters[2 + k];
   return FARMS_OK;
 }
 
@@ -586,8 +598,9 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   c->num_sms = prop.multiProcessorCount;
   c->fit_chunk = FIT_CHUNK_MIN;
   while (c->fit_chunk < FIT_CHUNK_MAX && (size_t)c->fit_chunk * 6 < c->npx) c->fit_chunk *= 2;
-  if (const char *e = getenv("FARMS_FIT_CHUNK")) c->fit_chunk = std::max(1024, atoi(e));  // tuning runs
-  if (const char *e = getenv("FARMS_POOL_IMPL")) c->pool_impl = strcmp(e, "bits") == 0 ? 2 : strcmp(e, "tile1") == 0 ? 3 : 1;
+  if (cfg->fit_chunk) c->fit_chunk = (int)std::min<uint32_t>(std::max<uint32_t>(cfg->fit_chunk, 1024u), 1u << 20);
+  if (cfg->pool_variant > 3) return bail(FARMS_ERR_ARG);
+  if (cfg->pool_variant) c->pool_impl = (int)cfg->pool_variant;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   for (int q = 0; q < FIT_WAYS - 1; q++) {
@@ -614,7 +627,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   ok &= cudaMalloc((void **)&c->hlcx, HALO_CAP * 8) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->hlcy, HALO_CAP * 8) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->d_err, sizeof(int)) == cudaSuccess;
-  ok &= cudaMalloc((void **)&c->d_counters, 2 * sizeof(unsigned long long)) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->d_work, 4 * sizeof(unsigned int)) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->d_small, 64) == cudaSuccess;
   ok &= cudaMallocHost((void **)&c->h_small, 64) == cudaSuccess;
@@ -733,9 +746,13 @@ int farms_slice_surface(farms_ctx *c, const uint16_t *d_x, const uint16_t *d_y, 
   int rc;
   if ((rc = ensure(c, c->surf_tmp, c->npx * sizeof(unsigned long long)))) return rc;
   CU(cudaMemsetAsync(c->surf_tmp.p, 0, c->npx * sizeof(unsigned long long), c->stream));
-  launch_slice_surface(d_x, d_y, d_t, (size_t)n, t0, c->H, (unsigned long long *)c->surf_tmp.p, c->stream);
+  CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+  launch_slice_surface(d_x, d_y, d_t, (size_t)n, t0, c->W, c->H, (unsigned long long *)c->surf_tmp.p, c->d_err, c->stream);
   launch_unpack_surface((const unsigned long long *)c->surf_tmp.p, c->npx, d_last_t, d_hit, c->stream);
+  k_publish<<<1, 32, 0, c->stream>>>(c->h_small, (const uint32_t *)c->d_err, 1);
+  CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
+  if (((int *)c->h_small)[0]) return fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
   return FARMS_OK;
 }
 

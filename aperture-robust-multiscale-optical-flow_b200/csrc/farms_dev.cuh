@@ -75,8 +75,8 @@ void launch_links(const uint32_t *skeys, const uint32_t *svals, const uint32_t *
                   int2 *prevp, int32_t *nextp, cudaStream_t s);
 void launch_slab_flags(const uint32_t *em, const uint32_t *et, size_t m, int slab_shift, uint32_t *flags, uint32_t *nonmono,
                        cudaStream_t s);
-void launch_slice_surface(const uint16_t *x, const uint16_t *y, const uint64_t *t, size_t n, uint64_t t0, int H,
-                          unsigned long long *packed, cudaStream_t s);
+void launch_slice_surface(const uint16_t *x, const uint16_t *y, const uint64_t *t, size_t n, uint64_t t0, int W, int H,
+                          unsigned long long *packed, int *err_flag, cudaStream_t s);
 void launch_unpack_surface(const unsigned long long *packed, size_t npx, uint32_t *last_t, uint8_t *hit,
                            cudaStream_t s);
 
@@ -104,11 +104,14 @@ void launch_build_records(const uint32_t *skeys, const uint32_t *sidx, size_t m,
                           const double *lcx, const double *lcy, int monotone, uint4 *rec, double *pay,
                           uint32_t *cell_start, uint32_t ncells, cudaStream_t s);
 // returns the number of kernels launched.  work_counter: four zeroed words; done: m zeroed bytes; fin: m - h zeroed words.
+// cand_count: four counters {candidates inspected, events pooled by the first fast pass, by the flagged second pass,
+// by k_pool_any}; kernels_used: FARMS_POOLK_* bits of the kernels launched are OR-ed in.
 int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_start, const uint32_t *slab_ids,
                    const uint32_t *slab_first, uint32_t *fin, uint32_t *item_ovf, uint8_t *done, size_t m, uint32_t ncells, int h,
                    const double *ev_len, const double *ev_lcx, const double *ev_lcy, int nslabs, PoolGeom g, int fast,
                    double flow_per_slab, double *global_r, double *global_theta, uint8_t *scale,
-                   unsigned int *work_counter, unsigned long long *cand_count, int num_sms, cudaStream_t s);
+                   unsigned int *work_counter, unsigned long long *cand_count, int num_sms, cudaStream_t s,
+                   unsigned *kernels_used);
 int pool_tile_smem_bytes();
 // words of the zeroed item_ovf array launch_pooling needs
 size_t pool_item_words(int W, int H, int nslabs);

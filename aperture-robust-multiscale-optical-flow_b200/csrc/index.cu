@@ -72,14 +72,18 @@ __global__ void k_slab_flags(const uint32_t *__restrict__ em, const uint32_t *__
 }
 
 __global__ void k_slice_surface(const uint16_t *__restrict__ x, const uint16_t *__restrict__ y,
-                                const uint64_t *__restrict__ t, size_t n, uint64_t t0, int H,
-                                unsigned long long *__restrict__ packed) {
+                                const uint64_t *__restrict__ t, size_t n, uint64_t t0, int W, int H,
+                                unsigned long long *__restrict__ packed, int *__restrict__ err) {
   size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   // Walk the slice backwards: blocks are scheduled roughly in order, so the latest events arrive first and
   // almost every earlier event of the same pixel sees a larger value already and skips its atomic.
   const size_t i = n - 1 - k;
   const uint32_t tr = (uint32_t)(t[i] - t0);
+  if (x[i] >= (uint32_t)W || y[i] >= (uint32_t)H) {  // same rule as k_ingest: FARMS_ERR_RANGE, never an OOB write
+    atomicOr(err, 1);
+    return;
+  }
   unsigned long long *cell = &packed[(size_t)x[i] * H + y[i]];
   // later index wins: index in the high word
   const unsigned long long mine = ((unsigned long long)(i + 1) << 32) | tr;
@@ -127,9 +131,9 @@ void launch_slab_flags(const uint32_t *em, const uint32_t *et, size_t m, int sla
                        cudaStream_t s) {
   if (m) k_slab_flags<<<nb(m, 256), 256, 0, s>>>(em, et, m, slab_shift, flags, nonmono);
 }
-void launch_slice_surface(const uint16_t *x, const uint16_t *y, const uint64_t *t, size_t n, uint64_t t0, int H,
-                          unsigned long long *packed, cudaStream_t s) {
-  if (n) k_slice_surface<<<nb(n, 256), 256, 0, s>>>(x, y, t, n, t0, H, packed);
+void launch_slice_surface(const uint16_t *x, const uint16_t *y, const uint64_t *t, size_t n, uint64_t t0, int W, int H,
+                          unsigned long long *packed, int *err_flag, cudaStream_t s) {
+  if (n) k_slice_surface<<<nb(n, 256), 256, 0, s>>>(x, y, t, n, t0, W, H, packed, err_flag);
 }
 void launch_unpack_surface(const unsigned long long *packed, size_t npx, uint32_t *last_t, uint8_t *hit,
                            cudaStream_t s) {

@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include "../../include/farms_b200.h"
 #include "farms_dev.cuh"
 
 namespace {
@@ -116,6 +117,7 @@ struct PoolArgs {
   uint8_t *scale;
   unsigned int *work_counter;
   unsigned long long *cand_count;
+  unsigned long long *path_count;  // events pooled by: [0] first fast pass, [1] flagged second pass, [2] k_pool_any
 };
 
 // ring sums of one event -> nested-square means -> arg-max scale -> outputs.  rl/rx/ry/rn hold ring k's
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
   const size_t m = A.m;
   const uint32_t mi = A.cell_start[A.ncells];
   const double *pay_len = A.pay, *pay_cx = A.pay + m, *pay_cy = A.pay + 2 * m;
-  unsigned long long ncand = 0;
+  unsigned long long ncand = 0, npooled = 0;
 
   constexpr unsigned int CHUNK = 32;  // index positions per grab: few atomics even when almost nothing is left to pool
   for (unsigned int base = 0, chunk_end = 0;; base += 32) {
@@ -278,9 +280,11 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
       }
       __syncwarp();
       finish_event<32>(A, lane, rl, rx, ry, rn, pay_cx[tpos], pay_cy[tpos], ii - A.h, true);
+      npooled++;
     }
   }
   if (lane == 0 && ncand) atomicAdd(A.cand_count, ncand);
+  if (lane == 0 && npooled) atomicAdd(A.path_count + 2, npooled);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -344,7 +348,9 @@ __device__ void stage_slabs(const PoolArgs &A, SM &S, int s0, int s1, const Regi
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ts = A.g.tile_shift, nty = A.g.nty, NT = A.g.ntx * A.g.nty, H = A.g.H;
   const int tx0 = R.rx0 >> ts, tx1 = R.rx1 >> ts, ty0 = R.ry0 >> ts, ty1 = R.ry1 >> ts;
-  const int nrun0 = tx1 - tx0 + 1;
+  // On a sensor taller than wide the reference's row bound (width - 1) can lie above the whole region
+  // (ry1 < ry0): no logical row of such an owner tile is reachable and nothing is staged.
+  const int nrun0 = R.ry1 >= R.ry0 ? tx1 - tx0 + 1 : 0;
   const int atx0 = R.ax0 >> ts, atx1 = R.ax1 >> ts;
   const int nrun1 = R.ay1 >= 0 ? atx1 - atx0 + 1 : 0;
   const int nrun = nrun0 + nrun1;
@@ -569,6 +575,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
   const int W = A.g.W, H = A.g.H, nty = A.g.nty, NT = A.g.ntx * A.g.nty;
   const unsigned int nitems = (unsigned int)otx_n * oty_n * nseg;
   unsigned long long ncand = 0;
+  unsigned int npooled = 0;
 
   for (;;) {
     __syncthreads();
@@ -804,7 +811,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
           }
           const bool fin = finish_event_checked(A, sub, rl, rx, ry, (int)rnf, (int)ii - A.h, have);
 
-          if (sub == 0 && fin) A.done[tpos] = 1;
+          if (sub == 0 && fin) {
+            A.done[tpos] = 1;
+            npooled++;
+          }
           // ---- undecided targets (a rival scale within the FP32 noise, cancelling vectors): pool them again
           // exactly, FP64 partials and the FP64 flow values of the contributors, one half-warp at a time
           // (the FP64 partials of one target take the warp's whole accumulator space) ----
@@ -851,13 +861,17 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
             }
             __syncwarp();
             finish_event<16>(A, sub, el, ex2, ey2, en, A.ev_lcx[ii], A.ev_lcy[ii], (int)ii - A.h, half == hsel);
-            if (half == hsel && sub == 0) A.done[tpos] = 1;
+            if (half == hsel && sub == 0) {
+              A.done[tpos] = 1;
+              npooled++;
+            }
           }
         }
       }
     }
   }
   if ((lane & 15) == 0 && ncand) atomicAdd(A.cand_count, ncand);
+  if ((lane & 15) == 0 && npooled) atomicAdd(A.path_count + (SECOND ? 1 : 0), (unsigned long long)npooled);
 }
 
 template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND>
@@ -866,12 +880,10 @@ void launch_tile(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
   using SM = TileSmem<WARPS, CAP, NSL>;
   static_assert(sizeof(SM) <= (CTAS == 2 ? 115712 : 232448), "shared memory of the tile kernel: 227 KB per CTA, 228 KB per SM");
   auto kern = k_pool_tile<WARPS, CAP, NSL, CTAS, SECOND>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    attr_set = true;
-  }
+  // per device/context, so set on every launch (a process-wide flag would leave every device but the first
+  // without the opt-in to > 48 KB of dynamic shared memory)
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   const int otx = (A.g.W + OT - 1) >> OT_SHIFT, oty = (A.g.H + OT - 1) >> OT_SHIFT;
   const int nseg = (nslabs + TK_SEG - 1) / TK_SEG;
   const long long items = (long long)otx * oty * nseg;
@@ -990,6 +1002,7 @@ __global__ void __launch_bounds__(BP_THREADS, 2) k_pool_bits(PoolArgs A, int otx
   const unsigned int nitems = (unsigned int)otx_n * oty_n * nseg;
   const double *pay_cx = A.pay + A.m, *pay_cy = A.pay + 2 * A.m;
   unsigned long long ncand = 0;
+  unsigned int npooled = 0;
 
   for (;;) {
     __syncthreads();
@@ -1013,7 +1026,7 @@ __global__ void __launch_bounds__(BP_THREADS, 2) k_pool_bits(PoolArgs A, int otx
     R.ax1 = min(R.rx1 + 1, W - 1);
     if (R.ax0 > R.ax1) R.ay1 = -1;
     const int tx0 = R.rx0 >> ts, tx1 = R.rx1 >> ts, ty0 = R.ry0 >> ts, ty1 = R.ry1 >> ts;
-    const int nrun0 = tx1 - tx0 + 1;
+    const int nrun0 = R.ry1 >= R.ry0 ? tx1 - tx0 + 1 : 0;  // empty on tall sensors whose row bound is above the region
     const int atx0 = R.ax0 >> ts, atx1 = R.ax1 >> ts;
     const int nrun1 = R.ay1 >= 0 ? atx1 - atx0 + 1 : 0;
     const int nrun = nrun0 + nrun1;
@@ -1397,12 +1410,14 @@ __global__ void __launch_bounds__(BP_THREADS, 2) k_pool_bits(PoolArgs A, int otx
           A.global_theta[out_index] = by;
           A.fin[out_index] = (uint32_t)bn | ((uint32_t)bk << 16);
           A.done[S.s_pos[qc]] = 1;
+          npooled++;
         }
       }
       d += nd;
     }
   }
   if (ncand) atomicAdd(A.cand_count, ncand);
+  if (npooled) atomicAdd(A.path_count, (unsigned long long)npooled);
 }
 
 // Second half of the fast path's output: mean vector = sums / count, then length and angle (src/vFlow.cpp:365-366).
@@ -1421,12 +1436,8 @@ __global__ void k_pool_finish(const uint32_t *__restrict__ fin, size_t n, double
 
 void launch_bits(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
   PoolArgs A = A0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_pool_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BitsSmem));
-    cudaFuncSetAttribute(k_pool_bits, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(k_pool_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BitsSmem));
+  cudaFuncSetAttribute(k_pool_bits, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   const int otx = (A.g.W + OT - 1) >> OT_SHIFT, oty = (A.g.H + OT - 1) >> OT_SHIFT;
   const int nseg = (nslabs + TK_SEG - 1) / TK_SEG;
   const long long items = (long long)otx * oty * nseg;
@@ -1465,10 +1476,12 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
                    const uint32_t *slab_first, uint32_t *fin, uint32_t *item_ovf, uint8_t *done, size_t m, uint32_t ncells, int h,
                    const double *ev_len, const double *ev_lcx, const double *ev_lcy, int nslabs, PoolGeom g, int fast,
                    double flow_per_slab, double *global_r, double *global_theta, uint8_t *scale,
-                   unsigned int *work_counter, unsigned long long *cand_count, int num_sms, cudaStream_t s) {
+                   unsigned int *work_counter, unsigned long long *cand_count, int num_sms, cudaStream_t s,
+                   unsigned *kernels_used) {
   if (!m) return 0;
   int launches = 0;
   PoolArgs A;
+  A.path_count = cand_count + 1;
   A.rec = rec; A.pay = pay; A.cell_start = cell_start; A.slab_ids = slab_ids; A.done = done;
   A.slab_first = slab_first; A.fin = fin; A.item_ovf = item_ovf;
   A.ev_len = ev_len; A.ev_lcx = ev_lcx; A.ev_lcy = ev_lcy;
@@ -1477,19 +1490,27 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
   A.cand_count = cand_count;
   if (fast && g.tile_shift == 4) {
     A.work_counter = work_counter;
-    if (fast == 2) launch_bits(A, nslabs, num_sms, s);  // bit-table variant: 8 warps, 2 CTAs per SM, ~110 KB each
-    else if (fast == 3) launch_tile<16, 768, 4, 1, false>(A, nslabs, num_sms, s);  // 16 warps, 1 CTA per SM, ~222 KB
-    else {
+    if (fast == 2) {
+      launch_bits(A, nslabs, num_sms, s);  // bit-table variant: 8 warps, 2 CTAs per SM, ~110 KB each
+      if (kernels_used) *kernels_used |= FARMS_POOLK_BITS;
+    } else if (fast == 3) {
+      launch_tile<16, 768, 4, 1, false>(A, nslabs, num_sms, s);  // 16 warps, 1 CTA per SM, ~222 KB
+      if (kernels_used) *kernels_used |= FARMS_POOLK_TILE_ONE_CTA;
+    } else {
       // flow events a slab holds inside one (32+100)^2 region, from the batch average
       const double per_region = flow_per_slab * 17424.0 / ((double)g.W * (double)g.H);
-      if (per_region < 200.0)  // thin slabs: 4 per round keep the round's task list full (320-record slots)
+      if (per_region < 200.0) {  // thin slabs: 4 per round keep the round's task list full (320-record slots)
         launch_tile<8, 320, 4, 2, false>(A, nslabs, num_sms, s);
-      else
+        if (kernels_used) *kernels_used |= FARMS_POOLK_TILE_SPARSE;
+      } else {
         launch_tile<8, 512, 2, 2, false>(A, nslabs, num_sms, s);  // 8 warps, 2 CTAs per SM, ~112 KB each
-      // rounds whose staging overflowed those slots (locally dense scenes) get a second chance with 640-record
+        if (kernels_used) *kernels_used |= FARMS_POOLK_TILE_DENSE;
+      }
+      // rounds whose staging overflowed those slots (locally dense scenes) get a second chance with 768-record
       // slots before the general kernel takes what is left
       A.work_counter = work_counter + 2;
       launch_tile<16, 768, 4, 1, true>(A, nslabs, num_sms, s);
+      if (kernels_used) *kernels_used |= FARMS_POOLK_TILE_SECOND;
       launches++;
     }
     const size_t nout = m - (size_t)h;
@@ -1502,8 +1523,8 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
   unsigned grid = (unsigned)num_sms * 5u;
   unsigned need = nb(m, 32 * PW);
   if (grid > need) grid = need;
-  static const bool skip_any = getenv("FARMS_DEBUG_SKIP_ANY") != nullptr;  // timing experiments only
-  if (!skip_any) k_pool_any<<<grid, PW * 32, 0, s>>>(A);
+  k_pool_any<<<grid, PW * 32, 0, s>>>(A);
+  if (kernels_used) *kernels_used |= FARMS_POOLK_ANY;
   launches++;
   return launches;
 }

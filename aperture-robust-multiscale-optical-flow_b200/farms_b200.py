@@ -16,6 +16,8 @@ OK, ERR_ARG, ERR_RANGE, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4, -5
 FLAG_DEBUG_DET = 1
 FLAG_EXACT_POOLING = 2
 FLAG_GENERIC_POOLING = FLAG_EXACT_POOLING
+POOLK_TILE_DENSE, POOLK_TILE_SPARSE, POOLK_TILE_SECOND, POOLK_TILE_ONE_CTA, POOLK_BITS, POOLK_ANY = 1, 2, 4, 8, 16, 32
+POOL_VARIANTS = {"tile": 1, "bits": 2, "tile1": 3}
 
 EXPORTS = [
     "farms_abi_version", "farms_create", "farms_destroy", "farms_reset", "farms_last_error", "farms_normalize_filtersize", "farms_get_params",
@@ -28,7 +30,8 @@ EXPORTS = [
 class Config(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("filtersize", C.c_int32),
                 ("inlier_check", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32),
-                ("max_batch", C.c_uint64), ("reorder_slack_us", C.c_uint32), ("reserved", C.c_uint32 * 7)]
+                ("max_batch", C.c_uint64), ("reorder_slack_us", C.c_uint32), ("pool_variant", C.c_uint32),
+                ("fit_chunk", C.c_uint32), ("slab_target", C.c_uint32), ("reserved", C.c_uint32 * 4)]
 
 
 class Out(C.Structure):
@@ -45,10 +48,13 @@ class Timings(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("h2d_ms", C.c_float), ("ingest_ms", C.c_float),
                 ("index_ms", C.c_float), ("fit_ms", C.c_float), ("bin_ms", C.c_float), ("pool_ms", C.c_float),
                 ("d2h_ms", C.c_float), ("events", C.c_uint64), ("valid_events", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("pool_candidates", C.c_uint64), ("reserved", C.c_uint64 * 4)]
+                ("kernel_launches", C.c_uint64), ("pool_candidates", C.c_uint64), ("pool_kernels", C.c_uint64),
+                ("pool_events", C.c_uint64 * 3)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "pool_events"}
+        d["pool_events_first"], d["pool_events_second"], d["pool_events_general"] = (int(v) for v in self.pool_events)
+        return d
 
 
 _lib = None
@@ -96,10 +102,12 @@ class Farms:
     (reference include/vFlow.h:99-104) on top of the C ABI."""
 
     def __init__(self, width, height, filtersize=3, inlier_check=5, device=0, flags=0, max_batch=0,
-                 reorder_slack_us=0):
+                 reorder_slack_us=0, pool_variant=0, fit_chunk=0, slab_target=0):
         L = lib()
         cfg = Config(width=width, height=height, filtersize=filtersize, inlier_check=inlier_check, device=device,
-                     flags=flags, max_batch=max_batch, reorder_slack_us=reorder_slack_us)
+                     flags=flags, max_batch=max_batch, reorder_slack_us=reorder_slack_us,
+                     pool_variant=POOL_VARIANTS.get(pool_variant, pool_variant), fit_chunk=fit_chunk,
+                     slab_target=slab_target)
         self._h = C.c_void_p()
         rc = L.farms_create(C.byref(self._h), C.byref(cfg))
         if rc != OK:

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define FARMS_B200_ABI_VERSION 1
+#define FARMS_B200_ABI_VERSION 2
 
 typedef enum {
   FARMS_OK = 0,
@@ -49,7 +49,12 @@ typedef struct {
   uint64_t max_batch;       /* events per internal device batch; 0 = default (16 Mi)               */
   uint32_t reorder_slack_us;/* extra history (us) kept across batch boundaries for streams whose
                                timestamps are not perfectly sorted; 0 = default (1000)            */
-  uint32_t reserved[7];
+  /* Tuning / test selectors (0 = the library's own choice; never read from the environment): */
+  uint32_t pool_variant;    /* fast pooling kernel: 0/1 staged-list k_pool_tile, 2 bit-table k_pool_bits, 3 the
+                               one-CTA-per-SM instantiation of k_pool_tile (both alternatives are parity-tested) */
+  uint32_t fit_chunk;       /* events per plane-fit chunk (SAE snapshot interval); 0 = from the sensor size  */
+  uint32_t slab_target;     /* flow events per (tile region, time slab) the slab length is chosen for; 0 = 70 */
+  uint32_t reserved[4];
 } farms_config;
 
 #define FARMS_FLAG_DEBUG_DET 1u       /* also produce the determinant column (farms_out.det)       */
@@ -95,8 +100,18 @@ typedef struct {
   uint64_t valid_events; /* events with valid local flow                                           */
   uint64_t kernel_launches;
   uint64_t pool_candidates; /* candidate flow events inspected by the pooling kernel               */
-  uint64_t reserved[4];
+  uint64_t pool_kernels;    /* FARMS_POOLK_* bits: which pooling kernels were launched              */
+  uint64_t pool_events[3];  /* events pooled by [0] the first fast pass (FP32 partials, or its in-kernel FP64
+                               re-pool when the scale decision was not clear-cut), [1] the flagged second pass
+                               with larger slots, [2] the general exact kernel k_pool_any                */
 } farms_timings;
+
+#define FARMS_POOLK_TILE_DENSE 1u    /* k_pool_tile<8 warps, 512-record slots, 2 slabs per round, 2 CTAs/SM> */
+#define FARMS_POOLK_TILE_SPARSE 2u   /* k_pool_tile<8, 320, 4, 2>: thin slabs                                 */
+#define FARMS_POOLK_TILE_SECOND 4u   /* k_pool_tile<16, 768, 4, 1>, flagged second pass                      */
+#define FARMS_POOLK_TILE_ONE_CTA 8u  /* k_pool_tile<16, 768, 4, 1> as the first pass (pool_variant 3)        */
+#define FARMS_POOLK_BITS 16u         /* k_pool_bits (pool_variant 2)                                         */
+#define FARMS_POOLK_ANY 32u          /* k_pool_any                                                           */
 
 /* ---- lifetime: replaces `vFlowManager vFlowM(...)` (src/main.cpp:186) ---- */
 int farms_create(farms_ctx **out, const farms_config *cfg);

@@ -35,6 +35,29 @@ struct farms_oracle {
   double *last_time; /* lastEventTime          vFlow.cpp:66  */
   double *len;       /* flowSurfaceLengthOn/Of (always written identically, vFlow.cpp:349-353) */
   double *theta;     /* flowSurfaceThetaOn/Of  */
+  /* ---- fast pooling mode (farms_oracle_set_fast): a FILTER in front of the same arithmetic ----
+   * `active` is a bitmap over the flat index holding a superset of the cells that can pass the test of
+   * vFlow.cpp:1002 (len > 0 and |t - lastEventTime| < 500); compute_true_flow_fast visits only those cells, in
+   * the reference's own order, applies the same test and adds in the same order, so every sum is bit-identical
+   * to compute_true_flow's.  A cell leaves the set when an event without flow overwrites it (vFlow.cpp:398-402)
+   * or when its latest event is 500 us old, which is final only while timestamps are non-decreasing: the first
+   * decreasing timestamp switches the oracle back to the plain scan for good. */
+  int fast;
+  uint32_t tmax;
+  uint64_t seq;
+  uint64_t *active;
+  double *lcos, *lsin; /* len*cos(theta), len*sin(theta) as evaluated at vFlow.cpp:1007-1008 (pure functions) */
+  uint64_t *last_seq;  /* sequence number of the latest event of the pixel */
+  struct fifo_ent *fifo; /* flow events in stream order, oldest first (ring buffer) */
+  size_t fifo_cap, fifo_head, fifo_len;
+  uint32_t *hit_i, *hit_j; /* scratch: contributing logical cells of the widest window */
+  size_t *hit_f;
+};
+
+struct fifo_ent {
+  size_t f;
+  uint32_t t;
+  uint64_t seq;
 };
 
 farms_oracle *farms_oracle_create(int width, int height, int filtersize, int inlier_check) {
@@ -64,6 +87,14 @@ farms_oracle *farms_oracle_create(int width, int height, int filtersize, int inl
 
 void farms_oracle_destroy(farms_oracle *o) {
   if (!o) return;
+  free(o->active);
+  free(o->lcos);
+  free(o->lsin);
+  free(o->last_seq);
+  free(o->fifo);
+  free(o->hit_i);
+  free(o->hit_j);
+  free(o->hit_f);
   free(o->sae);
   free(o->hit);
   free(o->last_time);
@@ -71,6 +102,31 @@ void farms_oracle_destroy(farms_oracle *o) {
   free(o->theta);
   free(o);
 }
+
+int farms_oracle_set_fast(farms_oracle *o, int on) {
+  if (!o) return -1;
+  if (!on) {
+    o->fast = 0;
+    return 0;
+  }
+  if (o->seq) return -1; /* only before the first event: the filter is built incrementally */
+  const size_t npx = (size_t)o->width * (size_t)o->height;
+  const size_t nhit = (size_t)(2 * MAX_WINDOW + 1) * (2 * MAX_WINDOW + 1);
+  o->active = (uint64_t *)calloc((npx + 63) / 64 + 1, sizeof(uint64_t));
+  o->lcos = (double *)calloc(npx, sizeof(double));
+  o->lsin = (double *)calloc(npx, sizeof(double));
+  o->last_seq = (uint64_t *)calloc(npx, sizeof(uint64_t));
+  o->fifo_cap = 1u << 16;
+  o->fifo = (struct fifo_ent *)malloc(o->fifo_cap * sizeof(struct fifo_ent));
+  o->hit_i = (uint32_t *)malloc(nhit * sizeof(uint32_t));
+  o->hit_j = (uint32_t *)malloc(nhit * sizeof(uint32_t));
+  o->hit_f = (size_t *)malloc(nhit * sizeof(size_t));
+  if (!o->active || !o->lcos || !o->lsin || !o->last_seq || !o->fifo || !o->hit_i || !o->hit_j || !o->hit_f) return -1;
+  o->fast = 1;
+  return 0;
+}
+
+int farms_oracle_is_fast(const farms_oracle *o) { return o ? o->fast : 0; }
 
 void farms_oracle_state(const farms_oracle *o, double *last_time, uint8_t *hit, double *len,
                         double *theta) {
@@ -314,6 +370,120 @@ static void compute_true_flow(const farms_oracle *o, int x, int y, uint32_t time
   }
 }
 
+/* The same function with the `active` filter in front (see struct farms_oracle).  The contributing cells of
+ * the widest square are collected once in the reference's enumeration order (i ascending, j ascending,
+ * vFlow.cpp:998-1000; logical cells, so an aliased pixel counts once per logical cell that maps to it); every
+ * smaller square's cells are a subsequence of that list, so walking the list with the square's bounds performs
+ * the reference's additions in the reference's order. */
+static void compute_true_flow_fast(farms_oracle *o, int x, int y, uint32_t time_, double *out_vx, double *out_vy,
+                                   int *out_scale) {
+  const int W = o->width, H = o->height;
+  const size_t npx = (size_t)W * (size_t)H;
+  const double tev = (double)time_;
+  size_t nh = 0;
+  const int xlo = imax(0, x - MAX_WINDOW), xhi = imin(x + MAX_WINDOW, W - 1);
+  const int jlo = imax(0, y - MAX_WINDOW), jhi = imin(y + MAX_WINDOW, W - 1); /* :1000 (sic) */
+  for (int i = xlo; i <= xhi && jlo <= jhi; i++) {
+    size_t f0 = (size_t)i * H + jlo, f1 = (size_t)i * H + jhi;
+    if (f0 >= npx) break;
+    if (f1 >= npx) f1 = npx - 1;
+    for (size_t w = f0 >> 6; w <= (f1 >> 6); w++) {
+      uint64_t bits = o->active[w];
+      if (w == (f0 >> 6)) bits &= ~0ull << (f0 & 63);
+      if (w == (f1 >> 6) && (f1 & 63) != 63) bits &= (1ull << ((f1 & 63) + 1)) - 1;
+      while (bits) {
+        const size_t f = (w << 6) + (size_t)__builtin_ctzll(bits);
+        bits &= bits - 1;
+        if (o->len[f] > 0 && (fabs(tev - o->last_time[f]) < KILL_OLD_FLOW_TIME)) { /* :1002 */
+          o->hit_i[nh] = (uint32_t)i;
+          o->hit_j[nh] = (uint32_t)(f - (size_t)i * H);
+          o->hit_f[nh] = f;
+          nh++;
+        }
+      }
+    }
+  }
+  double pool[NSCALES], vecx[NSCALES], vecy[NSCALES];
+  int nwin = 0;
+  for (int s = 0; s <= MAX_WINDOW; s += WINDOW_JUMP) { /* :987 */
+    double length_sp = 0, sx = 0, sy = 0, nn = 0;
+    const int ia = x - s, ib = x + s, ja = y - s, jb = y + s;
+    for (size_t k = 0; k < nh; k++) {
+      const int i = (int)o->hit_i[k], j = (int)o->hit_j[k];
+      if (i < ia || i > ib || j < ja || j > jb) continue;
+      const size_t f = o->hit_f[k];
+      length_sp = length_sp + o->len[f]; /* :1005 */
+      sx = sx + o->lcos[f];              /* :1007 */
+      sy = sy + o->lsin[f];              /* :1008 */
+      nn++;                              /* :1012 */
+    }
+    if (nn > 0) { /* :1023-1036 */
+      pool[nwin] = length_sp / nn;
+      vecx[nwin] = sx / nn;
+      vecy[nwin] = sy / nn;
+    } else {
+      pool[nwin] = 0;
+      vecx[nwin] = 0;
+      vecy[nwin] = 0;
+    }
+    nwin++;
+  }
+  double max_val = 0; /* :1047-1059 */
+  int max_idx = 0;
+  for (int k = 0; k < nwin; k++)
+    if (pool[k] > max_val) {
+      max_val = pool[k];
+      max_idx = k;
+    }
+  if (max_val > 0) { /* :1067-1078 */
+    *out_vx = vecx[max_idx];
+    *out_vy = vecy[max_idx];
+    *out_scale = max_idx * WINDOW_JUMP;
+  } else { /* :1085-1094 */
+    size_t f = (size_t)x * H + y;
+    *out_vx = o->len[f] * cos(o->theta[f]);
+    *out_vy = o->len[f] * sin(o->theta[f]);
+    *out_scale = 0;
+  }
+}
+
+/* fast mode bookkeeping for one event whose surfaces were just written */
+static void fast_note_event(farms_oracle *o, size_t f, uint32_t time_, int valid) {
+  o->seq++;
+  o->last_seq[f] = o->seq;
+  if (!valid) {
+    o->active[f >> 6] &= ~(1ull << (f & 63));
+    return;
+  }
+  o->active[f >> 6] |= 1ull << (f & 63);
+  o->lcos[f] = o->len[f] * cos(o->theta[f]);
+  o->lsin[f] = o->len[f] * sin(o->theta[f]);
+  if (o->fifo_len == o->fifo_cap) { /* grow the ring buffer, oldest entry to slot 0 */
+    struct fifo_ent *nf = (struct fifo_ent *)malloc(2 * o->fifo_cap * sizeof(struct fifo_ent));
+    for (size_t k = 0; k < o->fifo_len; k++) nf[k] = o->fifo[(o->fifo_head + k) % o->fifo_cap];
+    free(o->fifo);
+    o->fifo = nf;
+    o->fifo_head = 0;
+    o->fifo_cap *= 2;
+  }
+  struct fifo_ent *e = &o->fifo[(o->fifo_head + o->fifo_len) % o->fifo_cap];
+  e->f = f;
+  e->t = time_;
+  e->seq = o->seq;
+  o->fifo_len++;
+}
+
+/* drop cells whose latest event is >= 500 us older than `now` (final for non-decreasing timestamps) */
+static void fast_expire(farms_oracle *o, uint32_t now) {
+  while (o->fifo_len) {
+    const struct fifo_ent *e = &o->fifo[o->fifo_head];
+    if ((double)now - (double)e->t < KILL_OLD_FLOW_TIME) break;
+    if (o->last_seq[e->f] == e->seq) o->active[e->f >> 6] &= ~(1ull << (e->f & 63));
+    o->fifo_head = (o->fifo_head + 1) % o->fifo_cap;
+    o->fifo_len--;
+  }
+}
+
 /* Loop body of runFileCopy  vFlow.cpp:223-414 */
 int farms_oracle_process(farms_oracle *o, const int32_t *X, const int32_t *Y, const uint32_t *T,
                          const int32_t *POL, uint64_t n, const farms_oracle_out *out) {
@@ -326,6 +496,10 @@ int farms_oracle_process(farms_oracle *o, const int32_t *X, const int32_t *Y, co
       o->have_t0 = 1;
     }
     uint32_t time_ = T[e] - o->t0; /* :241 (unsigned wrap) */
+    if (o->fast) {
+      if (time_ < o->tmax) o->fast = 0; /* timestamps decreased: the filter's expiry is no longer final */
+      else o->tmax = time_;
+    }
     int pol = POL[e];
     if (pol < 0) pol = 0; /* :246 */
     size_t f = (size_t)x * H + y;
@@ -350,7 +524,12 @@ int farms_oracle_process(farms_oracle *o, const int32_t *X, const int32_t *Y, co
       o->len[f] = length;                        /* :349-353 */
       o->theta[f] = theta;
       double tvx = 0, tvy = 0;
-      compute_true_flow(o, x, y, time_, &tvx, &tvy, &scale); /* :362 */
+      if (o->fast) {
+        fast_note_event(o, f, time_, 1);
+        fast_expire(o, time_);
+        compute_true_flow_fast(o, x, y, time_, &tvx, &tvy, &scale);
+      } else
+        compute_true_flow(o, x, y, time_, &tvx, &tvy, &scale); /* :362 */
       gr = sqrt(tvy * tvy + tvx * tvx);                      /* :365 */
       gth = atan2(tvy, tvx);                                 /* :366 */
       lr = length;
@@ -358,6 +537,7 @@ int farms_oracle_process(farms_oracle *o, const int32_t *X, const int32_t *Y, co
     } else {
       o->len[f] = 0; /* :398-402 */
       o->theta[f] = 0;
+      if (o->fast) fast_note_event(o, f, time_, 0);
     }
     o->last_time[f] = (double)time_; /* :407 */
     if (out) {

@@ -2,7 +2,8 @@
  * Runs the tier-2 oracle over "<base>.txt" and writes "<base>_FARMSOut_oracle.txt" in the reference's
  * 11-column batch format (vFlow.cpp:436-440; ostream default == "%g"), so it can be diffed against
  * the tier-1 build's "<base>_FARMSOut_batch.txt".
- * usage: farms_oracle_cli <width> <height> <filtersize> <inlierCheck> <base> [numEvents] */
+ * usage: farms_oracle_cli <width> <height> <filtersize> <inlierCheck> <base> [numEvents]
+ * FARMS_ORACLE_FAST=1 selects the fast pooling mode (farms_oracle_set_fast). */
 #include <stdio.h>
 #include <stdlib.h>
 #include <time.h>
@@ -33,6 +34,7 @@ int main(int argc, char **argv) {
   o.local_r = malloc(n * 8); o.local_theta = malloc(n * 8); o.det = malloc(n * 8);
   o.valid = malloc(n); o.best_window = malloc(n);
   farms_oracle *orc = farms_oracle_create(W, H, fs, inl);
+  if (getenv("FARMS_ORACLE_FAST") && atoi(getenv("FARMS_ORACLE_FAST")) && farms_oracle_set_fast(orc, 1)) return 1;
   struct timespec a, b;
   clock_gettime(CLOCK_MONOTONIC, &a);
   int rc = farms_oracle_process(orc, x, y, t, p, n, &o);

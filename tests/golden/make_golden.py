@@ -11,12 +11,13 @@ import os
 import subprocess
 import sys
 import tempfile
+import time
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")]
 import numpy as np  # noqa: E402
-from kat_streams import HASH_CASES, SYNTH_CASES, TEXT_CASES, write_txt  # noqa: E402
+from kat_streams import HASH_CASES, LONG_SYNTH_CASES, SYNTH_CASES, TEXT_CASES, write_txt  # noqa: E402
 
 REF = os.path.join(ROOT, "oracle", "_ref", "FARMS_Flow")
 
@@ -51,10 +52,12 @@ def main():
             meta[name] = summary(raw)
         for name, (w, h, fs, inl, build) in HASH_CASES.items():
             meta[name] = summary(run_ref(w, h, fs, inl, *build(), d, name))
-        for name, (cfg, n, start) in SYNTH_CASES.items():
+        for name, (cfg, n, start) in list(SYNTH_CASES.items()) + list(LONG_SYNTH_CASES.items()):
             s = Synth(cfg)
             x, y, t, p = s.first(n, start)
+            t_start = time.time()
             m = summary(run_ref(s.width, s.height, s.filtersize, 5, x, y, t, p, d, name))
+            m["reference_wall_s"] = round(time.time() - t_start, 1)
             m["input_sha256"] = hashlib.sha256(np.stack([x.astype(np.int64), y.astype(np.int64), t.astype(np.int64),
                                                           p.astype(np.int64)], 1).tobytes()).hexdigest()
             meta[name] = m

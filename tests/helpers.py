@@ -32,15 +32,24 @@ def oracle_lib():
         L.farms_oracle_destroy.argtypes = [C.c_void_p]
         L.farms_oracle_process.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64, C.POINTER(_OracleOut)]
         L.farms_oracle_state.argtypes = [C.c_void_p] * 5
+        L.farms_oracle_set_fast.argtypes = [C.c_void_p, C.c_int]
+        L.farms_oracle_is_fast.argtypes = [C.c_void_p]
         _olib = L
     return _olib
 
 
 class Oracle:
-    def __init__(self, width, height, filtersize, inlier_check):
+    def __init__(self, width, height, filtersize, inlier_check, fast=False):
+        """fast=True: the oracle's filtered pooling walk (oracle/farms_oracle.h: bit-identical outputs, ~10-20x
+        faster on dense streams; the plain scan stays the witness it is checked against)."""
         self._h = oracle_lib().farms_oracle_create(width, height, filtersize, inlier_check)
         assert self._h
         self.npx = width * height
+        if fast:
+            assert oracle_lib().farms_oracle_set_fast(self._h, 1) == 0
+
+    def is_fast(self):
+        return bool(oracle_lib().farms_oracle_is_fast(self._h))
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -69,8 +78,8 @@ class Oracle:
         return lt, hit
 
 
-def run_oracle(width, height, filtersize, inlier_check, x, y, t, p=None):
-    return Oracle(width, height, filtersize, inlier_check).process(x, y, t, p)
+def run_oracle(width, height, filtersize, inlier_check, x, y, t, p=None, fast=False):
+    return Oracle(width, height, filtersize, inlier_check, fast=fast).process(x, y, t, p)
 
 
 # ---------------------------------------------------------------------------------------------------

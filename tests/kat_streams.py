@@ -75,3 +75,11 @@ SYNTH_CASES = {
     "synth_cfg3_346x260_fs7": (3, 40000, 0),
     "synth_cfg4_1280x720": (4, 150000, 0),
 }
+
+# long prefixes of the benchmark scenes (steady state: at 1280x720 the valid fraction only settles at ~54 % after
+# ~1 M events); the reference needs minutes for each, the fast mode of the tier-2 oracle seconds.
+LONG_SYNTH_CASES = {
+    "synth_cfg2_304x240_1M": (2, 1_000_000, 0),
+    "synth_cfg3_346x260_fs7_2M": (3, 2_000_000, 0),
+    "synth_cfg4_1280x720_2M": (4, 2_000_000, 0),
+}

@@ -41,7 +41,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, name), f"{name} is declared in include/farms_b200.h but not exported"
     import farms_b200
     assert sorted(farms_b200.EXPORTS) == declared
-    assert L.farms_abi_version() == 1
+    assert L.farms_abi_version() == 2
 
 
 def test_filtersize_normalisation_matches_reference():

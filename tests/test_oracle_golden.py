@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from helpers import ROOT, run_oracle
-from kat_streams import HASH_CASES, SYNTH_CASES, TEXT_CASES, write_txt
+from kat_streams import HASH_CASES, LONG_SYNTH_CASES, SYNTH_CASES, TEXT_CASES, sweeps, write_txt
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 META = json.load(open(os.path.join(GOLDEN, "golden.json")))
@@ -22,10 +22,11 @@ def _cli():
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "farms_oracle_cli"])
 
 
-def oracle_text(tmp_path, name, w, h, fs, inl, x, y, t, p):
+def oracle_text(tmp_path, name, w, h, fs, inl, x, y, t, p, fast=False):
     base = str(tmp_path / name)
     write_txt(base + ".txt", x, y, t, p)
-    subprocess.run([CLI, str(w), str(h), str(fs), str(inl), base], check=True, capture_output=True)
+    subprocess.run([CLI, str(w), str(h), str(fs), str(inl), base], check=True, capture_output=True,
+                   env=dict(os.environ, FARMS_ORACLE_FAST="1" if fast else "0"))
     return open(base + "_FARMSOut_oracle.txt", "rb").read()
 
 
@@ -103,3 +104,60 @@ def test_oracle_streaming_equals_one_shot():
         parts.append(o2.process(x[a:b], y[a:b], t[a:b], p[a:b]))
     for k in ("valid", "inliers", "scale", "global_r", "vx"):
         assert np.array_equal(np.concatenate([q[k] for q in parts]), full[k], equal_nan=(k in ("global_r", "vx")))
+
+
+@pytest.mark.parametrize("name", sorted(LONG_SYNTH_CASES))
+def test_long_prefix_golden_with_the_fast_oracle(name, tmp_path):
+    """Steady-state prefixes of the benchmark scenes (1-2 M events): the reference's own output (SHA-256 of its
+    11-column text, recorded by make_golden.py) against the tier-2 oracle in its fast pooling mode."""
+    from farms_synth import Synth
+    cfg, n, start = LONG_SYNTH_CASES[name]
+    s = Synth(cfg)
+    x, y, t, p = s.first(n, start)
+    inp = np.stack([x.astype(np.int64), y.astype(np.int64), t.astype(np.int64), p.astype(np.int64)], 1)
+    assert hashlib.sha256(inp.tobytes()).hexdigest() == META[name]["input_sha256"], "generator changed"
+    raw = oracle_text(tmp_path, name, s.width, s.height, s.filtersize, 5, x, y, t, p, fast=True)
+    assert hashlib.sha256(raw).hexdigest() == META[name]["sha256"]
+    # the point of these cases: most of the stream is in the steady state (valid fraction of the scene)
+    assert META[name]["valid"] > 0.3 * n
+
+
+@pytest.mark.parametrize("cfg,n,start", [(1, 60000, 0), (2, 80000, 30000), (3, 80000, 0), (4, 250000, 4000)])
+def test_fast_oracle_mode_is_bit_identical_to_the_plain_scan(cfg, n, start):
+    from farms_synth import Synth
+    from helpers import Oracle
+    s = Synth(cfg)
+    x, y, t, p = s.first(n, start)
+    slow = run_oracle(s.width, s.height, s.filtersize, 5, x, y, t, p)
+    o = Oracle(s.width, s.height, s.filtersize, 5, fast=True)
+    fast = o.process(x, y, t, p)
+    assert o.is_fast()
+    for k in slow:
+        assert np.array_equal(slow[k].view(np.uint8), fast[k].view(np.uint8)), k
+
+
+def test_fast_oracle_mode_falls_back_on_decreasing_timestamps():
+    from farms_synth import Synth
+    from helpers import Oracle
+    s = Synth(1)
+    x, y, t, p = s.first(30000, 0)
+    rng = np.random.default_rng(11)
+    t2 = t.astype(np.int64)
+    t2[10000:] += rng.integers(-200, 200, len(t) - 10000)
+    t2 = t2.astype(np.uint64)
+    slow = run_oracle(s.width, s.height, 5, 5, x, y, t2, p)
+    o = Oracle(s.width, s.height, 5, 5, fast=True)
+    fast = o.process(x, y, t2, p)
+    assert not o.is_fast()
+    for k in slow:
+        assert np.array_equal(slow[k].view(np.uint8), fast[k].view(np.uint8)), k
+
+
+def test_fast_oracle_mode_on_aliasing_shapes():
+    """width > height (flat-index aliasing of vFlow.cpp:1000) and width < height (row bound below the sensor)."""
+    for (w, h) in [(64, 20), (150, 40), (20, 64), (48, 200)]:
+        x, y, t, p = sweeps(w, h, slopes=((7, 3), (-5, 6)), gap=100)
+        slow = run_oracle(w, h, 5, 5, x, y, t, p)
+        fast = run_oracle(w, h, 5, 5, x, y, t, p, fast=True)
+        for k in slow:
+            assert np.array_equal(slow[k].view(np.uint8), fast[k].view(np.uint8)), (w, h, k)
