@@ -1,0 +1,480 @@
+// comm.cu -- time-sliced multi-GPU runs of the FARMS path behind the C ABI (include/farms_b200.h, farms_comm_*).
+//
+// The reference is single-threaded; what is distributed here is its event loop
+// (src/vFlow.cpp:223-414) cut into time slices, one per GPU.  Rank g owns the events of its slice, also processes
+// the 499-us causal halo in front of it (pooling admits |dt| < 500 us, src/vFlow.cpp:1002) and rebuilds the surface
+// of active events at its halo start from the "last event per pixel" surfaces of the earlier slices (the surface
+// never forgets, src/vFlow.cpp:267): one all-gather of W*H x 5 bytes per rank, folded in rank order.  The per-event
+// outputs of the README's 8-column contract (globalR, globalTheta, localR, localTheta as one float4) travel to the
+// root rank batch by batch while the next batch computes.
+//
+// Two transports behind one interface:
+//   NCCL   one process (or host thread) per GPU; ncclAllGather for the surfaces, ncclSend/ncclRecv per batch for
+//          the outputs.  libnccl.so.2 is loaded on first use (dlopen), so the single-GPU library has no NCCL
+//          dependency.
+//   LOCAL  all ranks are host threads of one process (the FARMS_Flow command line): the ranks publish their device
+//          buffers in a shared table and copy between devices directly (cudaMemcpyAsync over NVLink peer access),
+//          outputs are written straight into the root's buffer.  Also what lets a one-GPU box test the whole
+//          protocol (several ranks on one device, which NCCL refuses).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "farms_ctx.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily
+// ---------------------------------------------------------------------------------------------------------------
+struct NcclApi {
+  void *handle = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  std::string error;
+};
+
+#ifndef FARMS_NCCL_FALLBACK
+#define FARMS_NCCL_FALLBACK ""
+#endif
+
+NcclApi *nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char *names[] = {"libnccl.so.2", "libnccl.so", FARMS_NCCL_FALLBACK};
+    for (const char *nm : names) {
+      if (!nm[0]) continue;
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) {
+      api.error = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
+      return;
+    }
+#define SYM(field, name)                                                  \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, name)); \
+  if (!api.field) api.error = std::string("libnccl lacks ") + name;
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(AllGather, "ncclAllGather") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  });
+  return &api;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LOCAL transport: a group of host threads
+// ---------------------------------------------------------------------------------------------------------------
+struct LocalGroup {
+  int nranks = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  uint64_t generation = 0;
+  int refs = 0;
+  // published per rank
+  std::vector<const uint32_t *> surf_t;
+  std::vector<const uint8_t *> surf_hit;
+  std::vector<uint64_t> meta;  // 4 words per rank
+  float *root_dst = nullptr;
+  int failed = 0;
+
+  void barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    const uint64_t gen = generation;
+    if (++arrived == nranks) {
+      arrived = 0;
+      generation++;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return generation != gen; });
+    }
+  }
+};
+
+std::mutex g_groups_mu;
+std::vector<std::pair<uint64_t, LocalGroup *>> g_groups;  // keyed by the first 8 bytes of the group id
+
+}  // namespace
+
+struct farms_comm {
+  farms_ctx *ctx = nullptr;
+  int nranks = 1, rank = 0;
+  bool local = false;
+  ncclComm_t nccl = nullptr;
+  LocalGroup *group = nullptr;
+  cudaStream_t cstream = nullptr;  // transfers of outputs, beside the compute stream
+  // surface exchange
+  uint32_t *surf_t = nullptr, *all_t = nullptr;
+  uint8_t *surf_hit = nullptr, *all_hit = nullptr;
+  uint64_t *d_meta = nullptr, *h_meta = nullptr;  // 4 words per rank: events, halo events, max_batch, unused
+  // device-resident copy of a host slice (the slice is read twice: surface pass, then the event loop)
+  DevBuf dev_x, dev_y, dev_t;
+  // outputs on their way to the root
+  float *sendbuf[2] = {nullptr, nullptr};
+  size_t sendcap = 0;
+  cudaEvent_t ev_packed[2]{}, ev_sent[2]{};
+  bool sent_pending[2] = {false, false};
+  // state of the call in flight (read by the batch hook)
+  const farms_gather *gather = nullptr;
+  std::vector<uint64_t> n_all, n_halo, first_out;  // per rank
+  uint64_t maxb = 0;
+  uint64_t batches_seen = 0;     // batches with outputs this rank has packed
+  uint64_t recv_posted = 0;      // root: batch indices [0, recv_posted) have their receives posted
+  float last_gather_ms = 0.f;
+};
+
+namespace {
+
+#define CUC(call)                                                                                              \
+  do {                                                                                                         \
+    cudaError_t e_ = (call);                                                                                   \
+    if (e_ != cudaSuccess)                                                                                     \
+      return farms_fail(cm->ctx, e_ == cudaErrorMemoryAllocation ? FARMS_ERR_NOMEM : FARMS_ERR_CUDA,           \
+                        "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);                  \
+  } while (0)
+#define NC(call)                                                                                               \
+  do {                                                                                                         \
+    ncclResult_t r_ = (call);                                                                                  \
+    if (r_ != ncclSuccess)                                                                                     \
+      return farms_fail(cm->ctx, FARMS_ERR_COMM, "%s: %s (%s:%d)", #call, nccl_api()->GetErrorString(r_),      \
+                        __FILE__, __LINE__);                                                                   \
+  } while (0)
+
+int ensure_buf(farms_comm *cm, DevBuf &b, size_t bytes) {
+  if (b.bytes >= bytes) return 0;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+  const size_t want = bytes + bytes / 16 + 4096;
+  CUC(cudaMalloc(&b.p, want));
+  b.bytes = want;
+  return 0;
+}
+
+// owned events of rank r that internal batch k of its slice produces: count and position among its outputs
+void batch_outputs(const farms_comm *cm, int r, uint64_t k, uint64_t *count, uint64_t *out_off) {
+  const uint64_t lo = k * cm->maxb, hi = std::min(cm->n_all[r], (k + 1) * cm->maxb);
+  const uint64_t a = std::max(lo, cm->n_halo[r]);
+  *count = hi > a ? hi - a : 0;
+  *out_off = a - cm->n_halo[r];
+}
+uint64_t batches_of(const farms_comm *cm, int r) { return (cm->n_all[r] + cm->maxb - 1) / cm->maxb; }
+
+// root: post the receives of batch index k from every peer (one NCCL group: they run concurrently)
+int post_receives(farms_comm *cm, uint64_t k) {
+  NcclApi *N = nccl_api();
+  bool any = false;
+  for (int r = 0; r < cm->nranks; r++) {
+    if (r == cm->rank) continue;
+    uint64_t cnt, off;
+    batch_outputs(cm, r, k, &cnt, &off);
+    if (!cnt || k >= batches_of(cm, r)) continue;
+    if (!any) NC(N->GroupStart());
+    any = true;
+    NC(N->Recv(cm->gather->dst + 4 * (cm->first_out[r] + off), 4 * cnt, ncclFloat, r, cm->nccl, cm->cstream));
+  }
+  if (any) NC(N->GroupEnd());
+  return 0;
+}
+
+// Batch hook: the four contract columns of the batch as float4 per event, on their way to the root while the next
+// batch computes.
+int gather_hook(void *user, farms_ctx *c, const FarmsBatchView *v) {
+  farms_comm *cm = (farms_comm *)user;
+  const farms_gather *g = cm->gather;
+  const uint64_t my_first = cm->first_out[cm->rank];
+  if (cm->rank == g->root) {
+    // own outputs: packed straight into the destination
+    launch_pack4(v->gr, v->gth, v->lr, v->lth, v->n_out, (float4 *)(g->dst + 4 * (my_first + v->out_off)), v->stream);
+    CUC(cudaGetLastError());
+    if (!cm->local && cm->nranks > 1) {
+      // the peers run in step with this rank: by now they have (nearly) finished the previous batch, so its
+      // receive kernels do not sit on SMs waiting for data
+      const uint64_t upto = cm->batches_seen;  // batches before this one
+      for (; cm->recv_posted < upto; cm->recv_posted++) {
+        int rc = post_receives(cm, cm->recv_posted);
+        if (rc) return rc;
+      }
+    }
+    cm->batches_seen++;
+    return 0;
+  }
+  const int b = (int)(cm->batches_seen & 1);
+  if (v->n_out > cm->sendcap) return farms_fail(c, FARMS_ERR_STATE, "gather: batch larger than the send buffer");
+  if (cm->sent_pending[b]) CUC(cudaStreamWaitEvent(v->stream, cm->ev_sent[b], 0));  // buffer free again
+  launch_pack4(v->gr, v->gth, v->lr, v->lth, v->n_out, (float4 *)cm->sendbuf[b], v->stream);
+  CUC(cudaGetLastError());
+  CUC(cudaEventRecord(cm->ev_packed[b], v->stream));
+  CUC(cudaStreamWaitEvent(cm->cstream, cm->ev_packed[b], 0));
+  if (cm->local) {
+    // one process: the root's buffer is directly addressable (peer access / same device)
+    CUC(cudaMemcpyAsync(cm->group->root_dst + 4 * (my_first + v->out_off), cm->sendbuf[b], v->n_out * 16,
+                        cudaMemcpyDefault, cm->cstream));
+  } else {
+    NC(nccl_api()->Send(cm->sendbuf[b], 4 * v->n_out, ncclFloat, g->root, cm->nccl, cm->cstream));
+  }
+  CUC(cudaEventRecord(cm->ev_sent[b], cm->cstream));
+  cm->sent_pending[b] = true;
+  cm->batches_seen++;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int farms_comm_unique_id(void *id128) {
+  if (!id128) return FARMS_ERR_ARG;
+  NcclApi *N = nccl_api();
+  if (!N->error.empty()) return FARMS_ERR_COMM;
+  ncclUniqueId id;
+  if (N->GetUniqueId(&id) != ncclSuccess) return FARMS_ERR_COMM;
+  static_assert(sizeof(id) == FARMS_COMM_ID_BYTES, "NCCL unique id size");
+  memcpy(id128, &id, sizeof id);
+  return FARMS_OK;
+}
+
+int farms_comm_create(farms_comm **out, farms_ctx *ctx, int nranks, int rank, const void *id128, uint32_t flags) {
+  if (!out || !ctx || nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !id128)) return FARMS_ERR_ARG;
+  *out = nullptr;
+  farms_comm *cm = new (std::nothrow) farms_comm();
+  if (!cm) return FARMS_ERR_NOMEM;
+  cm->ctx = ctx;
+  cm->nranks = nranks;
+  cm->rank = rank;
+  cm->local = (flags & FARMS_COMM_LOCAL) != 0;
+  auto bail = [&](int code) {
+    farms_comm_destroy(cm);
+    return code;
+  };
+  if (cudaSetDevice(ctx->cfg.device) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&cm->cstream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+  for (int b = 0; b < 2; b++)
+    if (cudaEventCreateWithFlags(&cm->ev_packed[b], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&cm->ev_sent[b], cudaEventDisableTiming) != cudaSuccess)
+      return bail(FARMS_ERR_CUDA);
+  const size_t npx = ctx->npx;
+  bool ok = cudaMalloc((void **)&cm->surf_t, npx * 4) == cudaSuccess && cudaMalloc((void **)&cm->surf_hit, npx) == cudaSuccess &&
+            cudaMalloc((void **)&cm->all_t, (size_t)nranks * npx * 4) == cudaSuccess &&
+            cudaMalloc((void **)&cm->all_hit, (size_t)nranks * npx) == cudaSuccess &&
+            cudaMalloc((void **)&cm->d_meta, (size_t)nranks * 4 * sizeof(uint64_t)) == cudaSuccess &&
+            cudaMallocHost((void **)&cm->h_meta, (size_t)nranks * 4 * sizeof(uint64_t)) == cudaSuccess;
+  if (!ok) return bail(FARMS_ERR_NOMEM);
+  cm->n_all.assign(nranks, 0);
+  cm->n_halo.assign(nranks, 0);
+  cm->first_out.assign(nranks, 0);
+  if (nranks > 1 && cm->local) {
+    uint64_t key;
+    memcpy(&key, id128, sizeof key);
+    std::lock_guard<std::mutex> lk(g_groups_mu);
+    for (auto &kv : g_groups)
+      if (kv.first == key) cm->group = kv.second;
+    if (!cm->group) {
+      cm->group = new LocalGroup();
+      cm->group->nranks = nranks;
+      cm->group->surf_t.assign(nranks, nullptr);
+      cm->group->surf_hit.assign(nranks, nullptr);
+      cm->group->meta.assign((size_t)nranks * 4, 0);
+      g_groups.emplace_back(key, cm->group);
+    }
+    if (cm->group->nranks != nranks) return bail(FARMS_ERR_ARG);
+    cm->group->refs++;
+  } else if (nranks > 1) {
+    NcclApi *N = nccl_api();
+    if (!N->error.empty()) {
+      farms_fail(ctx, FARMS_ERR_COMM, "%s", N->error.c_str());
+      return bail(FARMS_ERR_COMM);
+    }
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    ncclResult_t r = N->CommInitRank(&cm->nccl, nranks, id, rank);
+    if (r != ncclSuccess) {
+      farms_fail(ctx, FARMS_ERR_COMM, "ncclCommInitRank: %s", N->GetErrorString(r));
+      return bail(FARMS_ERR_COMM);
+    }
+  }
+  *out = cm;
+  return FARMS_OK;
+}
+
+void farms_comm_destroy(farms_comm *cm) {
+  if (!cm) return;
+  if (cm->ctx) cudaSetDevice(cm->ctx->cfg.device);
+  if (cm->cstream) cudaStreamSynchronize(cm->cstream);
+  if (cm->nccl) nccl_api()->CommDestroy(cm->nccl);
+  if (cm->group) {
+    std::lock_guard<std::mutex> lk(g_groups_mu);
+    if (--cm->group->refs == 0) {
+      for (size_t i = 0; i < g_groups.size(); i++)
+        if (g_groups[i].second == cm->group) {
+          g_groups.erase(g_groups.begin() + (long)i);
+          break;
+        }
+      delete cm->group;
+    }
+  }
+  void *ps[] = {cm->surf_t, cm->surf_hit, cm->all_t, cm->all_hit, cm->d_meta, cm->dev_x.p, cm->dev_y.p, cm->dev_t.p,
+                cm->sendbuf[0], cm->sendbuf[1]};
+  for (void *p : ps)
+    if (p) cudaFree(p);
+  if (cm->h_meta) cudaFreeHost(cm->h_meta);
+  for (int b = 0; b < 2; b++) {
+    if (cm->ev_packed[b]) cudaEventDestroy(cm->ev_packed[b]);
+    if (cm->ev_sent[b]) cudaEventDestroy(cm->ev_sent[b]);
+  }
+  if (cm->cstream) cudaStreamDestroy(cm->cstream);
+  delete cm;
+}
+
+int farms_comm_process(farms_comm *cm, const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t n,
+                       uint64_t n_halo, uint64_t n_surface, uint64_t t0, uint32_t flags, const farms_out *out,
+                       const farms_gather *gather) {
+  if (!cm || !cm->ctx) return FARMS_ERR_ARG;
+  farms_ctx *c = cm->ctx;
+  c->err.clear();
+  if (n_halo > n || n_surface > n || (n && (!x || !y || !t))) return farms_fail(c, FARMS_ERR_ARG, "bad slice arguments");
+  if (n >= (1ull << 32) - 1) return farms_fail(c, FARMS_ERR_ARG, "slice too long");
+  if (gather && (gather->root < 0 || gather->root >= cm->nranks || (cm->rank == gather->root && !gather->dst)))
+    return farms_fail(c, FARMS_ERR_ARG, "bad gather descriptor");
+  const bool in_device = (flags & FARMS_IO_INPUT_ON_DEVICE) != 0, out_device = (flags & FARMS_IO_OUTPUT_ON_DEVICE) != 0;
+  CUC(cudaSetDevice(c->cfg.device));
+  cudaStream_t s = c->stream;
+  const int R = cm->nranks;
+  int rc = farms_set_t0(c, t0);
+  if (rc) return rc;
+  cm->maxb = c->cfg.max_batch ? c->cfg.max_batch : DEFAULT_MAX_BATCH;
+
+  // ---- a host slice is made device-resident once: it is read twice (surface pass, event loop) ----
+  const uint16_t *dx = x, *dy = y;
+  const uint64_t *dt = t;
+  if (!in_device && R > 1 && n) {
+    if ((rc = ensure_buf(cm, cm->dev_x, n * 2)) || (rc = ensure_buf(cm, cm->dev_y, n * 2)) || (rc = ensure_buf(cm, cm->dev_t, n * 8)))
+      return rc;
+    const size_t piece = 8u << 20;
+    for (uint64_t off = 0; off < n; off += piece) {  // pieces keep the copy engine and the surface kernel in step
+      const size_t nb = (size_t)std::min<uint64_t>(piece, n - off);
+      CUC(cudaMemcpyAsync((uint16_t *)cm->dev_x.p + off, x + off, nb * 2, cudaMemcpyHostToDevice, s));
+      CUC(cudaMemcpyAsync((uint16_t *)cm->dev_y.p + off, y + off, nb * 2, cudaMemcpyHostToDevice, s));
+      CUC(cudaMemcpyAsync((uint64_t *)cm->dev_t.p + off, t + off, nb * 8, cudaMemcpyHostToDevice, s));
+    }
+    dx = (const uint16_t *)cm->dev_x.p;
+    dy = (const uint16_t *)cm->dev_y.p;
+    dt = (const uint64_t *)cm->dev_t.p;
+  }
+
+  // ---- exchange: slice sizes, and the surface of active events at every slice start ----
+  cm->h_meta[4 * cm->rank + 0] = n;
+  cm->h_meta[4 * cm->rank + 1] = n_halo;
+  cm->h_meta[4 * cm->rank + 2] = cm->maxb;
+  cm->h_meta[4 * cm->rank + 3] = 0;
+  if (R > 1) {
+    // farms_slice_surface synchronises the compute stream: the uploads above are done when it returns
+    if ((rc = farms_slice_surface(c, dx, dy, dt, n_surface, t0, cm->surf_t, cm->surf_hit))) return rc;
+    const size_t npx = c->npx;
+    if (cm->local) {
+      LocalGroup *G = cm->group;
+      {
+        std::lock_guard<std::mutex> lk(G->mu);
+        G->surf_t[cm->rank] = cm->surf_t;
+        G->surf_hit[cm->rank] = cm->surf_hit;
+        memcpy(&G->meta[4 * cm->rank], &cm->h_meta[4 * cm->rank], 4 * sizeof(uint64_t));
+        if (gather && cm->rank == gather->root) G->root_dst = gather->dst;
+      }
+      G->barrier();
+      for (int r = 0; r < R; r++) {
+        memcpy(&cm->h_meta[4 * r], &G->meta[4 * r], 4 * sizeof(uint64_t));
+        if (r >= cm->rank) continue;  // only earlier slices are folded
+        CUC(cudaMemcpyAsync(cm->all_t + (size_t)r * npx, G->surf_t[r], npx * 4, cudaMemcpyDefault, s));
+        CUC(cudaMemcpyAsync(cm->all_hit + (size_t)r * npx, G->surf_hit[r], npx, cudaMemcpyDefault, s));
+      }
+      CUC(cudaStreamSynchronize(s));
+      G->barrier();  // every rank has read the published surfaces
+    } else {
+      NcclApi *N = nccl_api();
+      CUC(cudaMemcpyAsync(cm->d_meta + 4 * cm->rank, cm->h_meta + 4 * cm->rank, 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+      NC(N->GroupStart());
+      NC(N->AllGather(cm->surf_t, cm->all_t, npx, ncclUint32, cm->nccl, s));
+      NC(N->AllGather(cm->surf_hit, cm->all_hit, npx, ncclUint8, cm->nccl, s));
+      NC(N->AllGather(cm->d_meta + 4 * cm->rank, cm->d_meta, 4, ncclUint64, cm->nccl, s));
+      NC(N->GroupEnd());
+      CUC(cudaMemcpyAsync(cm->h_meta, cm->d_meta, (size_t)R * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+      CUC(cudaStreamSynchronize(s));
+    }
+    for (int r = 0; r < cm->rank; r++)  // later slices win: fold in stream order
+      launch_sae_fold(c->sae, npx, cm->all_t + (size_t)r * npx, cm->all_hit + (size_t)r * npx, s);
+    CUC(cudaGetLastError());
+  }
+  uint64_t first = 0;
+  for (int r = 0; r < R; r++) {
+    cm->n_all[r] = cm->h_meta[4 * r + 0];
+    cm->n_halo[r] = cm->h_meta[4 * r + 1];
+    if (cm->h_meta[4 * r + 2] != cm->maxb) return farms_fail(c, FARMS_ERR_ARG, "ranks disagree on max_batch");
+    cm->first_out[r] = first;
+    first += cm->n_all[r] - cm->n_halo[r];
+    if (gather && gather->counts) gather->counts[r] = cm->n_all[r] - cm->n_halo[r];
+  }
+
+  // ---- the event loop of this slice, outputs leaving batch by batch ----
+  FarmsBatchHook hook;
+  cm->gather = gather;
+  cm->batches_seen = 0;
+  cm->recv_posted = 0;
+  cm->sent_pending[0] = cm->sent_pending[1] = false;
+  if (gather) {
+    hook.fn = gather_hook;
+    hook.user = cm;
+    if (cm->rank != gather->root) {
+      const size_t want = (size_t)std::min<uint64_t>(cm->maxb, std::max<uint64_t>(n, 1));
+      if (want > cm->sendcap) {
+        CUC(cudaDeviceSynchronize());
+        for (int b = 0; b < 2; b++) {
+          if (cm->sendbuf[b]) cudaFree(cm->sendbuf[b]);
+          cm->sendbuf[b] = nullptr;
+        }
+        cm->sendcap = 0;
+        for (int b = 0; b < 2; b++) CUC(cudaMalloc((void **)&cm->sendbuf[b], want * 16));
+        cm->sendcap = want;
+      }
+    }
+  }
+  const bool stays_on_device = in_device || (R > 1 && n);
+  rc = farms_process_impl(c, dx, dy, dt, n, out, stays_on_device, out_device, n_halo, gather ? &hook : nullptr);
+  if (rc) return rc;
+  if (gather) {
+    if (!cm->local && R > 1 && cm->rank == gather->root) {
+      uint64_t most = 0;
+      for (int r = 0; r < R; r++) most = std::max(most, batches_of(cm, r));
+      for (; cm->recv_posted < most; cm->recv_posted++)
+        if ((rc = post_receives(cm, cm->recv_posted))) return rc;
+    }
+    CUC(cudaStreamSynchronize(cm->cstream));
+    if (cm->local && R > 1) cm->group->barrier();  // the root's buffer is complete when every rank has passed here
+  }
+  cm->gather = nullptr;
+  return FARMS_OK;
+}
+
+int farms_comm_info(const farms_comm *cm, int32_t *nranks, int32_t *rank, int32_t *transport) {
+  if (!cm) return FARMS_ERR_ARG;
+  if (nranks) *nranks = cm->nranks;
+  if (rank) *rank = cm->rank;
+  if (transport) *transport = cm->nranks == 1 ? 0 : cm->local ? 2 : 1;
+  return FARMS_OK;
+}
+
+}  // extern "C"

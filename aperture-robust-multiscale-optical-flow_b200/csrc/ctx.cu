@@ -16,98 +16,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/farms_b200.h"
-#include "farms_dev.cuh"
-
-namespace {
-
-constexpr uint64_t DEFAULT_MAX_BATCH = 16ull << 20;
-constexpr uint32_t DEFAULT_SLACK_US = 1000;
-constexpr size_t HALO_CAP = 8ull << 20;       // events carried across a batch boundary at most
-#ifndef FARMS_FIT_CHUNK_LOG2
-#define FARMS_FIT_CHUNK_LOG2 16
-#endif
-constexpr int FIT_CHUNK_MAX = 1 << FARMS_FIT_CHUNK_LOG2;  // events per SAE snapshot at most
-constexpr int FIT_CHUNK_MIN = 1 << 13;
-constexpr int FIT_WAYS = 4;  // plane-fit chunks in flight
-constexpr size_t CSR_BUDGET = 96ull << 20;    // max (slab, tile) cells of the pooling index per batch
-
-enum { EV_START, EV_H2D, EV_INGEST, EV_INDEX, EV_FIT, EV_BIN, EV_POOL, EV_END, EV_COUNT };
-
-struct DevBuf {
-  void *p = nullptr;
-  size_t bytes = 0;
-};
-
-}  // namespace
-
-// The per-event working arrays of one internal batch.  The host path keeps two sets so that the result
-// copies of batch k (device->host) overlap the kernels of batch k+1.
-struct WorkSet {
-  size_t cap = 0;  // capacity in events
-  uint16_t *ex = nullptr, *ey = nullptr;
-  uint32_t *et = nullptr, *em = nullptr, *keyA = nullptr, *valA = nullptr, *keyB = nullptr, *valB = nullptr,
-           *pixkeep = nullptr, *flags = nullptr, *slab_ids = nullptr, *slab_first = nullptr, *fin = nullptr;
-  int2 *prevp = nullptr;
-  int32_t *nextp = nullptr;
-  double *vx = nullptr, *vy = nullptr, *len = nullptr, *theta = nullptr, *lcx = nullptr, *lcy = nullptr,
-         *det = nullptr, *gr = nullptr, *gth = nullptr, *pay = nullptr;
-  uint8_t *valid = nullptr, *scale = nullptr, *done = nullptr;
-  int8_t *bw = nullptr;
-  uint16_t *inl = nullptr;
-  uint4 *rec = nullptr;
-  std::vector<void *> owned;
-};
-
-struct farms_ctx {
-  farms_config cfg{};
-  int W = 0, H = 0, fs = 0, r = 0, P = 0, min_inl = 0;
-  size_t npx = 0;
-  int num_sms = 148;
-  // Events per SAE snapshot.  A fit thread walks back one history link for every footprint cell that was hit
-  // again later in its chunk, so the chunk is kept to about a sixth of an event per pixel, at most 2^16 events:
-  // 2^16 at 1280x720 (measured with the two-stream overlap: 2^15 11.3 ms, 2^16 10.1, 2^17 10.7 per 20 M events),
-  // 2^14 at 346x260 (2^13 38.9 ms, 2^14 31.7, 2^15 33.4; without the overlap 2^17 took 66 ms).  Small chunks are
-  // launch-bound, large ones walk many dependent history links per event.
-  int fit_chunk = FIT_CHUNK_MAX;
-  int pool_impl = 1;  // 1 = staged-list fast path (k_pool_tile), 2 = bit-table variant (FARMS_POOL_IMPL=bits, A/B runs)
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[EV_COUNT]{};
-  std::string err;
-  bool have_t0 = false;
-  uint64_t t0 = 0;
-  uint64_t total_events = 0;
-  uint32_t last_M = 0;
-  unsigned long long valid_seen = 0;  // flow events counted so far in the current process call
-  size_t halo = 0;  // events in the halo store
-  size_t cap_in = 0;
-  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
-  cudaEvent_t ev_h2d[2]{}, ev_ingest[2]{}, ev_pool[2]{}, ev_d2h[2]{}, ev_c0 = nullptr, ev_c1 = nullptr;
-  bool d2h_pending[2] = {false, false};
-  farms_timings tm{};
-
-  // surface of active events, plus the extra copies and streams of the overlapped plane fit (chunk k works on
-  // surface k mod FIT_WAYS in stream k mod FIT_WAYS; way 0 is `sae` on the main stream)
-  uint2 *sae = nullptr, *sae_x[FIT_WAYS - 1] = {};
-  cudaStream_t fit_streams[FIT_WAYS - 1] = {};
-  cudaEvent_t ev_fit[FIT_WAYS - 1] = {};
-  WorkSet ws[2];
-  // halo store
-  uint16_t *hx = nullptr, *hy = nullptr;
-  uint32_t *ht = nullptr, *hm = nullptr;
-  double *hlen = nullptr, *hlcx = nullptr, *hlcy = nullptr;
-  // staging for the host path
-  uint16_t *in_x[2] = {nullptr, nullptr}, *in_y[2] = {nullptr, nullptr};
-  uint64_t *in_t[2] = {nullptr, nullptr};
-  // misc
-  DevBuf sort_temp, scan_temp, cell_start, fit_scratch, surf_tmp, item_ovf;
-  int *d_err = nullptr;
-  unsigned long long *d_counters = nullptr;  // [0] valid events, [1] pool candidates, [2..4] events per pooling path
-  unsigned pool_kernels = 0;
-  unsigned int *d_work = nullptr;
-  uint32_t *d_small = nullptr;  // device scratch words
-  uint32_t *h_small = nullptr;  // pinned host scratch words
-};
+#include "farms_ctx.cuh"
 
 namespace {
 
@@ -120,6 +29,20 @@ int fail(farms_ctx *c, int code, const char *fmt, ...) {
   if (c) c->err = buf;
   return code;
 }
+
+}  // namespace
+
+int farms_fail(farms_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+namespace {
 
 #define CU(call)                                                                                          \
   do {                                                                                                    \
@@ -218,13 +141,30 @@ int copy_out(farms_ctx *c, T *dst, const T *src, size_t n, bool to_device, cudaS
   return 0;
 }
 
-// One internal batch: n new events already on the device at (dx, dy, dt).
+// the output columns that exist once the plane fit of a batch is done (everything but globalR / globalTheta / scale)
+int copy_fit_columns(farms_ctx *c, WorkSet &w, const farms_out *out, size_t hh, size_t n_out, size_t out_off,
+                     bool out_device, cudaStream_t st) {
+  int rc;
+#define COL(field, src) \
+  if ((rc = copy_out(c, out->field ? out->field + out_off : nullptr, (src) + hh, n_out, out_device, st))) return rc;
+  COL(t_rel, w.et) COL(vx, w.vx) COL(vy, w.vy) COL(local_r, w.len) COL(local_theta, w.theta) COL(valid, w.valid)
+  COL(best_window, w.bw) COL(inliers, w.inl)
+#undef COL
+  if (out->det && w.det)
+    if ((rc = copy_out(c, out->det + out_off, w.det + hh, n_out, out_device, st))) return rc;
+  return 0;
+}
+
+// One internal batch: n new events already on the device at (dx, dy, dt).  The first `skip` of them are history
+// only (a time slice's causal halo): they are fitted (their flow is state) but neither pooled nor returned.
 // Results go out on `out_stream` (the compute stream itself, or the device->host stream of the host path).
-int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, const uint64_t *dt, size_t n,
-              const farms_out *out, size_t out_off, bool out_device, cudaStream_t out_stream, float *stage_ms) {
+int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, const uint64_t *dt, size_t n, size_t skip,
+              const farms_out *out, size_t out_off, bool out_device, cudaStream_t out_stream, float *stage_ms,
+              const FarmsBatchHook *hook) {
   cudaStream_t s = c->stream;
   WorkSet &w = c->ws[set];
   const size_t h = c->halo, m = h + n;
+  const size_t hh = h + skip, n_out = n - skip;  // first batch-local index with outputs, and how many
   int rc;
   if (m > w.cap && (rc = alloc_working(c, w, m + m / 8 + 1024))) return rc;
   // this set's previous results must have left the device before it is overwritten
@@ -254,7 +194,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   inclusive_max_scan_u32(w.et + h, w.em + h, n, c->last_M, c->scan_temp.p, s, L);
   CU(cudaMemcpyAsync(w.pixkeep, w.keyA, m * 4, cudaMemcpyDeviceToDevice, s));
   *L += 2;
-  k_publish<<<1, 32, 0, s>>>(c->h_small, (const uint32_t *)c->d_err, 1);
+  k_publish<<<1, 32, 0, s>>>(c->h_small + 8, (const uint32_t *)c->d_err, 1);  // read at the mid-batch sync below
   CU(cudaEventRecord(c->ev[EV_INGEST], s));
   CU(cudaEventRecord(c->ev_ingest[set], s));  // the input staging buffers of this set are free again
 
@@ -266,9 +206,6 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev[EV_INDEX], s));
 
-  // range errors are known by now without having stalled the sort
-  CU(cudaStreamSynchronize(s));
-  if (((int *)c->h_small)[0]) return fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
 
   // ---- K3 plane fit, chunk by chunk against the chunk-end SAE snapshot ----
   // FIT_WAYS surfaces and streams: chunk k works on surface k mod FIT_WAYS in stream k mod FIT_WAYS, so
@@ -311,6 +248,13 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev[EV_FIT], s));
 
+  // ---- the columns the plane fit produced can leave now, under the pooling of this batch ----
+  if (out && n_out && out_stream != s) {
+    CU(cudaEventRecord(c->ev_fitdone[set], s));
+    CU(cudaStreamWaitEvent(out_stream, c->ev_fitdone[set], 0));
+    if ((rc = copy_fit_columns(c, w, out, hh, n_out, out_off, out_device, out_stream))) return rc;
+  }
+
   // ---- K4a pooling index: dense time slabs x tiles ----
   // Slab length from the density of flow events: the shortest of 128 us, 256 us, ... that puts at least 70 flow
   // events of a (32+100)^2 tile region into a slab (shorter slabs cut fewer useless candidates than their fixed
@@ -320,6 +264,8 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   k_publish<<<1, 32, 0, s>>>(c->h_small + 2, (const uint32_t *)c->d_counters, 2);
   *L += 3;
   CU(cudaStreamSynchronize(s));
+  // (k_ingest clamps an out-of-range event to pixel (0,0), so the kernels above were safe to run)
+  if (((int *)c->h_small)[8]) return fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
   // flow events of this batch's new part (the fit ran above); the halo is assumed to have the same density
   const unsigned long long valid_total = *(const unsigned long long *)(c->h_small + 2);
   const double flow_frac = n ? (double)(valid_total - c->valid_seen) / (double)n : 0.0;
@@ -365,12 +311,12 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaEventRecord(c->ev[EV_BIN], s));
 
   // ---- K4b pooling ----
-  CU(cudaMemsetAsync(w.gr, 0, n * 8, s));
-  CU(cudaMemsetAsync(w.gth, 0, n * 8, s));
-  CU(cudaMemsetAsync(w.scale, 0, n, s));
+  CU(cudaMemsetAsync(w.gr, 0, n_out * 8, s));
+  CU(cudaMemsetAsync(w.gth, 0, n_out * 8, s));
+  CU(cudaMemsetAsync(w.scale, 0, n_out, s));
   CU(cudaMemsetAsync(c->d_work, 0, 4 * sizeof(unsigned int), s));
   CU(cudaMemsetAsync(w.done, 0, m, s));
-  CU(cudaMemsetAsync(w.fin, 0, n * sizeof(uint32_t), s));
+  CU(cudaMemsetAsync(w.fin, 0, n_out * sizeof(uint32_t), s));
   {
     const size_t iw = pool_item_words(c->W, c->H, (int)nslabs);
     if ((rc = ensure(c, c->item_ovf, iw * sizeof(uint32_t)))) return rc;
@@ -378,34 +324,30 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   }
   const int fast = (monotone && !(c->cfg.flags & FARMS_FLAG_GENERIC_POOLING)) ? c->pool_impl : 0;
   *L += launch_pooling(w.rec, w.pay, (const uint32_t *)c->cell_start.p, w.slab_ids, w.slab_first, w.fin, (uint32_t *)c->item_ovf.p, w.done, m, (uint32_t)ncells,
-                       (int)h, w.len, w.lcx, w.lcy, (int)nslabs, g, fast, flow_frac * (double)m / (double)nslabs, w.gr, w.gth, w.scale,
+                       (int)hh, w.len, w.lcx, w.lcy, (int)nslabs, g, fast, flow_frac * (double)m / (double)nslabs, w.gr, w.gth, w.scale,
                        c->d_work, c->d_counters + 1, c->num_sms, s, &c->pool_kernels);
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev[EV_POOL], s));
 
   // ---- results of the new events ----
-  if (out) {
+  if (hook && hook->fn && n_out) {
+    FarmsBatchView v{w.gr, w.gth, w.len + hh, w.theta + hh, n_out, out_off, s};
+    if ((rc = hook->fn(hook->user, c, &v))) return rc;
+  }
+  if (out && n_out) {
     if (out_stream != s) {
       CU(cudaEventRecord(c->ev_pool[set], s));
       CU(cudaStreamWaitEvent(out_stream, c->ev_pool[set], 0));
+    } else if ((rc = copy_fit_columns(c, w, out, hh, n_out, out_off, out_device, out_stream))) {
+      return rc;
     }
-    if ((rc = copy_out(c, out->t_rel ? out->t_rel + out_off : nullptr, w.et + h, n, out_device, out_stream))) return rc;
-    if ((rc = copy_out(c, out->global_r ? out->global_r + out_off : nullptr, w.gr, n, out_device, out_stream))) return rc;
-    if ((rc = copy_out(c, out->global_theta ? out->global_theta + out_off : nullptr, w.gth, n, out_device, out_stream))) return rc;
-    if ((rc = copy_out(c, out->vx ? out->vx + out_off : nullptr, w.vx + h, n, out_device, out_stream))) return rc;
-    if ((rc = copy_out(c, out->vy ? out->vy + out_off : nullptr, w.vy + h, n, out_device, out_stream))) return rc;
-    if ((rc = copy_out(c, out->local_r ? out->local_r + out_off : nullptr, w.len + h, n, out_device, out_stream))) return rc;
-    if ((rc = copy_out(c, out->local_theta ? out->local_theta + out_off : nullptr, w.theta + h, n, out_device, out_stream))) return rc;
-    if ((rc = copy_out(c, out->scale ? out->scale + out_off : nullptr, w.scale, n, out_device, out_stream))) return rc;
-    if ((rc = copy_out(c, out->valid ? out->valid + out_off : nullptr, w.valid + h, n, out_device, out_stream))) return rc;
-    if ((rc = copy_out(c, out->best_window ? out->best_window + out_off : nullptr, w.bw + h, n, out_device, out_stream))) return rc;
-    if ((rc = copy_out(c, out->inliers ? out->inliers + out_off : nullptr, w.inl + h, n, out_device, out_stream))) return rc;
-    if (out->det && w.det)
-      if ((rc = copy_out(c, out->det + out_off, w.det + h, n, out_device, out_stream))) return rc;
-    if (out_stream != s) {
-      CU(cudaEventRecord(c->ev_d2h[set], out_stream));
-      c->d2h_pending[set] = true;
-    }
+    if ((rc = copy_out(c, out->global_r ? out->global_r + out_off : nullptr, w.gr, n_out, out_device, out_stream))) return rc;
+    if ((rc = copy_out(c, out->global_theta ? out->global_theta + out_off : nullptr, w.gth, n_out, out_device, out_stream))) return rc;
+    if ((rc = copy_out(c, out->scale ? out->scale + out_off : nullptr, w.scale, n_out, out_device, out_stream))) return rc;
+  }
+  if (out_stream != s) {  // the set may be reused once these copies are done
+    CU(cudaEventRecord(c->ev_d2h[set], out_stream));
+    c->d2h_pending[set] = true;
   }
 
   // ---- new tail -> halo store ----
@@ -431,9 +373,8 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaMemcpyAsync(c->hlcx, w.lcx + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemcpyAsync(c->hlcy, w.lcy + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
   c->halo = nh;
-  CU(cudaStreamSynchronize(s));
 
-  // stage times of this batch
+  // stage times of this batch (the events were all recorded before the synchronisation above)
   float ms = 0;
   static const int order[] = {EV_H2D, EV_INGEST, EV_INDEX, EV_FIT, EV_BIN, EV_POOL, EV_END};
   for (int k = 1; k < 7; k++) {
@@ -443,17 +384,23 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   return 0;
 }
 
-int process(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t n, const farms_out *out,
-            bool device) {
+}  // namespace
+
+int farms_process_impl(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t n,
+                       const farms_out *out, bool in_device, bool out_device, uint64_t n_skip,
+                       const FarmsBatchHook *hook) {
   if (!c) return FARMS_ERR_ARG;
   c->err.clear();
   if (n == 0) return FARMS_OK;
   if (!x || !y || !t) return fail(c, FARMS_ERR_ARG, "null event array");
+  if (n_skip > n) return fail(c, FARMS_ERR_ARG, "n_skip exceeds n");
   CU(cudaSetDevice(c->cfg.device));
   cudaStream_t s = c->stream;
   if (!c->have_t0) {  // src/vFlow.cpp:194
-    if (device) {
-      CU(cudaMemcpy(&c->t0, t, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (in_device) {
+      CU(cudaMemcpyAsync(c->h_small + 12, t, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      memcpy(&c->t0, c->h_small + 12, sizeof(uint64_t));
     } else {
       c->t0 = t[0];
     }
@@ -466,10 +413,9 @@ int process(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *
   c->valid_seen = 0;
   c->pool_kernels = 0;
   float stage[8] = {0};
-  float h2d_ms = 0, d2h_ms = 0;
   CU(cudaEventRecord(c->ev[EV_START], s));
   const uint64_t nbatch = (n + maxb - 1) / maxb;
-  if (!device && c->cap_in < std::min<uint64_t>(n, maxb)) {
+  if (!in_device && c->cap_in < std::min<uint64_t>(n, maxb)) {
     const size_t want = (size_t)std::min<uint64_t>(n, maxb);
     CU(cudaDeviceSynchronize());
     for (int k = 0; k < 2; k++) {
@@ -484,8 +430,9 @@ int process(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *
     }
     c->cap_in = want;
   }
-  // host path: batch k+1 is uploaded while batch k computes, and the results of batch k go down while batch
-  // k+1 computes (three streams, two working sets)
+  // host input: batch k+1 is uploaded while batch k computes; host output: the results of batch k go down while
+  // batch k+1 computes (three streams, two working sets)
+  const bool two_sets = !in_device || !out_device;
   auto upload = [&](uint64_t k) -> int {
     const int set = (int)(k & 1);
     const uint64_t off = k * maxb;
@@ -497,53 +444,56 @@ int process(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *
     CU(cudaEventRecord(c->ev_h2d[set], c->h2d_stream));
     return 0;
   };
-  if (!device) {
+  auto drain = [&]() {
+    cudaDeviceSynchronize();
+    c->d2h_pending[0] = c->d2h_pending[1] = false;
+  };
+  if (!in_device) {
     int rc = upload(0);
     if (rc) return rc;
   }
   for (uint64_t k = 0; k < nbatch; k++) {
     const uint64_t off = k * maxb;
     const size_t nb = (size_t)std::min<uint64_t>(maxb, n - off);
-    const int set = device ? 0 : (int)(k & 1);
+    const int set = two_sets ? (int)(k & 1) : 0;
     const uint16_t *dx = x + off, *dy = y + off;
     const uint64_t *dt = t + off;
-    if (!device) {
+    if (!in_device) {
       if (k + 1 < nbatch) {
         int rc = upload(k + 1);
-        if (rc) return rc;
+        if (rc) { drain(); return rc; }
       }
       CU(cudaStreamWaitEvent(s, c->ev_h2d[set], 0));
       dx = c->in_x[set];
       dy = c->in_y[set];
       dt = c->in_t[set];
     }
-    int rc = run_batch(c, set, dx, dy, dt, nb, out, (size_t)off, device, device ? s : c->d2h_stream, stage);
+    const size_t skip = (size_t)(off >= n_skip ? 0 : std::min<uint64_t>(n_skip - off, nb));
+    const size_t out_off = (size_t)(off >= n_skip ? off - n_skip : 0);
+    int rc = run_batch(c, set, dx, dy, dt, nb, skip, out, out_off, out_device, out_device ? s : c->d2h_stream, stage, hook);
     if (rc) {
-      cudaDeviceSynchronize();
-      c->d2h_pending[0] = c->d2h_pending[1] = false;
+      drain();
       return rc;
     }
     c->total_events += nb;
   }
-  if (!device) {
-    CU(cudaStreamSynchronize(c->d2h_stream));
-    CU(cudaStreamSynchronize(c->h2d_stream));
-    c->d2h_pending[0] = c->d2h_pending[1] = false;
-  }
+  if (!out_device) CU(cudaStreamSynchronize(c->d2h_stream));
+  if (!in_device) CU(cudaStreamSynchronize(c->h2d_stream));
+  c->d2h_pending[0] = c->d2h_pending[1] = false;
   CU(cudaEventRecord(c->ev[EV_END], s));
   CU(cudaStreamSynchronize(s));
   float total = 0;
   CU(cudaEventElapsedTime(&total, c->ev[EV_START], c->ev[EV_END]));
+  CU(cudaMemcpyAsync(c->h_small + 16, c->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
   unsigned long long counters[8];
-  CU(cudaMemcpy(counters, c->d_counters, sizeof counters, cudaMemcpyDeviceToHost));
+  memcpy(counters, c->h_small + 16, sizeof counters);
   tm.total_ms = total;
-  tm.h2d_ms = h2d_ms;
   tm.ingest_ms = stage[1];
   tm.index_ms = stage[2];
   tm.fit_ms = stage[3];
   tm.bin_ms = stage[4];
   tm.pool_ms = stage[5];
-  tm.d2h_ms = d2h_ms;
   tm.events = n;
   tm.valid_events = counters[0];
   tm.pool_candidates = counters[1];
@@ -552,6 +502,7 @@ int process(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *
   return FARMS_OK;
 }
 
+namespace {
 }  // namespace
 
 extern "C" {
@@ -599,7 +550,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   c->fit_chunk = FIT_CHUNK_MIN;
   while (c->fit_chunk < FIT_CHUNK_MAX && (size_t)c->fit_chunk * 6 < c->npx) c->fit_chunk *= 2;
   if (cfg->fit_chunk) c->fit_chunk = (int)std::min<uint32_t>(std::max<uint32_t>(cfg->fit_chunk, 1024u), 1u << 20);
-  if (cfg->pool_variant > 3) return bail(FARMS_ERR_ARG);
+  if (cfg->pool_variant > 4) return bail(FARMS_ERR_ARG);
   if (cfg->pool_variant) c->pool_impl = (int)cfg->pool_variant;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
@@ -612,7 +563,8 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
     if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   {
     cudaEvent_t *evs[] = {&c->ev_h2d[0], &c->ev_h2d[1], &c->ev_ingest[0], &c->ev_ingest[1], &c->ev_pool[0],
-                          &c->ev_pool[1], &c->ev_d2h[0], &c->ev_d2h[1], &c->ev_c0, &c->ev_c1};
+                          &c->ev_pool[1], &c->ev_d2h[0], &c->ev_d2h[1], &c->ev_c0, &c->ev_c1, &c->ev_fitdone[0],
+                          &c->ev_fitdone[1]};
     for (cudaEvent_t *e : evs)
       if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   }
@@ -630,7 +582,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   ok &= cudaMalloc((void **)&c->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->d_work, 4 * sizeof(unsigned int)) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->d_small, 64) == cudaSuccess;
-  ok &= cudaMallocHost((void **)&c->h_small, 64) == cudaSuccess;
+  ok &= cudaMallocHost((void **)&c->h_small, 256) == cudaSuccess;
   if (!ok) return bail(FARMS_ERR_NOMEM);
   launch_sae_init(c->sae, c->npx, c->stream);
   if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail(FARMS_ERR_CUDA);
@@ -652,14 +604,15 @@ void farms_destroy(farms_ctx *c) {
   }
   void *ps[] = {c->sae, c->hx, c->hy, c->ht, c->hm, c->hlen, c->hlcx, c->hlcy, c->d_err, c->d_counters, c->d_work,
                 c->d_small, c->in_x[0], c->in_y[0], c->in_t[0], c->in_x[1], c->in_y[1], c->in_t[1], c->sort_temp.p,
-                c->scan_temp.p, c->cell_start.p, c->fit_scratch.p, c->surf_tmp.p, c->item_ovf.p};
+                c->scan_temp.p, c->cell_start.p, c->fit_scratch.p, c->surf_tmp.p, c->item_ovf.p, c->io_x.p, c->io_y.p,
+                c->io_t.p, c->io_surf_t.p, c->io_surf_hit.p};
   for (void *p : ps)
     if (p) cudaFree(p);
   if (c->h_small) cudaFreeHost(c->h_small);
   for (int i = 0; i < EV_COUNT; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaEvent_t evs[] = {c->ev_h2d[0], c->ev_h2d[1], c->ev_ingest[0], c->ev_ingest[1], c->ev_pool[0], c->ev_pool[1],
-                       c->ev_d2h[0], c->ev_d2h[1], c->ev_c0, c->ev_c1};
+                       c->ev_d2h[0], c->ev_d2h[1], c->ev_c0, c->ev_c1, c->ev_fitdone[0], c->ev_fitdone[1]};
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
   if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
@@ -681,13 +634,13 @@ int farms_get_params(const farms_ctx *c, int32_t *filtersize, int32_t *radius, i
 int farms_process_host(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *t, const uint8_t *p,
                        uint64_t n, const farms_out *out) {
   (void)p;
-  return process(c, x, y, t, n, out, false);
+  return farms_process_impl(c, x, y, t, n, out, false, false, 0, nullptr);
 }
 
 int farms_process_device(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *t, const uint8_t *p,
                          uint64_t n, const farms_out *out) {
   (void)p;
-  return process(c, x, y, t, n, out, true);
+  return farms_process_impl(c, x, y, t, n, out, true, true, 0, nullptr);
 }
 
 uint64_t farms_num_events(const farms_ctx *c) { return c ? c->total_events : 0; }
@@ -738,65 +691,80 @@ int farms_state_fold(farms_ctx *c, const uint32_t *d_last_t, const uint8_t *d_hi
   return FARMS_OK;
 }
 
+// last event per pixel of a device-resident slice, accumulated into the packed surface (surf_tmp); `first` clears it
+static int slice_surface_accumulate(farms_ctx *c, const uint16_t *d_x, const uint16_t *d_y, const uint64_t *d_t,
+                                    uint64_t n, uint64_t index_base, uint64_t t0, bool first) {
+  int rc;
+  if ((rc = ensure(c, c->surf_tmp, c->npx * sizeof(unsigned long long)))) return rc;
+  if (first) {
+    CU(cudaMemsetAsync(c->surf_tmp.p, 0, c->npx * sizeof(unsigned long long), c->stream));
+    CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+  }
+  launch_slice_surface(d_x, d_y, d_t, (size_t)n, (uint32_t)index_base, t0, c->W, c->H,
+                       (unsigned long long *)c->surf_tmp.p, c->d_err, c->stream);
+  CU(cudaGetLastError());
+  return FARMS_OK;
+}
+
+static int slice_surface_finish(farms_ctx *c, uint32_t *d_last_t, uint8_t *d_hit) {
+  launch_unpack_surface((const unsigned long long *)c->surf_tmp.p, c->npx, d_last_t, d_hit, c->stream);
+  k_publish<<<1, 32, 0, c->stream>>>(c->h_small + 8, (const uint32_t *)c->d_err, 1);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  if (((int *)c->h_small)[8]) return fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
+  return FARMS_OK;
+}
+
 int farms_slice_surface(farms_ctx *c, const uint16_t *d_x, const uint16_t *d_y, const uint64_t *d_t, uint64_t n,
                         uint64_t t0, uint32_t *d_last_t, uint8_t *d_hit) {
   if (!c || !d_last_t || !d_hit || (n && (!d_x || !d_y || !d_t))) return FARMS_ERR_ARG;
   if (n >= (1ull << 32) - 1) return fail(c, FARMS_ERR_ARG, "slice too long");
   CU(cudaSetDevice(c->cfg.device));
   int rc;
-  if ((rc = ensure(c, c->surf_tmp, c->npx * sizeof(unsigned long long)))) return rc;
-  CU(cudaMemsetAsync(c->surf_tmp.p, 0, c->npx * sizeof(unsigned long long), c->stream));
-  CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
-  launch_slice_surface(d_x, d_y, d_t, (size_t)n, t0, c->W, c->H, (unsigned long long *)c->surf_tmp.p, c->d_err, c->stream);
-  launch_unpack_surface((const unsigned long long *)c->surf_tmp.p, c->npx, d_last_t, d_hit, c->stream);
-  k_publish<<<1, 32, 0, c->stream>>>(c->h_small, (const uint32_t *)c->d_err, 1);
-  CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(c->stream));
-  if (((int *)c->h_small)[0]) return fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
-  return FARMS_OK;
+  if ((rc = slice_surface_accumulate(c, d_x, d_y, d_t, n, 0, t0, true))) return rc;
+  return slice_surface_finish(c, d_last_t, d_hit);
 }
 
+// Host arrays: the slice goes through the context's input staging buffers in pieces (all on the compute stream:
+// every copy is ordered before the kernel that reads it), the two surfaces come back the same way.
 int farms_slice_surface_host(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t n,
                              uint64_t t0, uint32_t *last_t, uint8_t *hit) {
   if (!c || !last_t || !hit || (n && (!x || !y || !t))) return FARMS_ERR_ARG;
+  if (n >= (1ull << 32) - 1) return fail(c, FARMS_ERR_ARG, "slice too long");
   CU(cudaSetDevice(c->cfg.device));
-  uint16_t *dx = nullptr, *dy = nullptr;
-  uint64_t *dt = nullptr;
-  uint32_t *dl = nullptr;
-  uint8_t *dh = nullptr;
-  const size_t cap = (size_t)std::max<uint64_t>(n, 1);
-  bool ok = cudaMalloc((void **)&dx, cap * 2) == cudaSuccess && cudaMalloc((void **)&dy, cap * 2) == cudaSuccess &&
-            cudaMalloc((void **)&dt, cap * 8) == cudaSuccess && cudaMalloc((void **)&dl, c->npx * 4) == cudaSuccess &&
-            cudaMalloc((void **)&dh, c->npx) == cudaSuccess;
-  int rc = ok ? FARMS_OK : fail(c, FARMS_ERR_NOMEM, "out of device memory for a %llu-event slice", (unsigned long long)n);
-  if (ok && n) {
-    ok = cudaMemcpy(dx, x, n * 2, cudaMemcpyHostToDevice) == cudaSuccess &&
-         cudaMemcpy(dy, y, n * 2, cudaMemcpyHostToDevice) == cudaSuccess &&
-         cudaMemcpy(dt, t, n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
-    if (!ok) rc = fail(c, FARMS_ERR_CUDA, "upload of the slice failed");
+  int rc;
+  const size_t piece = 4u << 20;
+  if ((rc = ensure(c, c->io_x, piece * 2)) || (rc = ensure(c, c->io_y, piece * 2)) || (rc = ensure(c, c->io_t, piece * 8)) ||
+      (rc = ensure(c, c->io_surf_t, c->npx * 4)) || (rc = ensure(c, c->io_surf_hit, c->npx)))
+    return rc;
+  if ((rc = slice_surface_accumulate(c, nullptr, nullptr, nullptr, 0, 0, t0, true))) return rc;
+  for (uint64_t off = 0; off < n; off += piece) {
+    const size_t nb = (size_t)std::min<uint64_t>(piece, n - off);
+    CU(cudaMemcpyAsync(c->io_x.p, x + off, nb * 2, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->io_y.p, y + off, nb * 2, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->io_t.p, t + off, nb * 8, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = slice_surface_accumulate(c, (const uint16_t *)c->io_x.p, (const uint16_t *)c->io_y.p,
+                                       (const uint64_t *)c->io_t.p, nb, off, t0, false)))
+      return rc;
   }
-  if (rc == FARMS_OK) rc = farms_slice_surface(c, dx, dy, dt, n, t0, dl, dh);
-  if (rc == FARMS_OK && (cudaMemcpy(last_t, dl, c->npx * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
-                         cudaMemcpy(hit, dh, c->npx, cudaMemcpyDeviceToHost) != cudaSuccess))
-    rc = fail(c, FARMS_ERR_CUDA, "download of the surface failed");
-  cudaFree(dx); cudaFree(dy); cudaFree(dt); cudaFree(dl); cudaFree(dh);
-  return rc;
+  if ((rc = slice_surface_finish(c, (uint32_t *)c->io_surf_t.p, (uint8_t *)c->io_surf_hit.p))) return rc;
+  CU(cudaMemcpyAsync(last_t, c->io_surf_t.p, c->npx * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(hit, c->io_surf_hit.p, c->npx, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return FARMS_OK;
 }
 
 int farms_state_fold_host(farms_ctx *c, const uint32_t *last_t, const uint8_t *hit) {
   if (!c || !last_t || !hit) return FARMS_ERR_ARG;
   CU(cudaSetDevice(c->cfg.device));
-  uint32_t *dl = nullptr;
-  uint8_t *dh = nullptr;
-  int rc = FARMS_OK;
-  if (cudaMalloc((void **)&dl, c->npx * 4) != cudaSuccess || cudaMalloc((void **)&dh, c->npx) != cudaSuccess)
-    rc = fail(c, FARMS_ERR_NOMEM, "out of device memory for a surface");
-  else if (cudaMemcpy(dl, last_t, c->npx * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-           cudaMemcpy(dh, hit, c->npx, cudaMemcpyHostToDevice) != cudaSuccess)
-    rc = fail(c, FARMS_ERR_CUDA, "upload of the surface failed");
-  if (rc == FARMS_OK) rc = farms_state_fold(c, dl, dh);
-  cudaFree(dl); cudaFree(dh);
-  return rc;
+  int rc;
+  if ((rc = ensure(c, c->io_surf_t, c->npx * 4)) || (rc = ensure(c, c->io_surf_hit, c->npx))) return rc;
+  CU(cudaMemcpyAsync(c->io_surf_t.p, last_t, c->npx * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->io_surf_hit.p, hit, c->npx, cudaMemcpyHostToDevice, c->stream));
+  launch_sae_fold(c->sae, c->npx, (const uint32_t *)c->io_surf_t.p, (const uint8_t *)c->io_surf_hit.p, c->stream);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  return FARMS_OK;
 }
 
 int farms_pack4_f32(farms_ctx *c, const double *d_a, const double *d_b, const double *d_c, const double *d_d,

@@ -34,6 +34,7 @@ struct Options {
   bool fast = false;  // --fast 1: FP32 ring partials in the pooling kernel (about 1e-7 relative on columns 5-6)
   bool binary = false;  // --binary 1: <filename>.evb in, <filename>_FARMSOut_.bin out (include/farms_textio.h)
   int gpus = 1;         // --gpus N: time-slice the recording over devices device .. device+N-1 (one host thread each)
+  bool same_device = false;  // --same-device 1: all slices on --device (in-process transport; one-GPU boxes, tests)
 };
 
 void usage() {
@@ -53,7 +54,8 @@ void usage() {
       "  --device arg          CUDA device ordinal (extension)\n"
       "  --fast arg            1 = fastest pooling kernel, columns 5-6 accurate to ~1e-7 (extension)\n"
       "  --binary arg          1 = binary side-format: <filename>.evb in, <filename>_FARMSOut_.bin out (extension)\n"
-      "  --gpus arg            time-slice the recording over this many GPUs, device .. device+N-1 (extension)\n");
+      "  --gpus arg            time-slice the recording over this many GPUs, device .. device+N-1 (extension)\n"
+      "  --same-device arg     1 = run all --gpus slices on --device (extension, one-GPU boxes)\n");
 }
 
 bool parse_int(const std::string &s, int &out) {
@@ -87,7 +89,8 @@ int parse_args(int argc, char **argv, Options &o) {
       return 2;
     }
     static const char *known[] = {"filename", "height", "width", "filtersize", "inlierCheck", "numEvents",
-                                  "numevents", "NUMEVENTS", "SERIAL", "v", "device", "fast", "binary", "gpus"};
+                                  "numevents", "NUMEVENTS", "SERIAL", "v", "device", "fast", "binary", "gpus",
+                                  "same-device"};
     bool ok = false;
     for (const char *k : known) ok |= name == k;
     if (!ok) {
@@ -123,6 +126,7 @@ int parse_args(int argc, char **argv, Options &o) {
     else if (name == "fast") { o.fast = iv == 1; }
     else if (name == "binary") { o.binary = iv == 1; }
     else if (name == "gpus") { o.gpus = iv < 1 ? 1 : iv; }
+    else if (name == "same-device") { o.same_device = iv == 1; }
   }
   // the reference honours the spellings in the order numEvents, numevents, NUMEVENTS (src/main.cpp:131-151)
   // and converts the int to unsigned long
@@ -135,17 +139,12 @@ int parse_args(int argc, char **argv, Options &o) {
   return 0;
 }
 
-// ---- single-process multi-GPU run: the recording is cut into equal time slices, one per GPU.
-// GPU g owns the events of stream time [g*D, (g+1)*D), also processes the 499-us causal halo in front of them
-// (pooling admits |dt| < 500 us, src/vFlow.cpp:1002) and rebuilds the surface of active events at its halo start
-// from the "last event per pixel" surfaces of the earlier slices (the surface never forgets, src/vFlow.cpp:267):
-// slice r contributes the events of [r*D - 499, (r+1)*D - 499), which tile the time axis; later slices win.
-struct SliceOut {
-  std::vector<uint32_t> t_rel;
-  std::vector<double> gr, gth, vx, vy, lr, lth;
-  std::vector<uint8_t> scale;
-};
-
+// ---- single-process multi-GPU run: the recording is cut into equal time slices, one per GPU,
+// one host thread and one context per slice, joined by a farms_comm (include/farms_b200.h): NCCL between the
+// devices, or the in-process transport when the slices share one device (--same-device 1, one-GPU boxes).
+// Slice g owns the events of stream time [g*D, (g+1)*D), also processes the 499-us causal halo in front of them
+// and contributes the events of [g*D - 499, (g+1)*D - 499) to the surface exchange (these ranges tile the time
+// axis).  Every slice writes its owned rows straight into the caller's output columns.
 int run_sliced(const Options &o, const farms_config &base, const farms_events &ev, const farms_out &out,
                farms_timings &tm_sum, uint64_t &events_done, std::string &err) {
   const size_t n = (size_t)ev.n;
@@ -159,84 +158,70 @@ int run_sliced(const Options &o, const farms_config &base, const farms_events &e
   auto first_at = [&](uint64_t ts) {  // first event with stream time >= ts
     return (size_t)(std::lower_bound(ev.t, ev.t + n, t0 + ts) - ev.t);
   };
-  const bool same_device = std::getenv("FARMS_CLI_SAME_DEVICE") != nullptr;  // tests on a one-GPU box
-  const size_t npx = (size_t)o.width * o.height;
+  unsigned char id[FARMS_COMM_ID_BYTES];
+  std::memset(id, 0, sizeof id);
+  if (o.same_device) {
+    const uint64_t key = (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count() ^ (uint64_t)(uintptr_t)&ev;
+    std::memcpy(id, &key, sizeof key);
+  } else if (farms_comm_unique_id(id) != FARMS_OK) {
+    err = "NCCL is not available (libnccl.so.2 cannot be loaded)";
+    return 1;
+  }
   std::vector<farms_ctx *> ctx(G, nullptr);
-  std::vector<std::vector<uint32_t>> surf_t(G);
-  std::vector<std::vector<uint8_t>> surf_hit(G);
+  std::vector<farms_comm *> comm(G, nullptr);
   std::vector<int> rc(G, FARMS_OK);
   std::vector<std::string> msg(G);
-  std::vector<SliceOut> so(G);
-  std::vector<size_t> lo(G), begin(G), end(G);
-  auto each_gpu = [&](auto fn) {
-    std::vector<std::thread> th;
-    for (int g = 0; g < G; g++) th.emplace_back([&, g] { fn(g); });
-    for (auto &t : th) t.join();
-    for (int g = 0; g < G; g++)
-      if (rc[g] != FARMS_OK) {
-        err = "GPU slice " + std::to_string(g) + ": " + msg[g];
-        return 1;
-      }
-    return 0;
-  };
-  // phase 1: contexts, and every slice's share of the surface exchange
-  int bad = each_gpu([&](int g) {
-    farms_config cfg = base;
-    cfg.device = same_device ? base.device : base.device + g;
-    rc[g] = farms_create(&ctx[g], &cfg);
-    if (rc[g] != FARMS_OK) { msg[g] = "farms_create failed (device " + std::to_string(cfg.device) + ")"; return; }
-    farms_set_t0(ctx[g], t0);
+  std::vector<size_t> lo(G), begin(G), end(G), surf_end(G);
+  for (int g = 0; g < G; g++) {
     begin[g] = first_at((uint64_t)g * D);
     end[g] = g == G - 1 ? n : first_at((uint64_t)(g + 1) * D);
     lo[g] = g == 0 ? 0 : first_at((uint64_t)g * D - std::min<uint64_t>(HALO, (uint64_t)g * D));
-    if (g < G - 1) {
-      const size_t s0 = lo[g], s1 = first_at((uint64_t)(g + 1) * D - std::min<uint64_t>(HALO, (uint64_t)(g + 1) * D));
-      surf_t[g].resize(npx);
-      surf_hit[g].resize(npx);
-      rc[g] = farms_slice_surface_host(ctx[g], ev.x + s0, ev.y + s0, ev.t + s0, s1 > s0 ? s1 - s0 : 0, t0,
-                                       surf_t[g].data(), surf_hit[g].data());
+    surf_end[g] = g == G - 1 ? lo[g] : first_at((uint64_t)(g + 1) * D - std::min<uint64_t>(HALO, (uint64_t)(g + 1) * D));
+  }
+  std::vector<std::thread> th;
+  for (int g = 0; g < G; g++)
+    th.emplace_back([&, g] {
+      farms_config cfg = base;
+      cfg.device = o.same_device ? base.device : base.device + g;
+      rc[g] = farms_create(&ctx[g], &cfg);
+      if (rc[g] != FARMS_OK) { msg[g] = "farms_create failed (device " + std::to_string(cfg.device) + ")"; }
+      // farms_comm_create is collective: every thread must call it, also after a failed farms_create elsewhere
+      if (rc[g] == FARMS_OK) {
+        rc[g] = farms_comm_create(&comm[g], ctx[g], G, g, id, o.same_device ? FARMS_COMM_LOCAL : 0u);
+        if (rc[g] != FARMS_OK) msg[g] = std::string("farms_comm_create: ") + farms_last_error(ctx[g]);
+      }
+      if (rc[g] != FARMS_OK) return;
+      farms_out fo;
+      std::memset(&fo, 0, sizeof fo);
+      const size_t at = begin[g];
+      fo.t_rel = out.t_rel + at; fo.global_r = out.global_r + at; fo.global_theta = out.global_theta + at;
+      fo.vx = out.vx + at; fo.vy = out.vy + at; fo.local_r = out.local_r + at; fo.local_theta = out.local_theta + at;
+      fo.scale = out.scale + at;
+      rc[g] = farms_comm_process(comm[g], ev.x + lo[g], ev.y + lo[g], ev.t + lo[g], end[g] - lo[g], begin[g] - lo[g],
+                                 surf_end[g] - lo[g], t0, 0u, &fo, nullptr);
       if (rc[g] != FARMS_OK) msg[g] = farms_last_error(ctx[g]);
+    });
+  for (auto &t : th) t.join();
+  int bad = 0;
+  for (int g = 0; g < G; g++)
+    if (rc[g] != FARMS_OK && !bad) {
+      err = "GPU slice " + std::to_string(g) + ": " + msg[g];
+      bad = 1;
     }
-  });
-  // phase 2: fold the earlier slices' surfaces in order, then process halo + owned events
-  if (!bad) bad = each_gpu([&](int g) {
-    for (int r = 0; r < g && rc[g] == FARMS_OK; r++)
-      rc[g] = farms_state_fold_host(ctx[g], surf_t[r].data(), surf_hit[r].data());
-    if (rc[g] != FARMS_OK) { msg[g] = farms_last_error(ctx[g]); return; }
-    const size_t m = end[g] - lo[g];
-    SliceOut &q = so[g];
-    q.t_rel.resize(m); q.gr.resize(m); q.gth.resize(m); q.vx.resize(m); q.vy.resize(m); q.lr.resize(m);
-    q.lth.resize(m); q.scale.resize(m);
-    farms_out fo;
-    std::memset(&fo, 0, sizeof fo);
-    fo.t_rel = q.t_rel.data(); fo.global_r = q.gr.data(); fo.global_theta = q.gth.data(); fo.vx = q.vx.data();
-    fo.vy = q.vy.data(); fo.local_r = q.lr.data(); fo.local_theta = q.lth.data(); fo.scale = q.scale.data();
-    if (m) rc[g] = farms_process_host(ctx[g], ev.x + lo[g], ev.y + lo[g], ev.t + lo[g], nullptr, m, &fo);
-    if (rc[g] != FARMS_OK) msg[g] = farms_last_error(ctx[g]);
-  });
   std::memset(&tm_sum, 0, sizeof tm_sum);
   events_done = 0;
   for (int g = 0; g < G; g++) {
     if (!bad && ctx[g]) {
-      const size_t skip = begin[g] - lo[g], cnt = end[g] - begin[g], at = begin[g];
-      const SliceOut &q = so[g];
-      std::copy_n(q.t_rel.begin() + skip, cnt, out.t_rel + at);
-      std::copy_n(q.gr.begin() + skip, cnt, out.global_r + at);
-      std::copy_n(q.gth.begin() + skip, cnt, out.global_theta + at);
-      std::copy_n(q.vx.begin() + skip, cnt, out.vx + at);
-      std::copy_n(q.vy.begin() + skip, cnt, out.vy + at);
-      std::copy_n(q.lr.begin() + skip, cnt, out.local_r + at);
-      std::copy_n(q.lth.begin() + skip, cnt, out.local_theta + at);
-      std::copy_n(q.scale.begin() + skip, cnt, out.scale + at);
       farms_timings tm;
       farms_get_timings(ctx[g], &tm);
       tm_sum.total_ms = std::max(tm_sum.total_ms, tm.total_ms);
       tm_sum.ingest_ms += tm.ingest_ms; tm_sum.index_ms += tm.index_ms; tm_sum.fit_ms += tm.fit_ms;
       tm_sum.bin_ms += tm.bin_ms; tm_sum.pool_ms += tm.pool_ms;
       tm_sum.valid_events += tm.valid_events;  // includes the halo events of every slice
-      tm_sum.events += cnt;
-      events_done += cnt;
+      tm_sum.events += end[g] - begin[g];
+      events_done += end[g] - begin[g];
     }
+    if (comm[g]) farms_comm_destroy(comm[g]);
     if (ctx[g]) farms_destroy(ctx[g]);
   }
   return bad;

@@ -72,7 +72,7 @@ __global__ void k_slab_flags(const uint32_t *__restrict__ em, const uint32_t *__
 }
 
 __global__ void k_slice_surface(const uint16_t *__restrict__ x, const uint16_t *__restrict__ y,
-                                const uint64_t *__restrict__ t, size_t n, uint64_t t0, int W, int H,
+                                const uint64_t *__restrict__ t, size_t n, uint32_t index_base, uint64_t t0, int W, int H,
                                 unsigned long long *__restrict__ packed, int *__restrict__ err) {
   size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -86,7 +86,7 @@ __global__ void k_slice_surface(const uint16_t *__restrict__ x, const uint16_t *
   }
   unsigned long long *cell = &packed[(size_t)x[i] * H + y[i]];
   // later index wins: index in the high word
-  const unsigned long long mine = ((unsigned long long)(i + 1) << 32) | tr;
+  const unsigned long long mine = ((unsigned long long)(index_base + (uint32_t)i + 1u) << 32) | tr;
   if (*(volatile unsigned long long *)cell < mine) atomicMax(cell, mine);
 }
 
@@ -131,9 +131,9 @@ void launch_slab_flags(const uint32_t *em, const uint32_t *et, size_t m, int sla
                        cudaStream_t s) {
   if (m) k_slab_flags<<<nb(m, 256), 256, 0, s>>>(em, et, m, slab_shift, flags, nonmono);
 }
-void launch_slice_surface(const uint16_t *x, const uint16_t *y, const uint64_t *t, size_t n, uint64_t t0, int W, int H,
-                          unsigned long long *packed, int *err_flag, cudaStream_t s) {
-  if (n) k_slice_surface<<<nb(n, 256), 256, 0, s>>>(x, y, t, n, t0, W, H, packed, err_flag);
+void launch_slice_surface(const uint16_t *x, const uint16_t *y, const uint64_t *t, size_t n, uint32_t index_base,
+                          uint64_t t0, int W, int H, unsigned long long *packed, int *err_flag, cudaStream_t s) {
+  if (n) k_slice_surface<<<nb(n, 256), 256, 0, s>>>(x, y, t, n, index_base, t0, W, H, packed, err_flag);
 }
 void launch_unpack_surface(const unsigned long long *packed, size_t npx, uint32_t *last_t, uint8_t *hit,
                            cudaStream_t s) {

@@ -893,6 +893,527 @@ void launch_tile(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
 
 
 // ------------------------------------------------------------------------------------------------
+// fast path, two-phase: k_pool_warp
+// ------------------------------------------------------------------------------------------------
+// Same owner-tile / slab-ring structure as k_pool_tile, with a different inner loop.  In k_pool_tile a lane tests
+// a staged record and, if it passes, immediately adds it to its ring accumulator in shared memory: 38 % of the
+// lanes pass, so the 22-instruction accumulate body runs at 38 % lane efficiency and dominates the kernel.  Here a
+// whole warp pools one event in two phases:
+//   A  every lane tests records (8-byte packed test record: one LDS.64, one VABSDIFF4 for the window, a 24-bit
+//      index/span compare for "still the latest event of its pixel and younger than 500 us") and appends the slot
+//      address of each passing record to its own lane-private queue (one predicated STS.U16, no ballots);
+//   B  every lane drains its queue: payload (|flow|cos, |flow|sin as float2), ring from the packed coordinates,
+//      read-modify-write of its float4 ring accumulator -- all lanes busy (a lane holds 17 +- 4 entries).
+// Staged records are 16 bytes instead of 20 (coordinates relative to the tile's region in one byte each, the index
+// relative to the slab's first event in 24 bits, the life span in 24 bits; a slab that does not fit 24 bits is
+// flagged as overflowed and left to the exact path), so the queues cost no slot capacity.
+constexpr int WQ_DEPTH = 32;   // queue entries per lane before a drain is forced
+constexpr int WP_PAD = 32;     // zeroed test records behind a slot's last record (span 0 never passes)
+
+template <int WARPS, int CAP, int NSL>
+struct WarpSmem {
+  static constexpr int RING = TK_LB + NSL, STRIDE = CAP + WP_PAD;
+  uint2 ta[RING * STRIDE];   // {x_rel | y_rel << 8 | idx_rel[15:0] << 16,  idx_rel[23:16] | span << 8}
+  float2 pb[RING * STRIDE];  // |flow|cos(theta), |flow|sin(theta)
+  float4 acc[WARPS][FARMS_NSCALES][32];  // per-lane ring partials: len, lcx, lcy, count
+  uint16_t queue[WARPS][WQ_DEPTH][32];
+  uint32_t tlist[NSL][TK_MAXT];
+  uint32_t run_s[RING * TK_MAXRUN], run_o[RING * TK_MAXRUN + 1];
+  uint8_t run_info[RING * TK_MAXRUN];
+  uint32_t slab_f[RING + 1], slab_pre[RING + 1];
+  uint32_t wcount[WARPS];
+  uint32_t slot_base[RING];  // index of the first event of the slab a slot holds (idx_rel is relative to it)
+  int tag[RING], count[RING], overflow[RING];
+  int dlo[NSL], dhi[NSL], ovf[NSL];
+  unsigned int ntg[NSL], tnext, item;
+};
+
+// stage_slabs for the packed layout (same one-pass ordered compaction over the concatenated index runs)
+template <class SM, int WARPS, int CAP, int NSL>
+__device__ void stage_slabs_packed(const PoolArgs &A, SM &S, int s0, int s1, const Region &R, uint32_t i_round) {
+  constexpr int THREADS = WARPS * 32, RING = TK_LB + NSL, STRIDE = SM::STRIDE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ts = A.g.tile_shift, nty = A.g.nty, NT = A.g.ntx * A.g.nty, H = A.g.H;
+  const int tx0 = R.rx0 >> ts, tx1 = R.rx1 >> ts, ty0 = R.ry0 >> ts, ty1 = R.ry1 >> ts;
+  const int nrun0 = R.ry1 >= R.ry0 ? tx1 - tx0 + 1 : 0;  // empty on tall sensors whose row bound is above the region
+  const int atx0 = R.ax0 >> ts, atx1 = R.ax1 >> ts;
+  const int nrun1 = R.ay1 >= 0 ? atx1 - atx0 + 1 : 0;
+  const int nrun = nrun0 + nrun1;
+  const int nsl = s1 - s0 + 1, nruns = nsl * nrun;
+  __syncthreads();  // previous users of the run tables, of wcount and of these slots are done
+  for (int q = tid; q < nruns; q += THREADS) {
+    const int sl = q / nrun, c = q - sl * nrun;
+    uint32_t a, b;
+    if (c < nrun0) {
+      const size_t cb = (size_t)(s0 + sl) * NT + (size_t)(tx0 + c) * nty;
+      a = A.cell_start[cb + ty0];
+      b = A.cell_start[cb + ty1 + 1];
+    } else {
+      const size_t cb = (size_t)(s0 + sl) * NT + (size_t)(atx0 + c - nrun0) * nty;
+      a = A.cell_start[cb];
+      b = A.cell_start[cb + (R.ay1 >> ts) + 1];
+    }
+    S.run_s[q] = a;
+    S.run_o[q + 1] = b - a;  // lengths first, offsets below
+    S.run_info[q] = (uint8_t)(sl | (c >= nrun0 ? 0x80 : 0));
+  }
+  if (tid < nsl) {
+    const int slot = (s0 + tid) % RING;
+    S.slot_base[slot] = A.slab_first[s0 + tid];
+    S.overflow[slot] = 0;
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive offsets of the runs in the flat list: consecutive runs per lane + a warp scan
+    constexpr int RPL = (RING * TK_MAXRUN + 31) / 32;
+    uint32_t loc[RPL], sum = 0;
+#pragma unroll
+    for (int j = 0; j < RPL; j++) {
+      const int q = lane * RPL + j;
+      loc[j] = q < nruns ? S.run_o[q + 1] : 0u;
+      sum += loc[j];
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    uint32_t run = inc - sum;
+#pragma unroll
+    for (int j = 0; j < RPL; j++) {
+      const int q = lane * RPL + j;
+      run += loc[j];
+      if (q < nruns) S.run_o[q + 1] = run;
+    }
+    if (lane == 0) S.run_o[0] = 0;
+  }
+  __syncthreads();
+  const uint32_t total = S.run_o[nruns];
+  if (tid <= nsl) {
+    S.slab_f[tid] = tid < nsl ? S.run_o[tid * nrun] : total;
+    S.slab_pre[tid] = 0;
+  }
+  const double *pay_cx = A.pay + A.m, *pay_cy = A.pay + 2 * A.m;
+  uint32_t out_base = 0;
+  int lo_hint = 0;  // this thread's flat positions only grow: the run search resumes where it stopped
+  for (uint32_t r0 = 0; r0 < total; r0 += 2 * THREADS) {
+    bool pass[2] = {false, false};
+    uint4 rec[2];
+    double cxv[2] = {0.0, 0.0}, cyv[2] = {0.0, 0.0};
+    uint32_t info[2] = {0, 0};
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const uint32_t f = r0 + e * THREADS + tid;
+      rec[e] = make_uint4(0, 0, 0, 0);
+      if (f < total) {
+        int lo = lo_hint, hi = nruns - 1;  // last run whose offset is <= f
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (S.run_o[mid] <= f) lo = mid; else hi = mid - 1;
+        }
+        lo_hint = lo;
+        const uint32_t pos = S.run_s[lo] + (f - S.run_o[lo]);
+        rec[e] = A.rec[pos];
+        cxv[e] = pay_cx[pos];
+        cyv[e] = pay_cy[pos];
+        info[e] = S.run_info[lo];
+        pass[e] = true;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      int x = (int)(rec[e].x & 0xffffu), y = (int)(rec[e].x >> 16);
+      if (!(info[e] & 0x80u)) {
+        pass[e] = pass[e] && x >= R.rx0 && x <= R.rx1 && y >= R.ry0 && y <= R.ry1;
+      } else {
+        pass[e] = pass[e] && x >= R.ax0 && x <= R.ax1 && y <= R.ay1;
+        x -= 1;   // logical window coordinates of the aliased cell
+        y += H;
+      }
+      // superseded at its pixel (or past 500 us) before the first event of the round: dead for every target
+      pass[e] = pass[e] && rec[e].w > i_round;
+      rec[e].x = (uint32_t)(x - R.rx0) | ((uint32_t)(y - R.ry0) << 8);  // both < 132 for a passing record
+    }
+    const unsigned bal0 = __ballot_sync(0xffffffffu, pass[0]), bal1 = __ballot_sync(0xffffffffu, pass[1]);
+    if (lane == 0) S.wcount[warp] = (uint32_t)__popc(bal0) | ((uint32_t)__popc(bal1) << 16);
+    __syncthreads();
+    uint32_t pre0 = 0, pre1 = 0, all0 = 0, all1 = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; w++) {
+      const uint32_t cw = S.wcount[w];
+      if (w < warp) {
+        pre0 += cw & 0xffffu;
+        pre1 += cw >> 16;
+      }
+      all0 += cw & 0xffffu;
+      all1 += cw >> 16;
+    }
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t g0 = out_base + pre0 + __popc(bal0 & lt), g1 = out_base + all0 + pre1 + __popc(bal1 & lt);
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const uint32_t f = r0 + e * THREADS + tid;
+      if (f < total)
+        for (int sl = 0; sl < nsl; sl++)
+          if (S.slab_f[sl] == f) S.slab_pre[sl] = e ? g1 : g0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int sl = (int)(info[e] & 0x7fu);
+      const uint32_t o = (e ? g1 : g0) - S.slab_pre[sl];
+      if (pass[e] && o < (uint32_t)CAP) {
+        const int slot = (s0 + sl) % RING;
+        const uint32_t rel = rec[e].z - S.slot_base[slot], span = rec[e].w - rec[e].z;
+        if ((rel | span) >> 24) S.overflow[slot] = 1;  // does not fit the packed record: leave the slab to the exact path
+        S.ta[slot * STRIDE + o] = make_uint2(rec[e].x | (rel << 16), ((rel >> 16) & 0xffu) | (span << 8));
+        S.pb[slot * STRIDE + o] = make_float2(__double2float_rn(cxv[e]), __double2float_rn(cyv[e]));
+      }
+    }
+    out_base += all0 + all1;
+  }
+  __syncthreads();
+  // slabs without any raw record at or after their first position (trailing empties) start at the end
+  if (tid <= nsl && S.slab_f[tid] >= total) S.slab_pre[tid] = out_base;
+  __syncthreads();
+  if (tid < nsl) {
+    const uint32_t raw = S.slab_pre[tid + 1] - S.slab_pre[tid];
+    const int slot = (s0 + tid) % RING;
+    S.tag[slot] = s0 + tid;
+    S.count[slot] = (int)min(raw, (uint32_t)CAP);
+    if (raw > (uint32_t)CAP) S.overflow[slot] = 1;
+  }
+  // test records the unrolled pooling loop may touch past the end of a slot: span 0 never passes
+  for (int q = tid; q < nsl * WP_PAD; q += THREADS) {
+    const int sl = q / WP_PAD;
+    const uint32_t cnt = min(S.slab_pre[sl + 1] - S.slab_pre[sl], (uint32_t)CAP);
+    S.ta[((s0 + sl) % RING) * STRIDE + cnt + (q - sl * WP_PAD)] = make_uint2(0u, 0u);
+  }
+}
+
+// Phase B of k_pool_warp: every lane adds the records it queued to its ring accumulators.
+template <class SM>
+__device__ __forceinline__ void drain_queue(SM &S, int warp, int lane, int cnt, uint32_t tw) {
+  const int mx = __reduce_max_sync(0xffffffffu, cnt);
+  for (int e = 0; e < mx; e++) {
+    if (e < cnt) {
+      const uint32_t a = S.queue[warp][e][lane];
+      const uint32_t d = __vabsdiffu4(S.ta[a].x, tw);  // |dx| in byte 0, |dy| in byte 1
+      const float2 p = S.pb[a];
+      const uint32_t mch = max(d & 0xffu, (d >> 8) & 0xffu);
+      const uint32_t ring = ((mch + FARMS_WINDOW_JUMP - 1) * 205u) >> 10;  // /5 for values <= 54
+      float fl;
+      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(fl) : "f"(p.x * p.x + p.y * p.y));
+      float4 v = S.acc[warp][ring][lane];
+      v.x += fl;
+      v.y += p.x;
+      v.z += p.y;
+      v.w += 1.f;
+      S.acc[warp][ring][lane] = v;
+    }
+  }
+}
+
+template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND>
+__global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_warp(PoolArgs A, int otx_n, int oty_n, int nseg) {
+  using SM = WarpSmem<WARPS, CAP, NSL>;
+  constexpr int THREADS = WARPS * 32, RING = SM::RING, STRIDE = SM::STRIDE;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SM &S = *reinterpret_cast<SM *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane & 15;
+  const int W = A.g.W, H = A.g.H, nty = A.g.nty, NT = A.g.ntx * A.g.nty;
+  const unsigned int nitems = (unsigned int)otx_n * oty_n * nseg;
+  unsigned long long ncand = 0;
+  unsigned int npooled = 0;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) S.item = atomicAdd(A.work_counter, 1u);
+    if (tid < RING) S.tag[tid] = -1;
+    __syncthreads();
+    const unsigned int item = S.item;
+    if (item >= nitems) break;
+    // items are ordered segment-major so that CTAs running together work on the same time span (L2 reuse)
+    const int seg = item / (otx_n * oty_n), ot = item % (otx_n * oty_n);
+    const int TX = ot / oty_n, TY = ot % oty_n;
+    const int X0 = TX << OT_SHIFT, Y0 = TY << OT_SHIFT;
+    Region R;
+    R.rx0 = max(X0 - FARMS_MAX_WINDOW, 0);
+    R.rx1 = min(X0 + OT - 1 + FARMS_MAX_WINDOW, W - 1);                       // src/vFlow.cpp:998
+    R.ry0 = max(Y0 - FARMS_MAX_WINDOW, 0);
+    const int jmax = min(min(Y0 + OT - 1, H - 1) + FARMS_MAX_WINDOW, W - 1);  // :1000 (sic: width - 1)
+    R.ry1 = min(jmax, H - 1);
+    // logical rows j in [H, 2H) alias pixel (i + 1, j - H); rows >= 2H are left to k_pool_any
+    R.ay1 = min(jmax, 2 * H - 1) - H;
+    R.ax0 = R.rx0 + 1;
+    R.ax1 = min(R.rx1 + 1, W - 1);
+    if (R.ax0 > R.ax1) R.ay1 = -1;
+    // index tiles (16x16) of the owner tile: 2 columns x 2 rows, clipped
+    const int itx0 = X0 >> 4, itx1 = min((X0 + OT - 1) >> 4, A.g.ntx - 1);
+    const int ity0 = Y0 >> 4, ity1 = min((Y0 + OT - 1) >> 4, nty - 1);
+    const int d_begin = seg * TK_SEG, d_end = min(d_begin + TK_SEG, A.nslabs);
+
+    for (int d = d_begin; d < d_end; d += NSL) {
+      const int nd = min(NSL, d_end - d);
+      // ---- targets of this round: flow events of the owner tile in slabs d .. d+nd-1 ----
+      uint32_t ta_[NSL][2], tb_[NSL][2], nraw[NSL];
+      uint32_t nraw_all = 0, nmax = 0;
+#pragma unroll
+      for (int w = 0; w < NSL; w++) {
+        nraw[w] = 0;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          ta_[w][c] = tb_[w][c] = 0;
+          if (w < nd && itx0 + c <= itx1) {
+            const size_t cb = (size_t)(d + w) * NT + (size_t)(itx0 + c) * nty;
+            ta_[w][c] = A.cell_start[cb + ity0];
+            tb_[w][c] = A.cell_start[cb + ity1 + 1];
+          }
+          nraw[w] += tb_[w][c] - ta_[w][c];
+        }
+        nraw_all += nraw[w];
+        nmax = max(nmax, nraw[w]);
+      }
+      if (nraw_all == 0) continue;  // uniform across the CTA
+      if (SECOND) {  // only rounds the first pass flagged do any work here
+        const uint32_t bits = A.item_ovf[item];
+        const int b0 = (d - d_begin) >> TK_OVF_SHIFT, b1 = (d + nd - 1 - d_begin) >> TK_OVF_SHIFT;
+        if (((bits >> b0) & ((2u << (b1 - b0)) - 1u)) == 0u) continue;
+      }
+
+      // ---- make sure the slabs of all windows of the round are staged ----
+      __syncthreads();  // the previous round is done with S.dlo / S.dhi / S.ovf
+      if (tid < NSL) {
+        const int dd = min(d + tid, d_end - 1);
+        const uint32_t t_first = A.slab_ids[dd] << A.g.slab_shift;
+        const uint32_t lo_id =
+            (t_first >= (uint32_t)(FARMS_KILL_OLD_FLOW_TIME - 1) ? t_first - (FARMS_KILL_OLD_FLOW_TIME - 1) : 0u) >> A.g.slab_shift;
+        int l = dd;
+        while (l > 0 && dd - l < TK_LB && A.slab_ids[l - 1] >= lo_id) l--;
+        S.dlo[tid] = l;
+        S.dhi[tid] = dd;
+      }
+      const uint32_t i_round = A.slab_first[d];
+      __syncthreads();
+      int s_first = 0x7fffffff, s_last = -1;
+#pragma unroll
+      for (int w = 0; w < NSL; w++) {
+        if (nraw[w]) {
+          s_first = min(s_first, S.dlo[w]);
+          s_last = max(s_last, S.dhi[w]);
+        }
+      }
+      // staged slabs are a contiguous range ending at the last staged slab, so what is missing is a suffix
+      int s_new = s_first;
+      while (s_new <= s_last && S.tag[s_new % RING] == s_new) s_new++;  // uniform: tags are read after a barrier
+      if (s_new <= s_last) stage_slabs_packed<SM, WARPS, CAP, NSL>(A, S, s_new, s_last, R, i_round);
+      __syncthreads();
+      if (tid < NSL) {
+        int o = 0;
+        for (int s = S.dlo[tid]; s <= S.dhi[tid]; s++) o |= S.overflow[s % RING];
+        S.ovf[tid] = o;
+        if (!SECOND && o && nraw[tid]) atomicOr(&A.item_ovf[item], 1u << ((d + tid - d_begin) >> TK_OVF_SHIFT));
+      }
+
+      for (uint32_t t0 = 0; t0 < nmax; t0 += TK_MAXT) {
+        __syncthreads();
+        if (tid < NSL) S.ntg[tid] = 0;
+        if (tid == 0) S.tnext = 0;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < NSL; w++)
+          for (uint32_t f = t0 + tid; f < min(nraw[w], t0 + TK_MAXT); f += THREADS) {
+            const uint32_t n0 = tb_[w][0] - ta_[w][0];
+            const uint32_t pos = f < n0 ? ta_[w][0] + f : ta_[w][1] + (f - n0);
+            const uint4 r = A.rec[pos];
+            const int yi = (int)(r.x >> 16);
+            // fast-path conditions: not a halo event, window rows stay below 2H, staging complete
+            const bool ok = (int)r.z >= A.h && min(yi + FARMS_MAX_WINDOW, W - 1) <= 2 * H - 1 && !S.ovf[w] &&
+                            (!SECOND || !A.done[pos]);
+            if (ok) S.tlist[w][atomicAdd(&S.ntg[w], 1u)] = pos;
+          }
+        __syncthreads();
+        uint32_t tstart[NSL + 1];
+        tstart[0] = 0;
+#pragma unroll
+        for (int w = 0; w < NSL; w++) tstart[w + 1] = tstart[w] + S.ntg[w];
+        const uint32_t tasks = tstart[NSL];
+
+        // ---- one warp pools one event ----
+        for (;;) {
+          uint32_t k = 0;
+          if (lane == 0) k = atomicAdd(&S.tnext, 1u);
+          k = __shfl_sync(0xffffffffu, k, 0);
+          if (k >= tasks) break;
+          int w = 0;
+#pragma unroll
+          for (int q = 1; q < NSL; q++) w += (k >= tstart[q]) ? 1 : 0;
+          const uint32_t tpos = S.tlist[w][k - tstart[w]];
+          const uint4 r = A.rec[tpos];
+          const int xi = (int)(r.x & 0xffffu), yi = (int)(r.x >> 16);
+          const uint32_t ii = r.z;
+          // the event's window in region coordinates; staged records all lie inside the sensor and inside the
+          // reference's row bound (width - 1), so "in the window" is |dx| <= 50 and |dy| <= 50
+          const uint32_t tw = (uint32_t)(xi - R.rx0) | ((uint32_t)(yi - R.ry0) << 8);
+#pragma unroll
+          for (int q = 0; q < FARMS_NSCALES; q++) S.acc[warp][q][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int sl = S.dlo[w], sh = S.dhi[w];
+          int cnt = 0;
+          for (int s = sl; s <= sh; s++) {
+            const int slot = s % RING;
+            const int n = S.count[slot];
+            const uint32_t iir = ii - S.slot_base[slot];
+            ncand += (lane == 0) ? n : 0;
+            const uint2 *recs = &S.ta[slot * STRIDE];
+            for (int g0 = 0; g0 < n; g0 += 128) {
+              if (__any_sync(0xffffffffu, cnt > WQ_DEPTH - 4)) {  // rare: a lane's queue could overflow this trip
+                __syncwarp();
+                drain_queue(S, warp, lane, cnt, tw);
+                cnt = 0;
+              }
+              uint2 c[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++)  // the last trip reads into the zeroed padding (span 0)
+                c[u] = (g0 + 32 * u < n) ? recs[g0 + 32 * u + lane] : make_uint2(0u, 0u);
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const uint32_t d4 = __vabsdiffu4(c[u].x, tw);
+                const uint32_t rel = __funnelshift_r(c[u].x, c[u].y, 16) & 0x00ffffffu;
+                // still the latest event of its pixel AND younger than 500 us  <=>  idx <= ii < end
+                const bool ok = (iir - rel) < (c[u].y >> 8) && ((d4 + 0x4d4du) & 0x8080u) == 0u;
+                if (ok) {
+                  S.queue[warp][cnt][lane] = (uint16_t)(slot * STRIDE + g0 + 32 * u + lane);
+                  cnt++;
+                }
+              }
+            }
+          }
+          __syncwarp();
+          drain_queue(S, warp, lane, cnt, tw);
+          __syncwarp();
+          // lanes 0..10 and 11..21 each combine 16 of ring (lane % 11)'s 32 per-lane partials: four at a time in
+          // FP32, the group sums in FP64 (the counts are exact either way)
+          double rl = 0.0, rx = 0.0, ry = 0.0;
+          float rnf = 0.f;
+          if (lane < 2 * FARMS_NSCALES) {
+            const int rg = lane < FARMS_NSCALES ? lane : lane - FARMS_NSCALES, hb = lane < FARMS_NSCALES ? 0 : 16;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; q4++) {
+              float4 g = S.acc[warp][rg][hb | ((4 * q4 + rg) & 15)];
+#pragma unroll
+              for (int q = 1; q < 4; q++) {
+                const float4 v = S.acc[warp][rg][hb | ((4 * q4 + q + rg) & 15)];
+                g.x += v.x;
+                g.y += v.y;
+                g.z += v.z;
+                g.w += v.w;
+              }
+              rl += (double)g.x;
+              rx += (double)g.y;
+              ry += (double)g.z;
+              rnf += g.w;
+            }
+          }
+          __syncwarp();
+          {
+            const double ol = __shfl_down_sync(0xffffffffu, rl, FARMS_NSCALES), ox = __shfl_down_sync(0xffffffffu, rx, FARMS_NSCALES),
+                         oy = __shfl_down_sync(0xffffffffu, ry, FARMS_NSCALES);
+            const float on = __shfl_down_sync(0xffffffffu, rnf, FARMS_NSCALES);
+            if (lane < FARMS_NSCALES) {
+              rl += ol;
+              rx += ox;
+              ry += oy;
+              rnf += on;
+            } else {
+              rl = rx = ry = 0.0;
+              rnf = 0.f;
+            }
+          }
+          const bool lower = lane < 16;
+          const bool fin = finish_event_checked(A, sub, rl, rx, ry, (int)rnf, (int)ii - A.h, lower);
+          const bool fin0 = __shfl_sync(0xffffffffu, fin, 0);
+          if (lane == 0 && fin0) {
+            A.done[tpos] = 1;
+            npooled++;
+          }
+          if (!fin0) {
+            // ---- undecided (a rival scale within the FP32 noise, cancelling vectors): pool it again exactly, FP64
+            // partials and the FP64 flow values of the contributors (lanes 0..15; the FP64 partials of one target
+            // take the warp's whole accumulator space) ----
+            __syncwarp();
+            double4 *dacc = reinterpret_cast<double4 *>(&S.acc[warp][0][0]);  // [ring][16 lanes] {len, lcx, lcy, n}
+            if (lower) {
+#pragma unroll
+              for (int q = 0; q < FARMS_NSCALES; q++) dacc[q * 16 + sub] = make_double4(0.0, 0.0, 0.0, 0.0);
+              for (int s = sl; s <= sh; s++) {
+                const int slot = s % RING;
+                const int n = S.count[slot];
+                const uint32_t base = S.slot_base[slot], iir = ii - base;
+                for (int q0 = sub; q0 < n; q0 += 16) {
+                  const uint2 c = S.ta[slot * STRIDE + q0];
+                  const uint32_t d4 = __vabsdiffu4(c.x, tw);
+                  const uint32_t rel = __funnelshift_r(c.x, c.y, 16) & 0x00ffffffu;
+                  const bool ok = (iir - rel) < (c.y >> 8) && ((d4 + 0x4d4du) & 0x8080u) == 0u;
+                  if (ok) {
+                    const uint32_t mch = max(d4 & 0xffu, (d4 >> 8) & 0xffu);
+                    const int ring = (int)(((mch + FARMS_WINDOW_JUMP - 1) * 205u) >> 10);
+                    const uint32_t j = base + rel;
+                    double4 v = dacc[ring * 16 + sub];
+                    v.x += A.ev_len[j];
+                    v.y += A.ev_lcx[j];
+                    v.z += A.ev_lcy[j];
+                    v.w += 1.0;
+                    dacc[ring * 16 + sub] = v;
+                  }
+                }
+              }
+            }
+            __syncwarp();
+            double el = 0.0, ex2 = 0.0, ey2 = 0.0, en = 0.0;
+            if (lower && sub < FARMS_NSCALES) {
+#pragma unroll 4
+              for (int q = 0; q < 16; q++) {
+                const double4 v = dacc[sub * 16 + ((q + sub) & 15)];
+                el += v.x;
+                ex2 += v.y;
+                ey2 += v.z;
+                en += v.w;
+              }
+            }
+            __syncwarp();
+            finish_event<16>(A, sub, el, ex2, ey2, en, A.ev_lcx[ii], A.ev_lcy[ii], (int)ii - A.h, lower);
+            if (lane == 0) {
+              A.done[tpos] = 1;
+              npooled++;
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0 && ncand) atomicAdd(A.cand_count, ncand);
+  if (lane == 0 && npooled) atomicAdd(A.path_count + (SECOND ? 1 : 0), (unsigned long long)npooled);
+}
+
+template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND>
+void launch_warp(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
+  PoolArgs A = A0;
+  using SM = WarpSmem<WARPS, CAP, NSL>;
+  static_assert(sizeof(SM) <= (CTAS == 2 ? 115712 : 232448), "shared memory of the warp kernel: 227 KB per CTA, 228 KB per SM");
+  static_assert(SM::RING * SM::STRIDE <= 65536, "queue entries are 16-bit slot addresses");
+  auto kern = k_pool_warp<WARPS, CAP, NSL, CTAS, SECOND>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  const int otx = (A.g.W + OT - 1) >> OT_SHIFT, oty = (A.g.H + OT - 1) >> OT_SHIFT;
+  const int nseg = (nslabs + TK_SEG - 1) / TK_SEG;
+  const long long items = (long long)otx * oty * nseg;
+  unsigned grid = (unsigned)std::min<long long>(items, (long long)num_sms * CTAS);
+  kern<<<grid, WARPS * 32, sizeof(SM), s>>>(A, otx, oty, nseg);
+}
+
+// ------------------------------------------------------------------------------------------------
 // fast path, bit-parallel: prefix bitmask tables over the staged records
 // ------------------------------------------------------------------------------------------------
 // A CTA owns a 32x32 owner tile and advances through its time slabs in rounds.  Per round it stages the flow
@@ -1496,6 +2017,20 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
     } else if (fast == 3) {
       launch_tile<16, 768, 4, 1, false>(A, nslabs, num_sms, s);  // 16 warps, 1 CTA per SM, ~222 KB
       if (kernels_used) *kernels_used |= FARMS_POOLK_TILE_ONE_CTA;
+    } else if (fast == 4) {
+      // two-phase kernel (k_pool_warp), same dense / sparse split and flagged second pass
+      const double per_region = flow_per_slab * 17424.0 / ((double)g.W * (double)g.H);
+      if (per_region < 200.0) {
+        launch_warp<8, 352, 4, 2, false>(A, nslabs, num_sms, s);
+        if (kernels_used) *kernels_used |= FARMS_POOLK_WARP_SPARSE;
+      } else {
+        launch_warp<8, 480, 2, 2, false>(A, nslabs, num_sms, s);
+        if (kernels_used) *kernels_used |= FARMS_POOLK_WARP_DENSE;
+      }
+      A.work_counter = work_counter + 2;
+      launch_warp<16, 768, 4, 1, true>(A, nslabs, num_sms, s);
+      if (kernels_used) *kernels_used |= FARMS_POOLK_WARP_SECOND;
+      launches++;
     } else {
       // flow events a slab holds inside one (32+100)^2 region, from the batch average
       const double per_region = flow_per_slab * 17424.0 / ((double)g.W * (double)g.H);

@@ -12,18 +12,23 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FARMS_B200_LIB", os.path.join(_HERE, "libfarms_b200.so"))
 
-OK, ERR_ARG, ERR_RANGE, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4, -5
+OK, ERR_ARG, ERR_RANGE, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_COMM = 0, -1, -2, -3, -4, -5, -6
+COMM_ID_BYTES = 128
+COMM_LOCAL = 1
+IO_INPUT_ON_DEVICE, IO_OUTPUT_ON_DEVICE = 1, 2
 FLAG_DEBUG_DET = 1
 FLAG_EXACT_POOLING = 2
 FLAG_GENERIC_POOLING = FLAG_EXACT_POOLING
 POOLK_TILE_DENSE, POOLK_TILE_SPARSE, POOLK_TILE_SECOND, POOLK_TILE_ONE_CTA, POOLK_BITS, POOLK_ANY = 1, 2, 4, 8, 16, 32
-POOL_VARIANTS = {"tile": 1, "bits": 2, "tile1": 3}
+POOLK_WARP_DENSE, POOLK_WARP_SPARSE, POOLK_WARP_SECOND = 64, 128, 256
+POOL_VARIANTS = {"tile": 1, "bits": 2, "tile1": 3, "warp": 4}
 
 EXPORTS = [
     "farms_abi_version", "farms_create", "farms_destroy", "farms_reset", "farms_last_error", "farms_normalize_filtersize", "farms_get_params",
     "farms_process_host", "farms_process_device", "farms_num_events", "farms_get_timings", "farms_set_t0",
     "farms_state_export", "farms_state_fold", "farms_slice_surface", "farms_pack4_f32",
     "farms_slice_surface_host", "farms_state_fold_host",
+    "farms_comm_unique_id", "farms_comm_create", "farms_comm_destroy", "farms_comm_info", "farms_comm_process",
 ]
 
 
@@ -42,6 +47,10 @@ class Out(C.Structure):
 OUT_DTYPES = {"t_rel": np.uint32, "global_r": np.float64, "global_theta": np.float64, "vx": np.float64,
               "vy": np.float64, "local_r": np.float64, "local_theta": np.float64, "scale": np.uint8,
               "valid": np.uint8, "best_window": np.int8, "inliers": np.uint16, "det": np.float64}
+
+
+class Gather(C.Structure):
+    _fields_ = [("root", C.c_int32), ("dst", C.c_void_p), ("counts", C.c_void_p)]
 
 
 class Timings(C.Structure):
@@ -87,6 +96,13 @@ def lib():
         L.farms_slice_surface.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                                           C.c_void_p, C.c_void_p]
         L.farms_pack4_f32.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_void_p]
+        L.farms_comm_unique_id.argtypes = [C.c_void_p]
+        L.farms_comm_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint32]
+        L.farms_comm_destroy.argtypes = [C.c_void_p]
+        L.farms_comm_destroy.restype = None
+        L.farms_comm_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 3
+        L.farms_comm_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                         C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(Out), C.POINTER(Gather)]
         _lib = L
     return _lib
 
@@ -195,3 +211,66 @@ class Farms:
         """a..d: f64 CUDA tensors of n entries; out4: float32 CUDA tensor of shape (>= n, 4)."""
         self._check(lib().farms_pack4_f32(self._h, a.data_ptr(), b.data_ptr(), c.data_ptr(), d.data_ptr(), a.numel(),
                                           out4.data_ptr()))
+
+
+def comm_unique_id():
+    """128 bytes identifying a new group (rank 0 makes them, every rank gets a copy)."""
+    buf = (C.c_ubyte * COMM_ID_BYTES)()
+    rc = lib().farms_comm_unique_id(buf)
+    if rc != OK:
+        raise FarmsError(rc, "farms_comm_unique_id: NCCL is not available")
+    return bytes(buf)
+
+
+class Comm:
+    """farms_comm: the time-sliced multi-GPU run of include/farms_b200.h on top of one Farms context per rank."""
+
+    def __init__(self, farms, nranks, rank, unique_id, local=False):
+        self.farms, self.nranks, self.rank = farms, nranks, rank
+        self._h = C.c_void_p()
+        idbuf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(bytes(unique_id).ljust(COMM_ID_BYTES, b"\0"))
+        rc = lib().farms_comm_create(C.byref(self._h), farms._h, nranks, rank, idbuf, COMM_LOCAL if local else 0)
+        if rc != OK:
+            raise FarmsError(rc, "farms_comm_create: " + lib().farms_last_error(farms._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().farms_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def transport(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        lib().farms_comm_info(self._h, C.byref(a), C.byref(b), C.byref(c))
+        return {0: "none", 1: "nccl", 2: "local"}[c.value]
+
+    def process(self, x, y, t, n_halo, n_surface, t0, out=None, gather_dst=None, root=0, device=False):
+        """One collective time-sliced pass.  x, y, t: this rank's slice including its halo -- numpy arrays
+        (device=False) or torch CUDA tensors (device=True).  out: dict of columns (numpy / CUDA tensors) for the
+        owned events, or None.  gather_dst: float32 CUDA tensor (total owned events, 4) on the root, or None for no
+        gather (ranks other than the root pass any non-None placeholder to take part).  Returns the per-rank counts."""
+        if device:
+            n = x.numel()
+            px, py, pt = x.data_ptr(), y.data_ptr(), t.data_ptr()
+        else:
+            x = np.ascontiguousarray(x, dtype=np.uint16)
+            y = np.ascontiguousarray(y, dtype=np.uint16)
+            t = np.ascontiguousarray(t, dtype=np.uint64)
+            n = len(x)
+            px, py, pt = x.ctypes.data, y.ctypes.data, t.ctypes.data
+        o = Out()
+        flags = IO_INPUT_ON_DEVICE if device else 0
+        if out is not None:
+            dev_out = any(hasattr(v, "data_ptr") for v in out.values())
+            flags |= IO_OUTPUT_ON_DEVICE if dev_out else 0
+            for k, v in out.items():
+                setattr(o, k, v.data_ptr() if hasattr(v, "data_ptr") else v.ctypes.data)
+        counts = np.zeros(self.nranks, np.uint64)
+        g = None
+        if gather_dst is not None:
+            g = Gather(root=root, dst=gather_dst.data_ptr() if self.rank == root else None, counts=counts.ctypes.data)
+        rc = lib().farms_comm_process(self._h, px, py, pt, n, int(n_halo), int(n_surface), int(t0), flags,
+                                      C.byref(o) if out is not None else None, C.byref(g) if g is not None else None)
+        self.farms._check(rc)
+        return counts

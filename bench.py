@@ -7,10 +7,12 @@
 A "step" is one pass of the hot path (ingest -> history index -> plane fit -> pooling) over one synthetic
 event stream of the BASELINE config the metric is quoted on: 1280x720, filtersize 5, 200 M events
 (configs[3]; deterministic generator tools/farms_synth.cpp).  `value` is measured with the stream already
-resident in HBM; `e2e` is the same pass through farms_process_host with pinned HOST buffers, host<->device
-copies inside the timed region.  N > 1: the stream is time-sliced, one slice of the same length per GPU
-(weak scaling), each rank rebuilding the surface of active events at its slice start from an NCCL
-all-gather of per-slice "last event per pixel" surfaces, plus a 499-us causal halo for pooling.
+resident in HBM; `e2e` is the same pass through the C ABI with pinned HOST buffers, host<->device copies inside
+the timed region.  N > 1: the stream is time-sliced, one slice per GPU, through farms_comm_process
+(include/farms_b200.h, csrc/comm.cu): NCCL all-gather of per-slice "last event per pixel" surfaces, a 499-us causal
+halo for pooling, and the contract columns of every rank gathered on rank 0 batch by batch (ncclSend/ncclRecv under
+the next batch's kernels).  --scaling weak (default): --events per GPU; --scaling strong: --events in total
+(configs[4] = 1 B events: `--scaling strong --events 1000000000`).
 """
 import argparse
 import json
@@ -33,7 +35,10 @@ UNIT = "Mevents/s"
 HALO_US = 499                 # pooling admits |dt| < 500 us (reference src/vFlow.cpp:1002)
 B_ALG_POOL = 54               # algorithmic HBM bytes per event of the pooling kernel
 B_ALG_FIT = 35                # ... of the plane-fit kernel (K3)
-E2E_COLUMNS = ["t_rel", "global_r", "global_theta", "vx", "vy", "local_r", "local_theta", "scale", "valid"]
+# device-resident outputs of the timed pass: every column of the reference's 11-column row (src/vFlow.cpp:438)
+DEV_COLUMNS = ["t_rel", "global_r", "global_theta", "vx", "vy", "local_r", "local_theta", "scale", "valid"]
+# end-to-end pass: the README's 8-column contract (x y t p are echoes that stay with the caller) + the valid flag
+E2E_COLUMNS = ["t_rel", "global_r", "global_theta", "local_r", "local_theta", "valid"]
 
 
 def measured_peak():
@@ -119,17 +124,58 @@ def reference_rate(sample_xytp, width, height, filtersize, tag):
         return n / sec, sec, "port"
 
 
+def bind_to_gpu_numa_node(dev_index):
+    """Run this rank (and so its pinned allocations, first-touch) on the CPUs of the GPU's NUMA node."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(dev_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(dev_index).pci_domain_id
+        devid = torch.cuda.get_device_properties(dev_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/numa_node"
+        node = int(open(path).read())
+        if node < 0:
+            return {"numa_node": node, "bound": False}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "bound": bool(allowed), "cpus": len(allowed)}
+    except Exception as e:  # no sysfs entry (virtualised box): leave the affinity alone
+        return {"numa_node": None, "bound": False, "why": str(e)[:80]}
+
+
+def roofline_kernels(peak):
+    """Per-kernel DRAM GB/s against the measured HBM peak, from the committed ncu launch list of this build
+    (profiles/kernels.json, written by tools/summarize_profiles.py from `ncu --metrics gpu__time_duration.sum,
+    dram__bytes_*`): cold-cache, serialised launches -- compare shares and fractions, not absolute times."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernels.json")) as fh:
+            k = json.load(fh)
+        return {"source": k.get("source"), "peak_gbs": peak,
+                "kernels": [{"kernel": e["kernel"], "share_of_step": e["share"], "dram_gbs": e["gbs"],
+                             "frac_of_hbm_peak": e["gbs"] / peak} for e in k["kernels"]]}
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--events", type=int, default=200_000_000, help="events per GPU per step")
+    ap.add_argument("--events", type=int, default=200_000_000, help="events per GPU (weak) or in total (strong) per step")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--config", type=int, default=4)
     ap.add_argument("--cpu-sample", type=int, default=450_000, help="events of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip exact-pooling / other-config / sliced-parity extras")
+    ap.add_argument("--parity-events", type=int, default=2_000_000)
+    ap.add_argument("--pool-variant", default="", help="A/B runs: tile | bits | tile1 | warp (default: the library's choice)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -138,8 +184,11 @@ def main():
     from farms_synth import Synth
     syn = Synth(args.config)
     W, H, FS = syn.width, syn.height, syn.filtersize
-    workload = (f"configs[{args.config - 1}]: synthetic {'high-rate pan' if args.config >= 4 else 'scene'} {W}x{H}, "
-                f"{args.events} events per GPU, filtersize {FS}, inlierCheck 5")
+    per_gpu = args.events if args.scaling == "weak" else args.events // max(world, 1)
+    cfg_name = f"configs[{args.config - 1}]" if not (args.scaling == "strong" and args.events >= 1_000_000_000) else "configs[4]"
+    workload = (f"{cfg_name}: synthetic {'high-rate pan' if args.config >= 4 else 'scene'} {W}x{H}, "
+                + (f"{args.events} events per GPU" if args.scaling == "weak" else f"{args.events} events in total")
+                + f", filtersize {FS}, inlierCheck 5")
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -156,7 +205,7 @@ def main():
         value = args.cpu_sample * len(rates) / total_sec / 1e6
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_sec / len(rates),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "timer": "reference's own loop timer (src/vFlow.cpp:214-423)"},
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
                                  "sample": f"first {args.cpu_sample} events of the workload stream per step "
@@ -172,98 +221,55 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    # this rank's time slice (stream microseconds), with the causal halo in front (slicing.py)
+    def new_comm(farms):
+        """farms_comm over the ranks of this job: rank 0 makes the NCCL id, torch.distributed only carries it."""
+        if world == 1:
+            return farms_b200.Comm(farms, 1, 0, b"")
+        idt = torch.zeros(farms_b200.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(farms_b200.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        return farms_b200.Comm(farms, world, rank, bytes(idt.cpu().numpy().tobytes()))
+
     import slicing
-    D = int(args.events / syn.rate * 1e6)
-    plan = slicing.slice_plan(rank, world, D, HALO_US)
-    tg0 = time.time()
-    x, y, t, p = syn.time_range(plan.t_lo, plan.t_end, pinned=True)
-    gen_s = time.time() - tg0
-    n_all = len(x)
-    # outputs of [0, n_halo) are discarded; [0, n_surf) is this rank's share of the SAE exchange
-    n_halo, n_surf = slicing.split_counts(t.astype(np.int64) - 1000, plan)
-    n_owned = n_all - n_halo
-    # global t0 = first timestamp of the whole stream (reference src/vFlow.cpp:194)
-    t0_t = torch.tensor([int(t[0]) if rank == 0 else 0], dtype=torch.int64, device=dev)
-    if dist:
-        dist.broadcast(t0_t, 0)
-    t0 = int(t0_t.item())
-
-    hx, hy = torch.from_numpy(x), torch.from_numpy(y)
-    ht = torch.from_numpy(t.view(np.int64))
-    dx, dy, dt = hx.to(dev), hy.to(dev), ht.to(dev)
-    npx = W * H
-    f = farms_b200.Farms(W, H, FS, 5, device=local_rank)
-    surf_t = torch.zeros(npx, dtype=torch.int32, device=dev)
-    surf_hit = torch.zeros(npx, dtype=torch.uint8, device=dev)
-    all_t = torch.zeros(world * npx, dtype=torch.int32, device=dev) if dist else None
-    all_hit = torch.zeros(world * npx, dtype=torch.uint8, device=dev) if dist else None
     tdt = {np.uint32: torch.int32, np.float64: torch.float64, np.uint8: torch.uint8}
-    dev_out = {k: torch.empty(n_all, dtype=tdt[farms_b200.OUT_DTYPES[k]], device=dev) for k in E2E_COLUMNS}
-    host_out = None
 
-    def exchange_state():
-        """SAE at this rank's halo start = fold of earlier ranks' 'last event per pixel' surfaces."""
-        f.set_t0(t0)
-        if not dist:
-            return
-        f.slice_surface(dx[:n_surf], dy[:n_surf], dt[:n_surf], t0, surf_t, surf_hit)
-        dist.all_gather_into_tensor(all_t, surf_t)
-        dist.all_gather_into_tensor(all_hit, surf_hit)
-        for r in range(rank):
-            f.state_fold(all_t[r * npx:(r + 1) * npx], all_hit[r * npx:(r + 1) * npx])
+    class Slice:
+        """This rank's time slice of a stream of `span_us` microseconds cut `world` ways (+ causal halo)."""
 
-    # final NCCL gather of the owned events' outputs to rank 0 (float4 per event); slices differ by a few
-    # events, so every rank sends n_max rows and rank 0 keeps the first sizes[r]
-    if dist:
-        sz = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(sz, torch.tensor([n_owned], dtype=torch.int64, device=dev))
-        sizes = [int(q.item()) for q in sz]
-        n_max = max(sizes)
-        packed = torch.zeros((n_max, 4), dtype=torch.float32, device=dev)
-        gathered = [torch.empty((n_max, 4), dtype=torch.float32, device=dev) for _ in range(world)] if rank == 0 else None
+        def __init__(self, synth, span_us, pinned):
+            D = -(-span_us // world)
+            self.D = D
+            plan = slicing.slice_plan(rank, world, D, HALO_US)
+            tg = time.time()
+            self.x, self.y, self.t, self.p = synth.time_range(plan.t_lo, min(plan.t_end, span_us), pinned=pinned)
+            self.gen_s = time.time() - tg
+            self.n = len(self.x)
+            self.n_halo, self.n_surf = slicing.split_counts(self.t.astype(np.int64) - 1000, plan)
+            if rank == world - 1:
+                self.n_surf = 0
+            self.n_owned = self.n - self.n_halo
+            t0_t = torch.tensor([int(self.t[0]) if rank == 0 else 0], dtype=torch.int64, device=dev)
+            if dist:
+                dist.broadcast(t0_t, 0)
+            self.t0 = int(t0_t.item())
 
-    def gather_outputs(cols):
-        if not dist:
-            return
-        f.pack4_f32(cols["global_r"][n_halo:], cols["global_theta"][n_halo:], cols["local_r"][n_halo:],
-                    cols["local_theta"][n_halo:], packed)
-        dist.gather(packed, gathered, dst=0)
+        def to_device(self):
+            self.dx = torch.from_numpy(self.x).to(dev)
+            self.dy = torch.from_numpy(self.y).to(dev)
+            self.dt = torch.from_numpy(self.t.view(np.int64)).to(dev)
 
-    launches = [0]
-    stage = {}
-
-    sect = {"exchange_s": 0.0, "process_s": 0.0, "gather_s": 0.0}
-
-    def step_device():
-        f.reset()
-        ta = time.perf_counter()
-        exchange_state()
-        torch.cuda.synchronize()
-        tb = time.perf_counter()
-        f.process_device(dx, dy, dt, columns=E2E_COLUMNS, out=dev_out)
-        tc = time.perf_counter()
-        sect["exchange_s"] += tb - ta
-        sect["process_s"] += tc - tb
-        tm = f.timings()
-        launches[0] += tm["kernel_launches"] + (3 + rank if dist else 0)
-        for k, v in tm.items():
-            stage[k] = stage.get(k, 0) + v
-        td = time.perf_counter()
-        gather_outputs(dev_out)
-        torch.cuda.synchronize()
-        sect["gather_s"] += time.perf_counter() - td
-
-    def step_host():
-        f.reset()
-        exchange_state()
-        # every rank's results land in pinned host memory of this node: nothing left to gather
-        f.process(x, y, t, columns=E2E_COLUMNS, out=host_out)
+    def all_counts(n_owned):
+        tot = torch.tensor([n_owned], dtype=torch.int64, device=dev)
+        if dist:
+            dist.all_reduce(tot)
+        return int(tot.item())
 
     def barrier():
         if dist:
@@ -280,7 +286,7 @@ def main():
         e1.record()
         barrier()
         wall = time.perf_counter() - w0
-        # the library works on its own stream and synchronises it before returning, so wall clock between two
+        # the library works on its own streams and synchronises them before returning, so wall clock between two
         # full synchronisations is the device-inclusive time; CUDA events on torch's stream bracket the same span
         dev_ms = e0.elapsed_time(e1)
         tmax = torch.tensor([max(wall, dev_ms * 1e-3)], dtype=torch.float64, device=dev)
@@ -288,42 +294,148 @@ def main():
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         return float(tmax.item())
 
+    # ---------------------------------------------------------------- sliced parity (N > 1), before any timing
+    sliced_parity = None
+    if world > 1 and not args.no_extras:
+        span = int(args.parity_events / syn.rate * 1e6)
+        sl = Slice(syn, span, pinned=False)
+        sl.to_device()
+        fp = farms_b200.Farms(W, H, FS, 5, device=local_rank)
+        cmp_ = new_comm(fp)
+        total = all_counts(sl.n_owned)
+        gathered = torch.zeros((total, 4), dtype=torch.float32, device=dev) if rank == 0 else torch.zeros(1, device=dev)
+        counts = cmp_.process(sl.dx, sl.dy, sl.dt, sl.n_halo, sl.n_surf, sl.t0, out=None, gather_dst=gathered, device=True)
+        barrier()
+        if rank == 0:
+            # the same events in one piece on this GPU alone
+            x1, y1, t1, _ = syn.time_range(0, span)
+            f1 = farms_b200.Farms(W, H, FS, 5, device=local_rank)
+            one = f1.process(x1, y1, t1, columns=["global_r", "global_theta", "local_r", "local_theta", "valid"])
+            g = gathered.cpu().numpy().astype(np.float64)
+            ok_n = len(x1) == total == int(counts.sum())
+            bad = np.zeros(min(len(x1), total), bool)
+            maxrel = 0.0
+            if ok_n:
+                for j, k in enumerate(["global_r", "global_theta", "local_r", "local_theta"]):
+                    a, b = g[:, j], one[k]
+                    if k.endswith("_r"):
+                        with np.errstate(invalid="ignore", divide="ignore"):
+                            rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+                        rel[b == 0] = np.abs(a[b == 0])
+                        bad |= rel > 1e-4
+                        maxrel = max(maxrel, float(rel.max()))
+                    else:
+                        d = np.abs(a - b) % (2 * np.pi)
+                        bad |= np.minimum(d, 2 * np.pi - d) > 1e-3
+            sliced_parity = {"events": int(total), "single_gpu_events": int(len(x1)), "mismatches": int(bad.sum()) if ok_n else -1,
+                             "max_rel_r": maxrel, "valid": int(one["valid"].sum()), "slices": world,
+                             "tolerance": "R 1e-4 relative, theta 1e-3 rad (float4 transport)", "transport": cmp_.transport()}
+            f1.close()
+        cmp_.close()
+        fp.close()
+        del gathered, sl
+        barrier()
+
+    # ---------------------------------------------------------------- the workload
+    span_us = int(args.events / syn.rate * 1e6) * (world if args.scaling == "weak" else 1)
+    sl = Slice(syn, span_us, pinned=True)
+    sl.to_device()
+    n_all, n_owned = sl.n, sl.n_owned
+    total_events = all_counts(n_owned)
+    f = farms_b200.Farms(W, H, FS, 5, device=local_rank, pool_variant=args.pool_variant or 0)
+    cm = new_comm(f)
+    dev_out = {k: torch.empty(n_owned, dtype=tdt[farms_b200.OUT_DTYPES[k]], device=dev) for k in DEV_COLUMNS}
+    gathered = torch.empty((total_events, 4), dtype=torch.float32, device=dev) if rank == 0 else torch.zeros(1, device=dev)
+    host_out = None
+    launches = [0]
+    stage = {}
+
+    def step_device():
+        f.reset()
+        cm.process(sl.dx, sl.dy, sl.dt, sl.n_halo, sl.n_surf, sl.t0, out=dev_out, gather_dst=gathered, device=True)
+        tm = f.timings()
+        launches[0] += tm["kernel_launches"] + (2 + rank if dist else 0)
+        for k, v in tm.items():
+            stage[k] = stage.get(k, 0) + v
+
+    def step_host():
+        f.reset()
+        # every rank's results land in pinned host memory of this node
+        cm.process(sl.x, sl.y, sl.t, sl.n_halo, sl.n_surf, sl.t0, out=host_out, gather_dst=None, device=False)
+
     for _ in range(args.warmup):
         step_device()
     launches[0] = 0
     stage.clear()
-    for k in sect:
-        sect[k] = 0.0
     sampler = ClockSampler(local_rank)
     sampler.start()
     sec = timed(step_device, args.steps)
     clocks = sampler.stop()
     launches_per_run = launches[0]
     stage_avg = {k: v / args.steps for k, v in stage.items()}
-
-    tot = torch.tensor([n_owned], dtype=torch.int64, device=dev)
-    if dist:
-        dist.all_reduce(tot)
-    total_events = int(tot.item())
     value = total_events * args.steps / sec / 1e6
 
     e2e = None
     if not args.no_e2e:
         host_out = {}
         for k in E2E_COLUMNS:
-            buf = torch.empty(n_all, dtype=tdt[farms_b200.OUT_DTYPES[k]]).pin_memory()
+            buf = torch.empty(n_owned, dtype=tdt[farms_b200.OUT_DTYPES[k]]).pin_memory()
             a = buf.numpy()
             host_out[k] = a.view(np.uint32) if farms_b200.OUT_DTYPES[k] is np.uint32 else a
         for _ in range(args.warmup):
             step_host()
         sec_h = timed(step_host, args.steps)
         h2d = n_all * (2 + 2 + 8)
-        d2h = n_all * sum(np.dtype(farms_b200.OUT_DTYPES[k]).itemsize for k in E2E_COLUMNS)
+        d2h = n_owned * sum(np.dtype(farms_b200.OUT_DTYPES[k]).itemsize for k in E2E_COLUMNS)
         e2e = {"value": total_events * args.steps / sec_h / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * sec_h / args.steps,
-               "api": "farms_process_host (pinned host SoA in, pinned host columns out)"}
+               "pcie_gbs_this_rank": (h2d + d2h) * args.steps / sec_h / 1e9, "numa": numa,
+               "columns": E2E_COLUMNS,
+               "api": ("farms_comm_process" if world > 1 else "farms_process_host") +
+                      " (pinned host SoA in, pinned host columns out: the README's 8-column contract)"}
+
+    # ---------------------------------------------------------------- extras on rank 0 (not part of `value`)
+    extras = {}
+    if rank == 0 and not args.no_extras and world == 1:
+        nx = min(20_000_000, n_all)
+        fx = farms_b200.Farms(W, H, FS, 5, device=local_rank, flags=farms_b200.FLAG_EXACT_POOLING)
+        cols = {k: dev_out[k][:nx] for k in DEV_COLUMNS}
+        fx.process_device(sl.dx[:nx], sl.dy[:nx], sl.dt[:nx], columns=DEV_COLUMNS, out=cols)
+        torch.cuda.synchronize()
+        ta = time.perf_counter()
+        fx.reset()
+        fx.process_device(sl.dx[:nx], sl.dy[:nx], sl.dt[:nx], columns=DEV_COLUMNS, out=cols)
+        torch.cuda.synchronize()
+        extras["exact_pooling"] = {"value": nx / (time.perf_counter() - ta) / 1e6, "unit": UNIT, "events": nx,
+                                   "what": "FARMS_FLAG_EXACT_POOLING (FP64 sums for every event; the FARMS_Flow text "
+                                           "mode's default), device-resident, one pass"}
+        fx.close()
+        other = []
+        for cfg_i, n_i in ((1, 100_000), (2, 5_000_000), (3, 20_000_000)):
+            si = Synth(cfg_i)
+            xi, yi, ti, _ = si.first(n_i)
+            dxi, dyi = torch.from_numpy(xi.copy()).to(dev), torch.from_numpy(yi.copy()).to(dev)
+            dti = torch.from_numpy(ti.copy().view(np.int64)).to(dev)
+            fi = farms_b200.Farms(si.width, si.height, si.filtersize, 5, device=local_rank)
+            oi = {k: torch.empty(n_i, dtype=tdt[farms_b200.OUT_DTYPES[k]], device=dev) for k in DEV_COLUMNS}
+            best = None
+            for it in range(4):
+                fi.reset()
+                torch.cuda.synchronize()
+                ta = time.perf_counter()
+                fi.process_device(dxi, dyi, dti, columns=DEV_COLUMNS, out=oi)
+                torch.cuda.synchronize()
+                dtm = time.perf_counter() - ta
+                if it:
+                    best = dtm if best is None else min(best, dtm)
+            other.append({"config": f"configs[{cfg_i - 1}]", "sensor": f"{si.width}x{si.height}", "filtersize": si.filtersize,
+                          "events": n_i, "value": n_i / best / 1e6, "unit": UNIT, "ms": 1e3 * best,
+                          "valid_events": int(fi.timings()["valid_events"])})
+            fi.close()
+        extras["other_configs"] = other
 
     if rank != 0:
+        cm.close()
         if dist:
             dist.destroy_process_group()
         return 0
@@ -352,7 +464,7 @@ def main():
                 "note": "shared-memory/issue-bound gather kernel: HBM is <1% utilised by construction, see DESIGN.md"}
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         sample = syn.first(args.cpu_sample)
         r, s_sec, kind = reference_rate(sample, W, H, FS, "cpu")
         cpu_baseline = {"value": r / 1e6, "unit": UNIT, "cores": 1, "kind": kind, "seconds": s_sec,
@@ -362,18 +474,33 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f64 plane fit and scale decisions; pooling sums f32 ring partials combined in f64 (exact f64 re-pool when undecided)",
+            "data": "synthetic",
             "config": {"workload": workload, "events_per_step_total": total_events, "l2": "inputs_larger_than_l2",
-                       "slicing": f"time slices of {D} us per GPU + {HALO_US} us causal halo" if world > 1 else "none",
-                       "generator_s": gen_s},
+                       "slicing": f"time slices of {sl.D} us per GPU + {HALO_US} us causal halo (farms_comm_process, "
+                                  f"transport {cm.transport()})" if world > 1 else "none",
+                       "generator_s": sl.gen_s,
+                       "value_starts_from": "x/y/t resident in HBM (SURVEY 8(d) counts from pinned host memory: that is `e2e`)",
+                       "delivered": "all 11-column outputs on the owning GPU (f64) + float4 contract columns of every "
+                                    "rank gathered on rank 0"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_run),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "stages_ms_per_step": {k: stage_avg[k] for k in ("total_ms", "ingest_ms", "index_ms", "fit_ms", "bin_ms",
                                                               "pool_ms") if k in stage_avg},
-            "rank0_sections_ms_per_step": {k: 1e3 * v / args.steps for k, v in sect.items()},
+            "pool_paths_events_per_step": {k: int(stage_avg.get(k, 0)) for k in ("pool_events_first", "pool_events_second",
+                                                                                 "pool_events_general")},
+            "pool_kernels": int(f.timings()["pool_kernels"]),
             "valid_events_per_step": int(stage_avg.get("valid_events", 0)),
             "pool_candidates_per_step": int(stage_avg.get("pool_candidates", 0))}
+    if sliced_parity is not None:
+        line["sliced_parity"] = sliced_parity
+    rk = roofline_kernels(peak)
+    if rk:
+        line["roofline_kernels"] = rk
+    line.update(extras)
     print(json.dumps(line))
+    cm.close()
     if dist:
         dist.destroy_process_group()
     return 0

@@ -31,7 +31,8 @@ typedef enum {
                               index out of bounds: src/vFlow.cpp:264-267)                           */
   FARMS_ERR_CUDA = -3,     /* CUDA runtime failure; farms_last_error() has the text                 */
   FARMS_ERR_NOMEM = -4,    /* host or device allocation failed                                     */
-  FARMS_ERR_STATE = -5     /* call order violated (e.g. results before any submit)                 */
+  FARMS_ERR_STATE = -5,    /* call order violated (e.g. results before any submit)                 */
+  FARMS_ERR_COMM = -6      /* NCCL failure (or libnccl.so.2 cannot be loaded); farms_last_error() has the text */
 } farms_status;
 
 typedef struct farms_ctx farms_ctx;
@@ -51,7 +52,7 @@ typedef struct {
                                timestamps are not perfectly sorted; 0 = default (1000)            */
   /* Tuning / test selectors (0 = the library's own choice; never read from the environment): */
   uint32_t pool_variant;    /* fast pooling kernel: 0/1 staged-list k_pool_tile, 2 bit-table k_pool_bits, 3 the
-                               one-CTA-per-SM instantiation of k_pool_tile (both alternatives are parity-tested) */
+                               one-CTA-per-SM instantiation of k_pool_tile, 4 two-phase k_pool_warp (all parity-tested) */
   uint32_t fit_chunk;       /* events per plane-fit chunk (SAE snapshot interval); 0 = from the sensor size  */
   uint32_t slab_target;     /* flow events per (tile region, time slab) the slab length is chosen for; 0 = 70 */
   uint32_t reserved[4];
@@ -112,6 +113,9 @@ typedef struct {
 #define FARMS_POOLK_TILE_ONE_CTA 8u  /* k_pool_tile<16, 768, 4, 1> as the first pass (pool_variant 3)        */
 #define FARMS_POOLK_BITS 16u         /* k_pool_bits (pool_variant 2)                                         */
 #define FARMS_POOLK_ANY 32u          /* k_pool_any                                                           */
+#define FARMS_POOLK_WARP_DENSE 64u   /* k_pool_warp<8 warps, 480-record slots, 2 slabs per round, 2 CTAs/SM>  */
+#define FARMS_POOLK_WARP_SPARSE 128u /* k_pool_warp<8, 352, 4, 2>                                            */
+#define FARMS_POOLK_WARP_SECOND 256u /* k_pool_warp<16, 768, 4, 1>, flagged second pass                      */
 
 /* ---- lifetime: replaces `vFlowManager vFlowM(...)` (src/main.cpp:186) ---- */
 int farms_create(farms_ctx **out, const farms_config *cfg);
@@ -173,6 +177,45 @@ int farms_state_fold_host(farms_ctx *ctx, const uint32_t *last_t, const uint8_t 
  * float4-per-event device buffer that goes over NVLink in a single NCCL gather. */
 int farms_pack4_f32(farms_ctx *ctx, const double *d_a, const double *d_b, const double *d_c, const double *d_d,
                     uint64_t n, float *d_out4);
+
+/* ---- time-sliced multi-GPU runs (no counterpart in the reference) --------------------------------
+ * One farms_ctx per GPU -- one process per GPU, or one host thread per GPU -- joined into a farms_comm.  The recording
+ * is cut into time slices, one per rank, in rank order.  Rank g passes the events of its slice INCLUDING the causal
+ * halo in front of it:
+ *     events [0, n_halo)     history only: processed (their local flow is state for the pooling of later events,
+ *                            which admits |dt| < 500 us, src/vFlow.cpp:1002), no outputs
+ *     events [n_halo, n)     owned: outputs are produced for these
+ *     events [0, n_surface)  this rank's share of the surface exchange: the shares of ranks 0 .. g-1 must tile the
+ *                            recording from its first event up to rank g's first (halo) event; 0 on the last rank
+ * farms_comm_process is collective.  It all-gathers the ranks' "last event per pixel" surfaces, folds the earlier
+ * ranks' surfaces into this context in rank order (the surface of active events never forgets, src/vFlow.cpp:267),
+ * runs the event loop and -- if `gather` is given -- delivers the README's contract columns of every rank's owned
+ * events to rank gather->root, batch by batch while the next batch computes.  The context must be fresh (just
+ * created or farms_reset).  Transports: NCCL (libnccl.so.2, loaded on first use) or, with FARMS_COMM_LOCAL, direct
+ * copies between host threads of one process. */
+typedef struct farms_comm farms_comm;
+#define FARMS_COMM_ID_BYTES 128
+#define FARMS_COMM_LOCAL 1u            /* all ranks are threads of this process: no NCCL, ranks may share a device */
+#define FARMS_IO_INPUT_ON_DEVICE 1u    /* x, y, t are device pointers                                           */
+#define FARMS_IO_OUTPUT_ON_DEVICE 2u   /* the farms_out columns are device pointers                             */
+
+typedef struct {
+  int32_t root;      /* rank that receives                                                                       */
+  float *dst;        /* root only: DEVICE buffer of 4 floats per owned event of the whole recording, rank after
+                        rank: globalR, globalTheta, localR, localTheta (the README's 8-column row minus the echoed
+                        x y t p; six printed digits fit a float)                                                  */
+  uint64_t *counts;  /* optional, host, nranks entries, filled on every rank: owned events per rank            */
+} farms_gather;
+
+/* rank 0: 128 bytes that identify the group; hand them to every rank (file, pipe, torch.distributed ...) */
+int farms_comm_unique_id(void *id128);
+int farms_comm_create(farms_comm **out, farms_ctx *ctx, int nranks, int rank, const void *id128, uint32_t flags);
+void farms_comm_destroy(farms_comm *comm);
+int farms_comm_info(const farms_comm *comm, int32_t *nranks, int32_t *rank, int32_t *transport /* 0 none, 1 NCCL, 2 local */);
+/* out: n - n_halo entries per column (any column, or out itself, may be NULL); io_flags: FARMS_IO_* */
+int farms_comm_process(farms_comm *comm, const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t n,
+                       uint64_t n_halo, uint64_t n_surface, uint64_t t0, uint32_t io_flags, const farms_out *out,
+                       const farms_gather *gather);
 
 #ifdef __cplusplus
 }

@@ -236,8 +236,8 @@ def test_cli_time_sliced_over_several_contexts_equals_one_run(tmp_path, monkeypa
     common = ["--width", str(s.width), "--height", str(s.height), "--filtersize", str(s.filtersize)]
     r1 = subprocess.run([CLI] + common + ["--filename", base1], capture_output=True, text=True)
     assert r1.returncode == 0, r1.stderr
-    monkeypatch.setenv("FARMS_CLI_SAME_DEVICE", "1")
-    r3 = subprocess.run([CLI] + common + ["--filename", base3, "--gpus", "3"], capture_output=True, text=True)
+    r3 = subprocess.run([CLI] + common + ["--filename", base3, "--gpus", "3", "--same-device", "1"],
+                        capture_output=True, text=True)
     assert r3.returncode == 0, r3.stderr
     a = np.loadtxt(base1 + "_FARMSOut_batch.txt")
     b = np.loadtxt(base3 + "_FARMSOut_batch.txt")
@@ -247,3 +247,128 @@ def test_cli_time_sliced_over_several_contexts_equals_one_run(tmp_path, monkeypa
     m = ~np.isnan(a)
     assert np.allclose(a[m], b[m], rtol=2e-6, atol=0)                             # 6 printed digits
     assert (a[:, 8] > 0).sum() > 10000
+
+
+def _plan_slices(t, G, halo=499):
+    """Equal time slices of a sorted stream: per rank (lo, begin, end, surf_end) as event indices."""
+    t0 = int(t[0])
+    span = int(t[-1]) - t0 + 1
+    D = -(-span // G)
+    at = lambda ts: int(np.searchsorted(t, t0 + ts, side="left"))
+    plan = []
+    for g in range(G):
+        begin = at(g * D)
+        end = len(t) if g == G - 1 else at((g + 1) * D)
+        lo = 0 if g == 0 else at(g * D - min(halo, g * D))
+        surf_end = lo if g == G - 1 else at((g + 1) * D - min(halo, (g + 1) * D))
+        plan.append((lo, begin, end, surf_end))
+    return t0, plan
+
+
+@pytest.mark.parametrize("device_io", [False, True])
+def test_comm_local_transport_three_slices_equal_one_run(device_io):
+    """farms_comm_process (csrc/comm.cu) with the in-process transport: three ranks as host threads on one GPU --
+    surface exchange, fold in rank order, causal halo without outputs, and the float4 gather on rank 0 -- against
+    one plain pass over the same recording."""
+    import threading
+    import torch
+    import farms_b200
+    from helpers import synth_stream
+    s, x, y, t, p = synth_stream(3, 200000, 0)
+    G = 3
+    one = farms_b200.Farms(s.width, s.height, s.filtersize, 5, max_batch=30000).process(x, y, t)
+    t0, plan = _plan_slices(t, G)
+    uid = os.urandom(16)
+    outs, errs, counts = [None] * G, [None] * G, [None] * G
+    total = sum(e - b for _, b, e, _ in plan)
+    dev = torch.device("cuda", 0)
+    gathered = torch.zeros((total, 4), dtype=torch.float32, device=dev)
+    cols = ["t_rel", "global_r", "global_theta", "vx", "vy", "local_r", "local_theta", "scale", "valid", "inliers"]
+
+    def run(g):
+        try:
+            lo, begin, end, surf_end = plan[g]
+            f = farms_b200.Farms(s.width, s.height, s.filtersize, 5, max_batch=30000)
+            cm = farms_b200.Comm(f, G, g, uid, local=True)
+            assert cm.transport() == "local"
+            n_own = end - begin
+            if device_io:
+                tdt = {np.uint32: torch.int32, np.float64: torch.float64, np.uint8: torch.uint8, np.uint16: torch.int16}
+                out = {k: torch.empty(n_own, dtype=tdt[farms_b200.OUT_DTYPES[k]], device=dev) for k in cols}
+                dx = torch.from_numpy(x[lo:end].copy()).to(dev)
+                dy = torch.from_numpy(y[lo:end].copy()).to(dev)
+                dt = torch.from_numpy(t[lo:end].copy().view(np.int64)).to(dev)
+                counts[g] = cm.process(dx, dy, dt, begin - lo, surf_end - lo, t0, out=out, gather_dst=gathered, device=True)
+                torch.cuda.synchronize()
+                outs[g] = {k: v.cpu().numpy() for k, v in out.items()}
+                outs[g]["t_rel"] = outs[g]["t_rel"].view(np.uint32)
+                outs[g]["inliers"] = outs[g]["inliers"].view(np.uint16)
+            else:
+                out = {k: np.empty(n_own, farms_b200.OUT_DTYPES[k]) for k in cols}
+                counts[g] = cm.process(x[lo:end], y[lo:end], t[lo:end], begin - lo, surf_end - lo, t0, out=out,
+                                       gather_dst=gathered)
+                outs[g] = out
+            assert f.timings()["events"] == end - lo
+            cm.close()
+            f.close()
+        except Exception as e:  # surfaced below
+            errs[g] = e
+
+    th = [threading.Thread(target=run, args=(g,)) for g in range(G)]
+    for q in th:
+        q.start()
+    for q in th:
+        q.join(timeout=300)
+    assert all(e is None for e in errs), errs
+    assert [int(c) for c in counts[0]] == [e - b for _, b, e, _ in plan]
+    got = {k: np.concatenate([o[k] for o in outs]) for k in cols}
+    for k in ("t_rel", "valid", "inliers", "scale"):
+        assert np.array_equal(got[k], one[k]), k
+    for k in ("vx", "vy", "local_r", "local_theta"):
+        assert np.array_equal(got[k], one[k], equal_nan=True), k
+    v = one["valid"].astype(bool)
+    assert v.sum() > 20000
+    assert np.allclose(got["global_r"], one["global_r"], rtol=1e-6, atol=0)
+    assert np.allclose(got["global_theta"], one["global_theta"], rtol=0, atol=1e-6)
+    g4 = gathered.cpu().numpy()
+    for j, k in enumerate(["global_r", "global_theta", "local_r", "local_theta"]):
+        assert np.allclose(g4[:, j], one[k].astype(np.float32), rtol=2e-6, atol=1e-6), k
+
+
+def test_comm_single_rank_gather_and_halo_skip():
+    """nranks = 1: no transport at all; the n_halo prefix is history only and the gather is a device-side pack."""
+    import torch
+    import farms_b200
+    from helpers import synth_stream
+    s, x, y, t, p = synth_stream(2, 90000, 0)
+    one = farms_b200.Farms(s.width, s.height, s.filtersize, 5).process(x, y, t)
+    f = farms_b200.Farms(s.width, s.height, s.filtersize, 5, max_batch=25000)
+    cm = farms_b200.Comm(f, 1, 0, b"")
+    n_halo = 31234
+    out = {k: np.empty(len(x) - n_halo, farms_b200.OUT_DTYPES[k]) for k in ("valid", "local_r", "global_r", "scale")}
+    g = torch.zeros((len(x) - n_halo, 4), dtype=torch.float32, device="cuda:0")
+    counts = cm.process(x, y, t, n_halo, 0, int(t[0]), out=out, gather_dst=g)
+    assert int(counts[0]) == len(x) - n_halo
+    assert np.array_equal(out["valid"], one["valid"][n_halo:])
+    assert np.array_equal(out["local_r"], one["local_r"][n_halo:])
+    assert np.array_equal(out["scale"], one["scale"][n_halo:])
+    assert np.allclose(out["global_r"], one["global_r"][n_halo:], rtol=1e-6)
+    assert np.allclose(g.cpu().numpy()[:, 2], one["local_r"][n_halo:].astype(np.float32), rtol=2e-6)
+    # the halo was fitted (it is flow state for the pooling of the owned events) but never pooled
+    tm = f.timings()
+    assert tm["pool_events_first"] + tm["pool_events_second"] + tm["pool_events_general"] == int(one["valid"][n_halo:].sum())
+
+
+def test_slice_surface_rejects_out_of_range_events():
+    import torch
+    import farms_b200
+    f = farms_b200.Farms(64, 48, 5, 5)
+    dev = torch.device("cuda", 0)
+    x = torch.tensor([1, 2, 70], dtype=torch.int16, device=dev)  # 70 >= width
+    y = torch.tensor([1, 2, 3], dtype=torch.int16, device=dev)
+    t = torch.tensor([10, 20, 30], dtype=torch.int64, device=dev)
+    lt = torch.zeros(64 * 48, dtype=torch.int32, device=dev)
+    hit = torch.zeros(64 * 48, dtype=torch.uint8, device=dev)
+    with pytest.raises(farms_b200.FarmsError) as e:
+        f.slice_surface(x, y, t, 0, lt, hit)
+    assert e.value.code == farms_b200.ERR_RANGE

@@ -120,7 +120,7 @@ def test_fast_pooling_equals_exact_pooling_on_long_dense_streams(config, n, star
     assert np.array_equal(fast["global_r"][~v], exact["global_r"][~v])
 
 
-@pytest.mark.parametrize("impl", ["bits", "tile1"])
+@pytest.mark.parametrize("impl", ["bits", "tile1", "warp", "tile"])
 def test_alternative_pooling_kernels_match_oracle_and_exact_kernel(impl):
     """k_pool_bits (farms_config.pool_variant 2: prefix bit tables over the staged records, a measured alternative
     to the default staged-list kernel) and the one-CTA-per-SM instantiation of k_pool_tile (variant 3) obey the same
@@ -129,7 +129,9 @@ def test_alternative_pooling_kernels_match_oracle_and_exact_kernel(impl):
     s, x, y, t, ref, f = _run_case(4, 120000, 0, None, pool_variant=impl)
     rep = compare(f.process(x, y, t), ref, f"cfg4 pooling variant {impl}")
     assert_parity(rep)
-    want = farms_b200.POOLK_BITS if impl == "bits" else farms_b200.POOLK_TILE_ONE_CTA
+    want = {"bits": farms_b200.POOLK_BITS, "tile1": farms_b200.POOLK_TILE_ONE_CTA,
+            "warp": farms_b200.POOLK_WARP_DENSE | farms_b200.POOLK_WARP_SPARSE,
+            "tile": farms_b200.POOLK_TILE_DENSE | farms_b200.POOLK_TILE_SPARSE}[impl]
     assert f.timings()["pool_kernels"] & want
     s, x, y, t, p = synth_stream(4, 2_000_000, 2000)
     fast = farms_b200.Farms(s.width, s.height, s.filtersize, 5, pool_variant=impl).process(x, y, t)
@@ -166,26 +168,36 @@ def test_locally_dense_streams_overflowing_the_staging_slots(squeeze):
 # reference's output on these very prefixes: tests/golden LONG_SYNTH_CASES) at the densities the benchmark runs at.
 # ---------------------------------------------------------------------------------------------------
 LONG = [
-    # config, events, first-pass kernel the stream must exercise, must the flagged second pass pool events too
-    (4, 2_000_000, "POOLK_TILE_DENSE", True),
-    (3, 2_000_000, None, False),
-    (2, 1_000_000, None, False),
+    # config, events, pooling variant, first-pass kernel the stream must exercise
+    (4, 2_000_000, "tile", "POOLK_TILE_DENSE"),  # (no slot overflows on this stream: the dense test below has them)
+    (4, 2_000_000, "warp", "POOLK_WARP_DENSE"),
+    (3, 2_000_000, "tile", None),
+    (3, 2_000_000, "warp", None),
+    (2, 1_000_000, "tile", None),
+    (2, 1_000_000, "warp", None),
 ]
+_ORACLE_CACHE = {}
 
 
-@pytest.mark.parametrize("config,n,first,second", LONG)
-def test_steady_state_parity_with_the_oracle(config, n, first, second):
+def _oracle_long(config, n):
+    if (config, n) not in _ORACLE_CACHE:
+        s, x, y, t, p = synth_stream(config, n, 0)
+        _ORACLE_CACHE[(config, n)] = (s, x, y, t, run_oracle(s.width, s.height, s.filtersize, 5, x, y, t, p, fast=True))
+    return _ORACLE_CACHE[(config, n)]
+
+
+@pytest.mark.parametrize("config,n,variant,first", LONG)
+def test_steady_state_parity_with_the_oracle(config, n, variant, first):
     """1-2 M-event prefixes: at 1280x720 the valid fraction only reaches its steady 45-54 % after ~1 M events, and
     only then do slabs hold enough flow events for launch_pooling to pick k_pool_tile<8,512,2,2> -- the
     instantiation the benchmark times.  The kernels that ran and the number of events each path pooled are read
     back from farms_timings and asserted, so this is the benchmarked path against the oracle, not a self-check."""
     import farms_b200
-    s, x, y, t, p = synth_stream(config, n, 0)
-    ref = run_oracle(s.width, s.height, s.filtersize, 5, x, y, t, p, fast=True)
-    f = farms_b200.Farms(s.width, s.height, s.filtersize, 5)
+    s, x, y, t, ref = _oracle_long(config, n)
+    f = farms_b200.Farms(s.width, s.height, s.filtersize, 5, pool_variant=variant)
     got = f.process(x, y, t)
     tm = f.timings()
-    rep = compare(got, ref, f"cfg{config} n={n} steady state")
+    rep = compare(got, ref, f"cfg{config} n={n} steady state, pooling variant {variant}")
     rep["timings"] = {k: tm[k] for k in ("pool_kernels", "pool_events_first", "pool_events_second", "pool_events_general")}
     print(json.dumps(rep))
     assert rep["valid_ref"] > 0.3 * n
@@ -194,11 +206,10 @@ def test_steady_state_parity_with_the_oracle(config, n, first, second):
     assert tm["pool_events_first"] > 0.9 * rep["valid_ref"]
     if first:
         assert tm["pool_kernels"] & getattr(farms_b200, first), tm
-    if second:
-        assert tm["pool_kernels"] & farms_b200.POOLK_TILE_SECOND and tm["pool_events_second"] > 0, tm
 
 
-def test_dense_stream_second_pass_and_general_kernel_against_the_oracle():
+@pytest.mark.parametrize("variant", ["tile", "warp"])
+def test_dense_stream_second_pass_and_general_kernel_against_the_oracle(variant):
     """Time-compressed 1280x720 stream (2.5x the density): the 512-record slots of the first pass overflow for a
     good share of the rounds, so the flagged second pass <16,768,4,1> and k_pool_any both pool a substantial number
     of events -- all three routes against the oracle in one run."""
@@ -206,19 +217,22 @@ def test_dense_stream_second_pass_and_general_kernel_against_the_oracle():
     s, x, y, t, p = synth_stream(4, 1_200_000, 0)
     t = (t[0] + ((t - t[0]).astype(np.float64) / 2.5).astype(np.uint64)).astype(np.uint64)
     ref = run_oracle(s.width, s.height, s.filtersize, 5, x, y, t, p, fast=True)
-    f = farms_b200.Farms(s.width, s.height, s.filtersize, 5)
+    f = farms_b200.Farms(s.width, s.height, s.filtersize, 5, pool_variant=variant)
     got = f.process(x, y, t)
     tm = f.timings()
-    rep = compare(got, ref, "cfg4 x2.5 density")
+    rep = compare(got, ref, f"cfg4 x2.5 density, variant {variant}")
     rep["timings"] = {k: tm[k] for k in ("pool_kernels", "pool_events_first", "pool_events_second", "pool_events_general")}
     print(json.dumps(rep))
     assert_parity(rep)
-    assert tm["pool_kernels"] & farms_b200.POOLK_TILE_DENSE and tm["pool_kernels"] & farms_b200.POOLK_TILE_SECOND
+    dense, second = ((farms_b200.POOLK_TILE_DENSE, farms_b200.POOLK_TILE_SECOND) if variant == "tile" else
+                     (farms_b200.POOLK_WARP_DENSE, farms_b200.POOLK_WARP_SECOND))
+    assert tm["pool_kernels"] & dense and tm["pool_kernels"] & second
     assert tm["pool_events_second"] > 1000, tm
 
 
+@pytest.mark.parametrize("variant", ["tile", "warp"])
 @pytest.mark.parametrize("w,h", [(20, 160), (48, 256), (33, 300)])
-def test_tall_sensors_fast_path(w, h):
+def test_tall_sensors_fast_path(w, h, variant):
     """height >= width + 100: the reference bounds window rows by width-1 (src/vFlow.cpp:1000), so owner tiles
     far below row `width` can reach no row at all.  The fast path must stage nothing there (not wrap its run
     lengths) and fall back to the event's own flow like the reference (:1085-1094)."""
@@ -226,12 +240,13 @@ def test_tall_sensors_fast_path(w, h):
     from kat_streams import sweeps
     x, y, t, p = sweeps(w, h, slopes=((9, 2), (-7, 3), (5, -2)), gap=150)
     ref = run_oracle(w, h, 5, 5, x, y, t, p)
-    f = farms_b200.Farms(w, h, 5, 5)
+    f = farms_b200.Farms(w, h, 5, 5, pool_variant=variant)
     got = f.process(x, y, t)
-    rep = compare(got, ref, f"tall sensor {w}x{h}")
+    rep = compare(got, ref, f"tall sensor {w}x{h} {variant}")
     print(json.dumps(rep))
     assert rep["valid_ref"] > 1000
     assert_parity(rep)
     tm = f.timings()
-    assert tm["pool_kernels"] & (farms_b200.POOLK_TILE_DENSE | farms_b200.POOLK_TILE_SPARSE)
+    assert tm["pool_kernels"] & (farms_b200.POOLK_TILE_DENSE | farms_b200.POOLK_TILE_SPARSE |
+                                 farms_b200.POOLK_WARP_DENSE | farms_b200.POOLK_WARP_SPARSE)
     assert tm["pool_events_first"] > 0
