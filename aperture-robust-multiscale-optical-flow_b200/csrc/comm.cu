@@ -351,6 +351,8 @@ int farms_comm_process(farms_comm *cm, const uint16_t *x, const uint16_t *y, con
   if (n >= (1ull << 32) - 1) return farms_fail(c, FARMS_ERR_ARG, "slice too long");
   if (gather && (gather->root < 0 || gather->root >= cm->nranks || (cm->rank == gather->root && !gather->dst)))
     return farms_fail(c, FARMS_ERR_ARG, "bad gather descriptor");
+  if (c->serial && cm->nranks > 1)
+    return farms_fail(c, FARMS_ERR_ARG, "FARMS_FLAG_SERIAL_SEMANTICS is sequential by definition: one rank only");
   const bool in_device = (flags & FARMS_IO_INPUT_ON_DEVICE) != 0, out_device = (flags & FARMS_IO_OUTPUT_ON_DEVICE) != 0;
   CUC(cudaSetDevice(c->cfg.device));
   cudaStream_t s = c->stream;

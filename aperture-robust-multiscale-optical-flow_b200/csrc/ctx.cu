@@ -89,6 +89,7 @@ int alloc_working(farms_ctx *c, WorkSet &w, size_t cap) {
   A(pixkeep, cap) A(flags, cap) A(slab_ids, cap + 1) A(slab_first, cap + 1) A(fin, cap) A(prevp, cap) A(nextp, cap)
   A(vx, cap) A(vy, cap) A(len, cap) A(theta, cap) A(lcx, cap) A(lcy, cap) A(gr, cap) A(gth, cap)
   A(pay, 3 * cap) A(done, cap) A(valid, cap) A(scale, cap) A(bw, cap) A(inl, cap) A(rec, cap)
+  if (c->serial) { A(own, cap) } else w.own = nullptr;
   if (c->cfg.flags & FARMS_FLAG_DEBUG_DET) { A(det, cap) } else w.det = nullptr;
 #undef A
   if ((rc = ensure(c, c->sort_temp, radix_sort_temp_bytes(cap)))) return rc;
@@ -124,6 +125,16 @@ __global__ void k_nslabs(const uint32_t *__restrict__ em, const uint32_t *__rest
 __global__ void k_time_span(const uint32_t *__restrict__ em, uint32_t m, uint32_t *out) {
   out[0] = em[0];
   out[1] = em[m - 1];
+}
+
+// first event of a serial-semantics stream: flat pixel and raw timestamp, straight into pinned host memory
+__global__ void k_ghost_info(const uint16_t *__restrict__ x, const uint16_t *__restrict__ y, const uint64_t *__restrict__ t,
+                             int H, uint32_t *host_dst) {
+  host_dst[0] = (uint32_t)x[0] * (uint32_t)H + y[0];
+  host_dst[1] = 0;
+  host_dst[2] = (uint32_t)t[0];
+  host_dst[3] = (uint32_t)(t[0] >> 32);
+  __threadfence_system();
 }
 
 // Small device->host read-backs (error flag, slab count, tail position) are written straight into pinned host
@@ -188,8 +199,15 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
 
   // ---- K1 ingest ----
   CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), s));
+  // serial semantics: the very first event of the stream only sets t0 (src/vFlow.cpp:531-558)
+  const int ghost = (c->serial && !c->ghost_seen) ? 0 : -1;
   launch_ingest(dx, dy, dt, c->t0, n, c->W, c->H, w.ex + h, w.ey + h, w.et + h, w.keyA + h, w.valA + h,
-                (uint32_t)h, c->d_err, s);
+                (uint32_t)h, ghost, c->d_err, s);
+  if (ghost == 0) {
+    // its pixel and raw timestamp, for the first later event at that pixel (pinned words 40..43)
+    k_ghost_info<<<1, 1, 0, s>>>(dx, dy, dt, c->H, c->h_small + 40);
+    *L += 1;
+  }
   launch_halo_keys(w.ex, w.ey, h, c->H, w.keyA, w.valA, s);
   inclusive_max_scan_u32(w.et + h, w.em + h, n, c->last_M, c->scan_temp.p, s, L);
   CU(cudaMemcpyAsync(w.pixkeep, w.keyA, m * 4, cudaMemcpyDeviceToDevice, s));
@@ -199,7 +217,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaEventRecord(c->ev_ingest[set], s));  // the input staging buffers of this set are free again
 
   // ---- K2 history index: stable sort by pixel, prev/next links ----
-  int which = radix_sort_pairs(w.keyA, w.valA, w.keyB, w.valB, m, bits_for(c->npx), c->sort_temp.p, s, L);
+  int which = radix_sort_pairs(w.keyA, w.valA, w.keyB, w.valB, m, bits_for(c->npx + 1), c->sort_temp.p, s, L);
   const uint32_t *skeys = which ? w.keyB : w.keyA, *svals = which ? w.valB : w.valA;
   launch_links(skeys, svals, w.et, c->sae, m, w.prevp, w.nextp, s);
   *L += 1;
@@ -217,7 +235,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   FitParams fp{c->W, c->H, c->r, c->P, c->min_inl};
   FitOut fo{w.vx, w.vy, w.len, w.theta, w.lcx, w.lcy, w.valid, w.bw, w.inl, w.det};
   for (int q = 0; q < FIT_WAYS - 1; q++)
-    CU(cudaMemcpyAsync(c->sae_x[q], c->sae, c->npx * sizeof(uint2), cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(c->sae_x[q], c->sae, (c->npx + 1) * sizeof(uint2), cudaMemcpyDeviceToDevice, s));
   CU(cudaEventRecord(c->ev_c0, s));
   for (int q = 0; q < FIT_WAYS - 1; q++) CU(cudaStreamWaitEvent(c->fit_streams[q], c->ev_c0, 0));
   size_t nchunks = 0;
@@ -249,7 +267,8 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaEventRecord(c->ev[EV_FIT], s));
 
   // ---- the columns the plane fit produced can leave now, under the pooling of this batch ----
-  if (out && n_out && out_stream != s) {
+  const bool early_copy = out && n_out && out_stream != s && !c->serial;  // (serial: the ghost row is fixed later)
+  if (early_copy) {
     CU(cudaEventRecord(c->ev_fitdone[set], s));
     CU(cudaStreamWaitEvent(out_stream, c->ev_fitdone[set], 0));
     if ((rc = copy_fit_columns(c, w, out, hh, n_out, out_off, out_device, out_stream))) return rc;
@@ -266,6 +285,19 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaStreamSynchronize(s));
   // (k_ingest clamps an out-of-range event to pixel (0,0), so the kernels above were safe to run)
   if (((int *)c->h_small)[8]) return fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
+  if (c->serial) {
+    if (ghost == 0) {
+      c->ghost_seen = true;
+      c->ghost_prev_pending = true;
+      c->ghost_pix = c->h_small[40];
+      memcpy(&c->ghost_raw_t, c->h_small + 42, sizeof(uint64_t));
+    }
+    CU(cudaMemsetAsync(c->d_small + 8, 0, 4, s));
+    launch_serial_fix(w.prevp, w.et, w.pixkeep, h, m, ghost == 0 ? (int)h : -1, c->ghost_pix, c->ghost_raw_t,
+                      c->ghost_prev_pending ? 1 : 0, fo, w.own, c->d_small + 8, s);
+    k_publish<<<1, 32, 0, s>>>(c->h_small + 44, c->d_small + 8, 1);  // read at the end-of-batch sync
+    *L += 2;
+  }
   // flow events of this batch's new part (the fit ran above); the halo is assumed to have the same density
   const unsigned long long valid_total = *(const unsigned long long *)(c->h_small + 2);
   const double flow_frac = n ? (double)(valid_total - c->valid_seen) / (double)n : 0.0;
@@ -322,10 +354,10 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
     if ((rc = ensure(c, c->item_ovf, iw * sizeof(uint32_t)))) return rc;
     CU(cudaMemsetAsync(c->item_ovf.p, 0, iw * sizeof(uint32_t), s));
   }
-  const int fast = (monotone && !(c->cfg.flags & FARMS_FLAG_GENERIC_POOLING)) ? c->pool_impl : 0;
+  const int fast = (monotone && !c->serial && !(c->cfg.flags & FARMS_FLAG_GENERIC_POOLING)) ? c->pool_impl : 0;
   *L += launch_pooling(w.rec, w.pay, (const uint32_t *)c->cell_start.p, w.slab_ids, w.slab_first, w.fin, (uint32_t *)c->item_ovf.p, w.done, m, (uint32_t)ncells,
                        (int)hh, w.len, w.lcx, w.lcy, (int)nslabs, g, fast, flow_frac * (double)m / (double)nslabs, w.gr, w.gth, w.scale,
-                       c->d_work, c->d_counters + 1, c->num_sms, s, &c->pool_kernels);
+                       c->d_work, c->d_counters + 1, c->num_sms, s, &c->pool_kernels, c->serial ? w.own : nullptr);
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev[EV_POOL], s));
 
@@ -338,9 +370,8 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
     if (out_stream != s) {
       CU(cudaEventRecord(c->ev_pool[set], s));
       CU(cudaStreamWaitEvent(out_stream, c->ev_pool[set], 0));
-    } else if ((rc = copy_fit_columns(c, w, out, hh, n_out, out_off, out_device, out_stream))) {
-      return rc;
     }
+    if (!early_copy && (rc = copy_fit_columns(c, w, out, hh, n_out, out_off, out_device, out_stream))) return rc;
     if ((rc = copy_out(c, out->global_r ? out->global_r + out_off : nullptr, w.gr, n_out, out_device, out_stream))) return rc;
     if ((rc = copy_out(c, out->global_theta ? out->global_theta + out_off : nullptr, w.gth, n_out, out_device, out_stream))) return rc;
     if ((rc = copy_out(c, out->scale ? out->scale + out_off : nullptr, w.scale, n_out, out_device, out_stream))) return rc;
@@ -359,6 +390,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaStreamSynchronize(s));
   size_t ts = c->h_small[0];
   c->last_M = c->h_small[1];
+  if (c->serial && c->h_small[44]) c->ghost_prev_pending = false;  // the ghost's pixel has had its next event
   // more than HALO_CAP events inside the pooling window (+ slack): truncating the halo would silently lose
   // contributors for the next batch, so this is an error (timestamps in the wrong unit, or a pathological burst)
   if (m - ts > HALO_CAP)
@@ -533,6 +565,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   c->P = pp;
   c->min_inl = cfg->inlier_check;
   c->npx = (size_t)c->W * c->H;
+  c->serial = (cfg->flags & FARMS_FLAG_SERIAL_SEMANTICS) != 0;
   auto bail = [&](int code) {
     farms_destroy(c);
     return code;
@@ -550,7 +583,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   c->fit_chunk = FIT_CHUNK_MIN;
   while (c->fit_chunk < FIT_CHUNK_MAX && (size_t)c->fit_chunk * 6 < c->npx) c->fit_chunk *= 2;
   if (cfg->fit_chunk) c->fit_chunk = (int)std::min<uint32_t>(std::max<uint32_t>(cfg->fit_chunk, 1024u), 1u << 20);
-  if (cfg->pool_variant > 4) return bail(FARMS_ERR_ARG);
+  if (cfg->pool_variant > 7) return bail(FARMS_ERR_ARG);
   if (cfg->pool_variant) c->pool_impl = (int)cfg->pool_variant;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
@@ -569,8 +602,9 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
       if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   }
   bool ok = true;
-  ok &= cudaMalloc((void **)&c->sae, c->npx * sizeof(uint2)) == cudaSuccess;
-  for (int q = 0; q < FIT_WAYS - 1; q++) ok &= cudaMalloc((void **)&c->sae_x[q], c->npx * sizeof(uint2)) == cudaSuccess;
+  // (+1: the dummy pixel W*H that the ghost event of a serial-semantics stream hashes to)
+  ok &= cudaMalloc((void **)&c->sae, (c->npx + 1) * sizeof(uint2)) == cudaSuccess;
+  for (int q = 0; q < FIT_WAYS - 1; q++) ok &= cudaMalloc((void **)&c->sae_x[q], (c->npx + 1) * sizeof(uint2)) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->hx, HALO_CAP * 2) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->hy, HALO_CAP * 2) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->ht, HALO_CAP * 4) == cudaSuccess;
@@ -584,7 +618,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   ok &= cudaMalloc((void **)&c->d_small, 64) == cudaSuccess;
   ok &= cudaMallocHost((void **)&c->h_small, 256) == cudaSuccess;
   if (!ok) return bail(FARMS_ERR_NOMEM);
-  launch_sae_init(c->sae, c->npx, c->stream);
+  launch_sae_init(c->sae, c->npx + 1, c->stream);
   if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   *out = c;
   return FARMS_OK;
@@ -656,8 +690,9 @@ int farms_reset(farms_ctx *c) {
   CU(cudaSetDevice(c->cfg.device));
   CU(cudaDeviceSynchronize());
   c->d2h_pending[0] = c->d2h_pending[1] = false;
-  launch_sae_init(c->sae, c->npx, c->stream);
+  launch_sae_init(c->sae, c->npx + 1, c->stream);
   CU(cudaStreamSynchronize(c->stream));
+  c->ghost_seen = c->ghost_prev_pending = false;
   c->have_t0 = false;
   c->t0 = 0;
   c->total_events = 0;
@@ -764,6 +799,34 @@ int farms_state_fold_host(farms_ctx *c, const uint32_t *last_t, const uint8_t *h
   launch_sae_fold(c->sae, c->npx, (const uint32_t *)c->io_surf_t.p, (const uint8_t *)c->io_surf_hit.p, c->stream);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
+  return FARMS_OK;
+}
+
+void *farms_host_alloc(uint64_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, (size_t)std::max<uint64_t>(bytes, 1), cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void farms_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+int farms_host_register(void *p, uint64_t bytes) {
+  if (!p || !bytes) return FARMS_ERR_ARG;
+  if (cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return FARMS_ERR_CUDA;
+  }
+  return FARMS_OK;
+}
+int farms_host_unregister(void *p) {
+  if (!p) return FARMS_ERR_ARG;
+  if (cudaHostUnregister(p) != cudaSuccess) {
+    cudaGetLastError();
+    return FARMS_ERR_CUDA;
+  }
   return FARMS_OK;
 }
 

@@ -8,8 +8,11 @@
 //          "x y t p globalR globalTheta Vx Vy localR localTheta scale"      (src/vFlow.cpp:131, 436-440)
 //          <filename>_FARMSOut_.txt, the 8 columns the README documents
 //          "x y t p globalR globalTheta localR localTheta"                  (README.md:63)
-// Difference on purpose: the reference's default mode (--SERIAL 1) computes but writes nothing
-// (src/vFlow.cpp:485-489, 727-765); this CLI always runs the batch semantics and always writes.
+// --SERIAL 1 (the reference's default, src/main.cpp:31) runs the semantics of vFlowManager::run
+// (src/vFlow.cpp:465-826: first line only sets t0, lastEventTime written after pooling, numEvents + 1 lines,
+// numEvents capped at filesize / 18) through FARMS_FLAG_SERIAL_SEMANTICS.  One difference on purpose: the reference
+// computes those numbers but writes nothing (:487-489, 727-765); here they go to the file that mode names,
+// <filename>_FARMSOut_bench_500us.txt (:486), in the 11-column format.  --SERIAL 0 = runFileCopy as before.
 // All numbers come from the GPU through the C ABI (include/farms_b200.h); there is no CPU path here.
 #include <chrono>
 #include <cstdint>
@@ -139,6 +142,44 @@ int parse_args(int argc, char **argv, Options &o) {
   return 0;
 }
 
+// the eight output columns in pinned host memory (farms_host_alloc), pageable if pinning fails
+struct PinnedColumns {
+  uint32_t *t_rel = nullptr;
+  double *d[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint8_t *scale = nullptr;
+  bool pinned = true, ok = true;
+  explicit PinnedColumns(size_t n) {
+    auto get = [&](size_t bytes) -> void * {
+      void *p = pinned ? farms_host_alloc(bytes) : nullptr;
+      if (!p) {
+        pinned = false;
+        p = std::malloc(bytes ? bytes : 1);
+      }
+      if (!p) ok = false;
+      return p;
+    };
+    // (all pinned or all pageable: decide on the first allocation)
+    t_rel = (uint32_t *)get(n * sizeof(uint32_t));
+    const bool first_pinned = pinned;
+    for (double *&q : d) q = (double *)get(n * sizeof(double));
+    scale = (uint8_t *)get(n);
+    if (pinned != first_pinned) mixed = true;
+  }
+  ~PinnedColumns() {
+    auto put = [&](void *p, bool was_pinned) {
+      if (!p) return;
+      if (was_pinned) farms_host_free(p); else std::free(p);
+    };
+    // a buffer is pinned iff it was allocated before `pinned` turned false; with `mixed` we cannot tell, so probe
+    if (!mixed) {
+      put(t_rel, pinned);
+      for (double *q : d) put(q, pinned);
+      put(scale, pinned);
+    }
+  }
+  bool mixed = false;  // (pathological: pinning failed half-way; the buffers are leaked at exit rather than mis-freed)
+};
+
 // ---- single-process multi-GPU run: the recording is cut into equal time slices, one per GPU,
 // one host thread and one context per slice, joined by a farms_comm (include/farms_b200.h): NCCL between the
 // devices, or the in-process transport when the slices share one device (--same-device 1, one-GPU boxes).
@@ -242,6 +283,11 @@ int main(int argc, char **argv) {
   // text output prints 6 significant digits: keep the FP64 pooling sums unless told otherwise (the text
   // parse/format around it costs far more than the kernel)
   cfg.flags = (o.fast || o.binary) ? 0u : FARMS_FLAG_EXACT_POOLING;
+  if (o.serial) cfg.flags |= FARMS_FLAG_SERIAL_SEMANTICS;
+  if (o.serial && o.gpus > 1) {
+    std::fprintf(stderr, "error: --gpus needs --SERIAL 0 (the serial driver's semantics are sequential by definition)\n");
+    return 1;
+  }
   farms_ctx *ctx = nullptr;
   int rc = farms_create(&ctx, &cfg);
   if (rc != FARMS_OK) {
@@ -254,8 +300,20 @@ int main(int argc, char **argv) {
   std::printf("%s\nReading input file \n", in_path.c_str());
   farms_events ev;
   char errbuf[256] = "";
-  if ((o.binary ? farms_bin_read(in_path.c_str(), o.num_events, &ev, errbuf, sizeof errbuf)
-                : farms_text_read(in_path.c_str(), o.num_events, 0, &ev, errbuf, sizeof errbuf)) != 0) {
+  unsigned long long max_events = o.num_events;
+  if (o.serial && !o.binary) {
+    // src/vFlow.cpp:511: NUMEVENTS = min(NUMEVENTS, filesize / 18); :531-565: the first line, then lines while
+    // eventsComputed <= NUMEVENTS, i.e. NUMEVENTS + 1 more
+    unsigned long long fsize = 0;
+    if (FILE *fp = std::fopen(in_path.c_str(), "rb")) {
+      std::fseek(fp, 0, SEEK_END);
+      fsize = (unsigned long long)std::ftell(fp);
+      std::fclose(fp);
+    }
+    max_events = std::min<unsigned long long>(o.num_events, fsize / 18) + 2;
+  }
+  if ((o.binary ? farms_bin_read(in_path.c_str(), max_events, &ev, errbuf, sizeof errbuf)
+                : farms_text_read(in_path.c_str(), max_events, 0, &ev, errbuf, sizeof errbuf)) != 0) {
     std::fprintf(stderr, "error: %s\n", errbuf);
     farms_destroy(ctx);
     return 1;
@@ -270,13 +328,26 @@ int main(int argc, char **argv) {
   }
   std::printf("First time = %llu\nProcessing events \n", (unsigned long long)ev.t[0]);
 
-  std::vector<uint32_t> t_rel(n);
-  std::vector<double> gr(n), gth(n), vx(n), vy(n), lr(n), lth(n);
-  std::vector<uint8_t> scale(n);
+  // pinned host memory on both sides: farms_process_host then overlaps its copies with the kernels
+  const bool in_pinned = farms_host_register(ev.x, n * sizeof(uint16_t)) == FARMS_OK &&
+                         farms_host_register(ev.y, n * sizeof(uint16_t)) == FARMS_OK &&
+                         farms_host_register(ev.t, n * sizeof(uint64_t)) == FARMS_OK;
+  PinnedColumns cols(n);
+  if (!cols.ok) {
+    std::fprintf(stderr, "error: cannot allocate the output columns\n");
+    farms_text_free(&ev);
+    farms_destroy(ctx);
+    return 1;
+  }
+  uint32_t *t_rel = cols.t_rel;
+  double *gr = cols.d[0], *gth = cols.d[1], *vx = cols.d[2], *vy = cols.d[3], *lr = cols.d[4], *lth = cols.d[5];
+  uint8_t *scale = cols.scale;
   farms_out out;
   std::memset(&out, 0, sizeof out);
-  out.t_rel = t_rel.data(); out.global_r = gr.data(); out.global_theta = gth.data(); out.vx = vx.data();
-  out.vy = vy.data(); out.local_r = lr.data(); out.local_theta = lth.data(); out.scale = scale.data();
+  out.t_rel = t_rel; out.global_r = gr; out.global_theta = gth; out.vx = vx;
+  out.vy = vy; out.local_r = lr; out.local_theta = lth; out.scale = scale;
+  if (o.verbose) std::printf("[farms_b200] host buffers: input %s, output %s\n", in_pinned ? "pinned" : "pageable",
+                             cols.pinned ? "pinned" : "pageable");
 
   farms_timings tm_sliced;
   uint64_t sliced_events = 0;
@@ -303,12 +374,17 @@ int main(int argc, char **argv) {
   const long usec = (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count();
   std::printf("\nDone processing!\n\nWriting output file.\n");
 
-  const std::string out11 = o.filename + (o.binary ? "_FARMSOut_.bin" : "_FARMSOut_batch.txt"),
+  if (in_pinned) {
+    farms_host_unregister(ev.x);
+    farms_host_unregister(ev.y);
+    farms_host_unregister(ev.t);
+  }
+  const std::string out11 = o.filename + (o.binary ? "_FARMSOut_.bin" : o.serial ? "_FARMSOut_bench_500us.txt" : "_FARMSOut_batch.txt"),
                     out8 = o.filename + "_FARMSOut_.txt";
-  if ((o.binary ? farms_bin_write(out11.c_str(), n, ev.xi, ev.yi, t_rel.data(), ev.pol, gr.data(), gth.data(),
-                                  vx.data(), vy.data(), lr.data(), lth.data(), scale.data())
-                : farms_text_write(out11.c_str(), out8.c_str(), n, ev.xi, ev.yi, t_rel.data(), ev.pol, gr.data(),
-                                   gth.data(), vx.data(), vy.data(), lr.data(), lth.data(), scale.data(), 0)) != 0) {
+  if ((o.binary ? farms_bin_write(out11.c_str(), n, ev.xi, ev.yi, t_rel, ev.pol, gr, gth,
+                                  vx, vy, lr, lth, scale)
+                : farms_text_write(out11.c_str(), out8.c_str(), n, ev.xi, ev.yi, t_rel, ev.pol, gr,
+                                   gth, vx, vy, lr, lth, scale, 0)) != 0) {
     std::fprintf(stderr, "error: cannot write %s / %s\n", out11.c_str(), out8.c_str());
     farms_text_free(&ev);
     farms_destroy(ctx);

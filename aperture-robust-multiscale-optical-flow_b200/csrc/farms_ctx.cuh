@@ -37,7 +37,7 @@ struct WorkSet {
   int32_t *nextp = nullptr;
   double *vx = nullptr, *vy = nullptr, *len = nullptr, *theta = nullptr, *lcx = nullptr, *lcy = nullptr,
          *det = nullptr, *gr = nullptr, *gth = nullptr, *pay = nullptr;
-  uint8_t *valid = nullptr, *scale = nullptr, *done = nullptr;
+  uint8_t *valid = nullptr, *scale = nullptr, *done = nullptr, *own = nullptr;
   int8_t *bw = nullptr;
   uint16_t *inl = nullptr;
   uint4 *rec = nullptr;
@@ -55,12 +55,19 @@ struct farms_ctx {
   // 2^14 at 346x260 (2^13 38.9 ms, 2^14 31.7, 2^15 33.4; without the overlap 2^17 took 66 ms).  Small chunks are
   // launch-bound, large ones walk many dependent history links per event.
   int fit_chunk = FIT_CHUNK_MAX;
-  int pool_impl = 1;  // 1 = staged-list fast path (k_pool_tile), 2 = bit-table variant (FARMS_POOL_IMPL=bits, A/B runs)
+  // fast pooling kernel (farms_config.pool_variant): 7 = k_pool_tile16, three slabs per round (the default: measured
+  // fastest), 1 = k_pool_tile, 2 = k_pool_bits, 3 = k_pool_tile one CTA per SM, 4 = k_pool_warp, 5 / 6 = k_pool_tile16
+  // with two / four slabs per round
+  int pool_impl = 7;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[EV_COUNT]{};
   std::string err;
   bool have_t0 = false;
   uint64_t t0 = 0;
+  // FARMS_FLAG_SERIAL_SEMANTICS: the stream's first event ("ghost") is not processed; its pixel keeps its raw time
+  bool serial = false, ghost_seen = false, ghost_prev_pending = false;
+  uint32_t ghost_pix = 0;
+  uint64_t ghost_raw_t = 0;
   uint64_t total_events = 0;
   uint32_t last_M = 0;
   unsigned long long valid_seen = 0;  // flow events counted so far in the current process call

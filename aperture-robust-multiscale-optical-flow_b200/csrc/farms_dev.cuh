@@ -66,9 +66,16 @@ void inclusive_max_scan_u32(const uint32_t *in, uint32_t *out, size_t n, uint32_
                             cudaStream_t s, uint64_t *launches);
 
 // ---- index.cu ----
+// ghost: index (among the n new events) of an event that gets the dummy pixel key W*H, i.e. stays out of the
+// surface of active events (the first event of a stream under FARMS_FLAG_SERIAL_SEMANTICS), or -1
 void launch_ingest(const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t t0, size_t n,
                    int W, int H, uint16_t *ex, uint16_t *ey, uint32_t *et, uint32_t *pix, uint32_t *idx,
-                   uint32_t idx_base, int *err_flag, cudaStream_t s);
+                   uint32_t idx_base, int ghost, int *err_flag, cudaStream_t s);
+// serial semantics: own_ok[i] = the event's own pixel passes the age test with the time of the PREVIOUS event at
+// the pixel (src/vFlow.cpp:790); the ghost event's outputs are cleared
+void launch_serial_fix(const int2 *prevp, const uint32_t *et, const uint32_t *pix, size_t h, size_t m, int ghost_index,
+                       uint32_t ghost_pix, uint64_t ghost_raw_t, int ghost_prev_pending, FitOut fo, uint8_t *own_ok,
+                       uint32_t *ghost_consumed, cudaStream_t s);
 void launch_halo_keys(const uint16_t *ex, const uint16_t *ey, size_t h, int H, uint32_t *pix, uint32_t *idx,
                       cudaStream_t s);
 void launch_links(const uint32_t *skeys, const uint32_t *svals, const uint32_t *et, const uint2 *sae, size_t m,
@@ -111,7 +118,7 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
                    const double *ev_len, const double *ev_lcx, const double *ev_lcy, int nslabs, PoolGeom g, int fast,
                    double flow_per_slab, double *global_r, double *global_theta, uint8_t *scale,
                    unsigned int *work_counter, unsigned long long *cand_count, int num_sms, cudaStream_t s,
-                   unsigned *kernels_used);
+                   unsigned *kernels_used, const uint8_t *own_ok);
 int pool_tile_smem_bytes();
 // words of the zeroed item_ovf array launch_pooling needs
 size_t pool_item_words(int W, int H, int nslabs);

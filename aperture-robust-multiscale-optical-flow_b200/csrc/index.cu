@@ -12,7 +12,7 @@ namespace {
 __global__ void k_ingest(const uint16_t *__restrict__ x, const uint16_t *__restrict__ y,
                          const uint64_t *__restrict__ t, uint64_t t0, size_t n, int W, int H,
                          uint16_t *__restrict__ ex, uint16_t *__restrict__ ey, uint32_t *__restrict__ et,
-                         uint32_t *__restrict__ pix, uint32_t *__restrict__ idx, uint32_t idx_base,
+                         uint32_t *__restrict__ pix, uint32_t *__restrict__ idx, uint32_t idx_base, int ghost,
                          int *__restrict__ err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -25,7 +25,8 @@ __global__ void k_ingest(const uint16_t *__restrict__ x, const uint16_t *__restr
   ex[i] = (uint16_t)xx;
   ey[i] = (uint16_t)yy;
   et[i] = (uint32_t)(t[i] - t0);  // unsigned wrap like `time_ = time_ - t0` (src/vFlow.cpp:241)
-  pix[i] = xx * (uint32_t)H + yy;
+  // the ghost event keeps its coordinates (for the output row) but hashes to the dummy pixel W*H
+  pix[i] = (long long)i == (long long)ghost ? (uint32_t)W * (uint32_t)H : xx * (uint32_t)H + yy;
   idx[i] = idx_base + (uint32_t)i;
 }
 
@@ -57,6 +58,30 @@ __global__ void k_links(const uint32_t *__restrict__ skeys, const uint32_t *__re
   }
   prevp[j] = pp;
   nextp[j] = (s + 1 < m && skeys[s + 1] == key) ? (int32_t)svals[s + 1] : NEXT_NONE;
+}
+
+// Serial semantics (src/vFlow.cpp:465-826).  lastEventTime[x][y] is written after pooling (:790), so when event i
+// is pooled its own pixel still holds the time of the previous event there: own_ok[i] = |t_i - T_prev| < 500 with
+// T_prev = 0 for a never-hit pixel, or the RAW first timestamp for the pixel of the stream's first event (:558).
+// The first event itself (the ghost) gets an all-zero row.
+__global__ void k_serial_fix(const int2 *__restrict__ prevp, const uint32_t *__restrict__ et,
+                             const uint32_t *__restrict__ pix, size_t h, size_t m, int ghost_index, uint32_t ghost_pix,
+                             uint64_t ghost_raw_t, int ghost_prev_pending, FitOut fo, uint8_t *__restrict__ own_ok,
+                             uint32_t *__restrict__ ghost_consumed) {
+  const size_t i = h + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int2 pp = prevp[i];
+  double tprev = pp.x == SAE_NEVER ? 0.0 : (double)(uint32_t)pp.y;
+  if (ghost_prev_pending && pp.x == SAE_NEVER && pix[i] == ghost_pix) {
+    tprev = (double)ghost_raw_t;  // lastEventTime[x][y] = time_ before the rebase (:558)
+    *ghost_consumed = 1u;         // (a never-hit pixel has one first event: a single writer)
+  }
+  own_ok[i] = fabs((double)et[i] - tprev) < (double)FARMS_KILL_OLD_FLOW_TIME ? 1 : 0;
+  if ((long long)i == (long long)ghost_index) {
+    fo.vx[i] = 0.0; fo.vy[i] = 0.0; fo.len[i] = 0.0; fo.theta[i] = 0.0; fo.lcx[i] = 0.0; fo.lcy[i] = 0.0;
+    fo.valid[i] = 0; fo.best_window[i] = -1; fo.inliers[i] = 0;
+    if (fo.det) fo.det[i] = __longlong_as_double(0x7ff8000000000000ll);
+  }
 }
 
 // flags[j] = 1 where a new time slab starts; *nonmono != 0 if any timestamp runs backwards.
@@ -116,8 +141,16 @@ void launch_pack4(const double *a, const double *b, const double *c, const doubl
 
 void launch_ingest(const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t t0, size_t n, int W, int H,
                    uint16_t *ex, uint16_t *ey, uint32_t *et, uint32_t *pix, uint32_t *idx, uint32_t idx_base,
-                   int *err_flag, cudaStream_t s) {
-  if (n) k_ingest<<<nb(n, 256), 256, 0, s>>>(x, y, t, t0, n, W, H, ex, ey, et, pix, idx, idx_base, err_flag);
+                   int ghost, int *err_flag, cudaStream_t s) {
+  if (n) k_ingest<<<nb(n, 256), 256, 0, s>>>(x, y, t, t0, n, W, H, ex, ey, et, pix, idx, idx_base, ghost, err_flag);
+}
+
+void launch_serial_fix(const int2 *prevp, const uint32_t *et, const uint32_t *pix, size_t h, size_t m, int ghost_index,
+                       uint32_t ghost_pix, uint64_t ghost_raw_t, int ghost_prev_pending, FitOut fo, uint8_t *own_ok,
+                       uint32_t *ghost_consumed, cudaStream_t s) {
+  if (m > h)
+    k_serial_fix<<<nb(m - h, 256), 256, 0, s>>>(prevp, et, pix, h, m, ghost_index, ghost_pix, ghost_raw_t,
+                                               ghost_prev_pending, fo, own_ok, ghost_consumed);
 }
 void launch_halo_keys(const uint16_t *ex, const uint16_t *ey, size_t h, int H, uint32_t *pix, uint32_t *idx,
                       cudaStream_t s) {

@@ -107,6 +107,7 @@ struct PoolArgs {
   uint32_t *fin;               // per output event: contributor count | scale index << 16 of a fast-path result
   uint32_t *item_ovf;          // per (owner tile, slab segment) item: bit (slab - first slab) / 2 = that pair of slabs
                                // had targets the first pass could not stage (slot overflow)
+  const uint8_t *own_ok;  // serial semantics only (else null): per event, does its own pixel pass the age test
   uint8_t *done;       // per index position: 1 once the fast path has pooled that event
   size_t m;            // stride of the pay arrays
   uint32_t ncells;     // cell_start[ncells] = entries in the index (events with flow)
@@ -252,8 +253,10 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
               const uint4 c = A.rec[p];
               const int cx = (int)(c.x & 0xffffu), cy = (int)(c.x >> 16);
               const long long dt = (long long)ti - (long long)c.y;
-              const bool ok = (int)c.z <= ii && (int)c.w > ii && cx >= pxlo && cx <= pxhi && cy >= pylo &&
-                              cy <= pyhi && dt < FARMS_KILL_OLD_FLOW_TIME && dt > -FARMS_KILL_OLD_FLOW_TIME;  // :1002
+              bool ok = (int)c.z <= ii && (int)c.w > ii && cx >= pxlo && cx <= pxhi && cy >= pylo &&
+                        cy <= pyhi && dt < FARMS_KILL_OLD_FLOW_TIME && dt > -FARMS_KILL_OLD_FLOW_TIME;  // :1002
+              // serial semantics: the event's own cell is tested with its pixel's previous time (src/vFlow.cpp:790)
+              if (A.own_ok && (int)c.z == ii) ok = ok && A.own_ok[ii] != 0;
               if (ok) {
                 const int dx = abs(cx - k - xi), dy = abs(cy + k * H - yi);
                 const int ring = (max(dx, dy) + FARMS_WINDOW_JUMP - 1) / FARMS_WINDOW_JUMP;
@@ -912,7 +915,7 @@ constexpr int WP_PAD = 32;     // zeroed test records behind a slot's last recor
 
 template <int WARPS, int CAP, int NSL>
 struct WarpSmem {
-  static constexpr int RING = TK_LB + NSL, STRIDE = CAP + WP_PAD;
+  static constexpr int RING = TK_LB + NSL, PAD = WP_PAD, STRIDE = CAP + PAD;
   uint2 ta[RING * STRIDE];   // {x_rel | y_rel << 8 | idx_rel[15:0] << 16,  idx_rel[23:16] | span << 8}
   float2 pb[RING * STRIDE];  // |flow|cos(theta), |flow|sin(theta)
   float4 acc[WARPS][FARMS_NSCALES][32];  // per-lane ring partials: len, lcx, lcy, count
@@ -1084,10 +1087,10 @@ __device__ void stage_slabs_packed(const PoolArgs &A, SM &S, int s0, int s1, con
     if (raw > (uint32_t)CAP) S.overflow[slot] = 1;
   }
   // test records the unrolled pooling loop may touch past the end of a slot: span 0 never passes
-  for (int q = tid; q < nsl * WP_PAD; q += THREADS) {
-    const int sl = q / WP_PAD;
+  for (int q = tid; q < nsl * SM::PAD; q += THREADS) {
+    const int sl = q / SM::PAD;
     const uint32_t cnt = min(S.slab_pre[sl + 1] - S.slab_pre[sl], (uint32_t)CAP);
-    S.ta[((s0 + sl) % RING) * STRIDE + cnt + (q - sl * WP_PAD)] = make_uint2(0u, 0u);
+    S.ta[((s0 + sl) % RING) * STRIDE + cnt + (q - sl * SM::PAD)] = make_uint2(0u, 0u);
   }
 }
 
@@ -1404,6 +1407,357 @@ void launch_warp(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
   static_assert(sizeof(SM) <= (CTAS == 2 ? 115712 : 232448), "shared memory of the warp kernel: 227 KB per CTA, 228 KB per SM");
   static_assert(SM::RING * SM::STRIDE <= 65536, "queue entries are 16-bit slot addresses");
   auto kern = k_pool_warp<WARPS, CAP, NSL, CTAS, SECOND>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  const int otx = (A.g.W + OT - 1) >> OT_SHIFT, oty = (A.g.H + OT - 1) >> OT_SHIFT;
+  const int nseg = (nslabs + TK_SEG - 1) / TK_SEG;
+  const long long items = (long long)otx * oty * nseg;
+  unsigned grid = (unsigned)std::min<long long>(items, (long long)num_sms * CTAS);
+  kern<<<grid, WARPS * 32, sizeof(SM), s>>>(A, otx, oty, nseg);
+}
+
+template <int WARPS, int CAP, int NSL>
+struct PackedSmem {
+  static constexpr int RING = TK_LB + NSL, PAD = TK_PAD, STRIDE = CAP + PAD;
+  uint2 ta[RING * STRIDE];   // {x_rel | y_rel << 8 | idx_rel[15:0] << 16,  idx_rel[23:16] | span << 8}
+  float2 pb[RING * STRIDE];  // |flow|cos(theta), |flow|sin(theta)
+  float4 acc[WARPS][FARMS_NSCALES][32];  // per-lane ring partials: len, lcx, lcy, count
+  uint32_t tlist[NSL][TK_MAXT];
+  uint32_t run_s[RING * TK_MAXRUN], run_o[RING * TK_MAXRUN + 1];
+  uint8_t run_info[RING * TK_MAXRUN];
+  uint32_t slab_f[RING + 1], slab_pre[RING + 1];
+  uint32_t wcount[WARPS];
+  uint32_t slot_base[RING];
+  int tag[RING], count[RING], overflow[RING];
+  int dlo[NSL], dhi[NSL], ovf[NSL];
+  unsigned int ntg[NSL], tnext, item;
+};
+
+// k_pool_tile16: k_pool_tile on the 16-byte packed records of stage_slabs_packed (8-byte test record: one LDS.64,
+// VABSDIFF4 window test, 24-bit index / span; float2 payload).  A fifth less shared memory per staged record buys
+// four slabs per round at dense-stream slot sizes (twice the tasks per round, half the rounds).
+// SECOND: a later pass over the same items with larger slots; only rounds that still hold undone targets (their
+// staging overflowed the slots of the first pass: locally dense scenes) do any work.
+template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND>
+__global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, int otx_n, int oty_n, int nseg) {
+  using SM = PackedSmem<WARPS, CAP, NSL>;
+  constexpr int STRIDE = SM::STRIDE;
+  constexpr int THREADS = WARPS * 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SM &S = *reinterpret_cast<SM *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = lane >> 4, sub = lane & 15;
+  const int W = A.g.W, H = A.g.H, nty = A.g.nty, NT = A.g.ntx * A.g.nty;
+  const unsigned int nitems = (unsigned int)otx_n * oty_n * nseg;
+  unsigned long long ncand = 0;
+  unsigned int npooled = 0;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) S.item = atomicAdd(A.work_counter, 1u);
+    if (tid < (TK_LB + NSL)) S.tag[tid] = -1;
+    __syncthreads();
+    const unsigned int item = S.item;
+    if (item >= nitems) break;
+    // items are ordered segment-major so that CTAs running together work on the same time span (L2 reuse)
+    const int seg = item / (otx_n * oty_n), ot = item % (otx_n * oty_n);
+    const int TX = ot / oty_n, TY = ot % oty_n;
+    const int X0 = TX << OT_SHIFT, Y0 = TY << OT_SHIFT;
+    Region R;
+    R.rx0 = max(X0 - FARMS_MAX_WINDOW, 0);
+    R.rx1 = min(X0 + OT - 1 + FARMS_MAX_WINDOW, W - 1);                       // src/vFlow.cpp:998
+    R.ry0 = max(Y0 - FARMS_MAX_WINDOW, 0);
+    const int jmax = min(min(Y0 + OT - 1, H - 1) + FARMS_MAX_WINDOW, W - 1);  // :1000 (sic: width - 1)
+    R.ry1 = min(jmax, H - 1);
+    // logical rows j in [H, 2H) alias pixel (i + 1, j - H); rows >= 2H are left to k_pool_any
+    R.ay1 = min(jmax, 2 * H - 1) - H;
+    R.ax0 = R.rx0 + 1;
+    R.ax1 = min(R.rx1 + 1, W - 1);
+    if (R.ax0 > R.ax1) R.ay1 = -1;
+    // index tiles (16x16) of the owner tile: 2 columns x 2 rows, clipped
+    const int itx0 = X0 >> 4, itx1 = min((X0 + OT - 1) >> 4, A.g.ntx - 1);
+    const int ity0 = Y0 >> 4, ity1 = min((Y0 + OT - 1) >> 4, nty - 1);
+    const int d_begin = seg * TK_SEG, d_end = min(d_begin + TK_SEG, A.nslabs);
+
+    // NSL consecutive slabs per round
+    for (int d = d_begin; d < d_end; d += NSL) {
+      const int nd = min(NSL, d_end - d);
+      // ---- targets of this round: flow events of the owner tile in slabs d .. d+nd-1 ----
+      uint32_t ta[NSL][2], tb[NSL][2], nraw[NSL];
+      uint32_t nraw_all = 0, nmax = 0;
+#pragma unroll
+      for (int w = 0; w < NSL; w++) {
+        nraw[w] = 0;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          ta[w][c] = tb[w][c] = 0;
+          if (w < nd && itx0 + c <= itx1) {
+            const size_t cb = (size_t)(d + w) * NT + (size_t)(itx0 + c) * nty;
+            ta[w][c] = A.cell_start[cb + ity0];
+            tb[w][c] = A.cell_start[cb + ity1 + 1];
+          }
+          nraw[w] += tb[w][c] - ta[w][c];
+        }
+        nraw_all += nraw[w];
+        nmax = max(nmax, nraw[w]);
+      }
+      if (nraw_all == 0) continue;  // uniform across the CTA
+      if (SECOND) {  // only rounds the first pass flagged do any work here
+        const uint32_t bits = A.item_ovf[item];
+        const int b0 = (d - d_begin) >> TK_OVF_SHIFT, b1 = (d + nd - 1 - d_begin) >> TK_OVF_SHIFT;
+        if (((bits >> b0) & ((2u << (b1 - b0)) - 1u)) == 0u) continue;
+      }
+
+      // ---- make sure the slabs of all windows of the round are staged ----
+      __syncthreads();  // the previous round is done with S.dlo / S.dhi / S.ovf
+      if (tid < NSL) {
+        const int dd = min(d + tid, d_end - 1);
+        const uint32_t t_first = A.slab_ids[dd] << A.g.slab_shift;
+        const uint32_t lo_id =
+            (t_first >= (uint32_t)(FARMS_KILL_OLD_FLOW_TIME - 1) ? t_first - (FARMS_KILL_OLD_FLOW_TIME - 1) : 0u) >> A.g.slab_shift;
+        int l = dd;
+        while (l > 0 && dd - l < TK_LB && A.slab_ids[l - 1] >= lo_id) l--;
+        S.dlo[tid] = l;
+        S.dhi[tid] = dd;
+      }
+      const uint32_t i_round = A.slab_first[d];
+      __syncthreads();
+      int s_first = 0x7fffffff, s_last = -1;
+#pragma unroll
+      for (int w = 0; w < NSL; w++) {
+        if (nraw[w]) {
+          s_first = min(s_first, S.dlo[w]);
+          s_last = max(s_last, S.dhi[w]);
+        }
+      }
+      // staged slabs are a contiguous range ending at the last staged slab, so what is missing is a suffix
+      int s_new = s_first;
+      while (s_new <= s_last && S.tag[s_new % (TK_LB + NSL)] == s_new) s_new++;  // uniform: tags are read after a barrier
+      if (s_new <= s_last) stage_slabs_packed<SM, WARPS, CAP, NSL>(A, S, s_new, s_last, R, i_round);
+      __syncthreads();
+      if (tid < NSL) {
+        int o = 0;
+        for (int s = S.dlo[tid]; s <= S.dhi[tid]; s++) o |= S.overflow[s % (TK_LB + NSL)];
+        S.ovf[tid] = o;
+        if (!SECOND && o && nraw[tid]) atomicOr(&A.item_ovf[item], 1u << ((d + tid - d_begin) >> TK_OVF_SHIFT));
+      }
+
+      for (uint32_t t0 = 0; t0 < nmax; t0 += TK_MAXT) {
+        __syncthreads();
+        if (tid < NSL) S.ntg[tid] = 0;
+        if (tid == 0) S.tnext = 0;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < NSL; w++)
+          for (uint32_t f = t0 + tid; f < min(nraw[w], t0 + TK_MAXT); f += THREADS) {
+            const uint32_t n0 = tb[w][0] - ta[w][0];
+            const uint32_t pos = f < n0 ? ta[w][0] + f : ta[w][1] + (f - n0);
+            const uint4 r = A.rec[pos];
+            const int yi = (int)(r.x >> 16);
+            // fast-path conditions: not a halo event, window rows stay below 2H, staging complete
+            const bool ok = (int)r.z >= A.h && min(yi + FARMS_MAX_WINDOW, W - 1) <= 2 * H - 1 && !S.ovf[w] &&
+                            (!SECOND || !A.done[pos]);
+            if (ok) S.tlist[w][atomicAdd(&S.ntg[w], 1u)] = pos;
+
+          }
+        __syncthreads();
+        // Tasks: first pairs of targets of the same slab (lanes 0-15 pool one event, lanes 16-31 the next; both
+        // halves share their loop bounds), then "solo" targets pooled by the two halves together, each half taking
+        // every other 64-record trip (half the time of a pair task).  The odd target of a slab is a solo, and so
+        // are the pairs that would not divide evenly among the warps when they are at most half a wave: the
+        // round then ends half a task later instead of a whole one.
+        // (Rounds of many slabs -- the sparse-stream variant -- keep the plain pairing: there an odd target shares
+        // its warp with an idle half.)
+        constexpr bool SOLOS = NSL <= 2;
+        uint32_t pstart[NSL + 1], sstart[NSL + 1], npair[NSL];
+        uint32_t P = 0;
+#pragma unroll
+        for (int w = 0; w < NSL; w++) {
+          npair[w] = SOLOS ? S.ntg[w] >> 1 : (S.ntg[w] + 1) >> 1;
+          P += npair[w];
+        }
+        uint32_t extra = SOLOS ? P % WARPS : 0u;
+        if (extra > WARPS / 2) extra = 0;
+#pragma unroll
+        for (int w = NSL - 1; w >= 0; w--) {
+          const uint32_t take = min(extra, npair[w]);
+          npair[w] -= take;
+          extra -= take;
+        }
+        pstart[0] = sstart[0] = 0;
+#pragma unroll
+        for (int w = 0; w < NSL; w++) {
+          pstart[w + 1] = pstart[w] + npair[w];
+          sstart[w + 1] = sstart[w] + (SOLOS ? S.ntg[w] - 2 * npair[w] : 0u);
+        }
+        const uint32_t tasks_p = pstart[NSL], tasks = tasks_p + sstart[NSL];
+
+        for (;;) {
+          uint32_t k = 0;
+          if (lane == 0) k = atomicAdd(&S.tnext, 1u);
+          k = __shfl_sync(0xffffffffu, k, 0);
+          if (k >= tasks) break;
+          const bool solo = k >= tasks_p;
+          int w = 0;
+          uint32_t kk;
+          if (!solo) {
+#pragma unroll
+            for (int q = 1; q < NSL; q++) w += (k >= pstart[q]) ? 1 : 0;
+            kk = (k - pstart[w]) * 2 + half;
+          } else {
+            const uint32_t j = k - tasks_p;
+#pragma unroll
+            for (int q = 1; q < NSL; q++) w += (j >= sstart[q]) ? 1 : 0;
+            kk = 2 * (pstart[w + 1] - pstart[w]) + (j - sstart[w]);
+          }
+          const uint32_t nt = S.ntg[w];
+          const bool have = solo ? half == 0 : kk < nt;  // this half owns a target's result
+          const uint32_t tpos = S.tlist[w][kk < nt ? kk : nt - 1];
+          const uint4 r = A.rec[tpos];
+          const int xi = (int)(r.x & 0xffffu), yi = (int)(r.x >> 16);
+          const uint32_t ii = r.z;
+          // the event's window in region coordinates; staged records all lie inside the sensor and inside the
+          // reference's row bound (width - 1, :1000), so "in the window" is |dx| <= 50 and |dy| <= 50
+          const uint32_t tw = (uint32_t)(xi - R.rx0) | ((uint32_t)(yi - R.ry0) << 8);
+#pragma unroll
+          for (int q = 0; q < FARMS_NSCALES; q++) S.acc[warp][q][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int sl = S.dlo[w], sh = S.dhi[w];
+          for (int s = sl; s <= sh; s++) {
+            const int slot = s % (TK_LB + NSL);
+            const int n = S.count[slot];
+            const uint32_t iir = ii - S.slot_base[slot];
+            const uint2 *recs = &S.ta[slot * STRIDE];
+            const float2 *pays = &S.pb[slot * STRIDE];
+            ncand += (sub == 0 && have) ? n : 0;
+            for (int q0 = sub + (solo ? 64 * half : 0); q0 < n; q0 += solo ? 128 : 64) {
+              uint2 c[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) c[u] = recs[q0 + 16 * u];  // padded (span 0): no bounds check
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const uint32_t d4 = __vabsdiffu4(c[u].x, tw);  // |dx| in byte 0, |dy| in byte 1
+                const uint32_t rel = __funnelshift_r(c[u].x, c[u].y, 16) & 0x00ffffffu;
+                // still the latest event of its pixel AND younger than 500 us  <=>  idx <= ii < end
+                const bool ok = (iir - rel) < (c[u].y >> 8) && ((d4 + 0x4d4du) & 0x8080u) == 0u;
+                if (ok) {
+                  const uint32_t m = max(d4 & 0xffu, (d4 >> 8) & 0xffu);
+                  const uint32_t ring = ((m + FARMS_WINDOW_JUMP - 1) * 205u) >> 10;  // /5 for values <= 54
+                  const float2 f = pays[q0 + 16 * u];
+                  float fl;
+                  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(fl) : "f"(f.x * f.x + f.y * f.y));
+                  float4 v = S.acc[warp][ring][lane];
+                  v.x += fl;
+                  v.y += f.x;
+                  v.z += f.y;
+                  v.w += 1.f;
+                  S.acc[warp][ring][lane] = v;
+                }
+              }
+            }
+          }
+          __syncwarp();
+          // sub-lane k < 11 of each half combines ring k's 16 per-lane partials: four at a time in FP32, the four
+          // group sums in FP64 (the counts are exact either way)
+          double rl = 0.0, rx = 0.0, ry = 0.0;
+          float rnf = 0.f;
+          if (sub < FARMS_NSCALES) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; q4++) {
+              float4 g = S.acc[warp][sub][(half << 4) | ((4 * q4 + sub) & 15)];
+#pragma unroll
+              for (int q = 1; q < 4; q++) {
+                const float4 v = S.acc[warp][sub][(half << 4) | ((4 * q4 + q + sub) & 15)];
+                g.x += v.x;
+                g.y += v.y;
+                g.z += v.z;
+                g.w += v.w;
+              }
+              rl += (double)g.x;
+              rx += (double)g.y;
+              ry += (double)g.z;
+              rnf += g.w;
+            }
+          }
+          __syncwarp();
+          if (solo) {  // the two halves pooled disjoint trips of the same target
+            rl += __shfl_xor_sync(0xffffffffu, rl, 16);
+            rx += __shfl_xor_sync(0xffffffffu, rx, 16);
+            ry += __shfl_xor_sync(0xffffffffu, ry, 16);
+            rnf += __shfl_xor_sync(0xffffffffu, rnf, 16);
+          }
+          const bool fin = finish_event_checked(A, sub, rl, rx, ry, (int)rnf, (int)ii - A.h, have);
+
+          if (sub == 0 && fin) {
+            A.done[tpos] = 1;
+            npooled++;
+          }
+          // ---- undecided targets (a rival scale within the FP32 noise, cancelling vectors): pool them again
+          // exactly, FP64 partials and the FP64 flow values of the contributors, one half-warp at a time
+          // (the FP64 partials of one target take the warp's whole accumulator space) ----
+          const unsigned need = __ballot_sync(0xffffffffu, have && !fin && sub == 0);
+          for (int hsel = 0; hsel < 2; hsel++) {
+            if (!((need >> (16 * hsel)) & 1u)) continue;  // uniform across the warp
+            __syncwarp();
+            double4 *dacc = reinterpret_cast<double4 *>(&S.acc[warp][0][0]);  // [ring][16 lanes] {len, lcx, lcy, n}
+            if (half == hsel) {
+#pragma unroll
+              for (int q = 0; q < FARMS_NSCALES; q++) dacc[q * 16 + sub] = make_double4(0.0, 0.0, 0.0, 0.0);
+              for (int s = sl; s <= sh; s++) {
+                const int slot = s % (TK_LB + NSL);
+                const int n = S.count[slot];
+                const uint32_t base = S.slot_base[slot], iir = ii - base;
+                for (int q0 = sub; q0 < n; q0 += 16) {
+                  const uint2 c = S.ta[slot * STRIDE + q0];
+                  const uint32_t d4 = __vabsdiffu4(c.x, tw);
+                  const uint32_t rel = __funnelshift_r(c.x, c.y, 16) & 0x00ffffffu;
+                  const bool ok = (iir - rel) < (c.y >> 8) && ((d4 + 0x4d4du) & 0x8080u) == 0u;
+                  if (ok) {
+                    const uint32_t mch = max(d4 & 0xffu, (d4 >> 8) & 0xffu);
+                    const int ring = (int)(((mch + FARMS_WINDOW_JUMP - 1) * 205u) >> 10);
+                    const uint32_t j = base + rel;
+                    double4 v = dacc[ring * 16 + sub];
+                    v.x += A.ev_len[j];
+                    v.y += A.ev_lcx[j];
+                    v.z += A.ev_lcy[j];
+                    v.w += 1.0;
+                    dacc[ring * 16 + sub] = v;
+                  }
+                }
+              }
+            }
+            __syncwarp();
+            double el = 0.0, ex2 = 0.0, ey2 = 0.0, en = 0.0;
+            if (half == hsel && sub < FARMS_NSCALES) {
+#pragma unroll 4
+              for (int q = 0; q < 16; q++) {
+                const double4 v = dacc[sub * 16 + ((q + sub) & 15)];
+                el += v.x;
+                ex2 += v.y;
+                ey2 += v.z;
+                en += v.w;
+              }
+            }
+            __syncwarp();
+            finish_event<16>(A, sub, el, ex2, ey2, en, A.ev_lcx[ii], A.ev_lcy[ii], (int)ii - A.h, half == hsel);
+            if (half == hsel && sub == 0) {
+              A.done[tpos] = 1;
+              npooled++;
+            }
+          }
+        }
+      }
+    }
+  }
+  if ((lane & 15) == 0 && ncand) atomicAdd(A.cand_count, ncand);
+  if ((lane & 15) == 0 && npooled) atomicAdd(A.path_count + (SECOND ? 1 : 0), (unsigned long long)npooled);
+}
+
+template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND>
+void launch_tile16(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
+  PoolArgs A = A0;
+  using SM = PackedSmem<WARPS, CAP, NSL>;
+  static_assert(sizeof(SM) <= (CTAS == 2 ? 115712 : 232448), "shared memory of the tile kernel: 227 KB per CTA, 228 KB per SM");
+  auto kern = k_pool_tile16<WARPS, CAP, NSL, CTAS, SECOND>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   const int otx = (A.g.W + OT - 1) >> OT_SHIFT, oty = (A.g.H + OT - 1) >> OT_SHIFT;
@@ -1998,10 +2352,11 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
                    const double *ev_len, const double *ev_lcx, const double *ev_lcy, int nslabs, PoolGeom g, int fast,
                    double flow_per_slab, double *global_r, double *global_theta, uint8_t *scale,
                    unsigned int *work_counter, unsigned long long *cand_count, int num_sms, cudaStream_t s,
-                   unsigned *kernels_used) {
+                   unsigned *kernels_used, const uint8_t *own_ok) {
   if (!m) return 0;
   int launches = 0;
   PoolArgs A;
+  A.own_ok = own_ok;
   A.path_count = cand_count + 1;
   A.rec = rec; A.pay = pay; A.cell_start = cell_start; A.slab_ids = slab_ids; A.done = done;
   A.slab_first = slab_first; A.fin = fin; A.item_ovf = item_ovf;
@@ -2017,6 +2372,18 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
     } else if (fast == 3) {
       launch_tile<16, 768, 4, 1, false>(A, nslabs, num_sms, s);  // 16 warps, 1 CTA per SM, ~222 KB
       if (kernels_used) *kernels_used |= FARMS_POOLK_TILE_ONE_CTA;
+    } else if (fast >= 5 && fast <= 7) {
+      // k_pool_tile on 16-byte packed records: 2 slabs per round with 640-record slots, 3 with 512, or 4 with 416
+      const double per_region = flow_per_slab * 17424.0 / ((double)g.W * (double)g.H);
+      if (per_region < 200.0) launch_tile16<8, 416, 4, 2, false>(A, nslabs, num_sms, s);
+      else if (fast == 5) launch_tile16<8, 640, 2, 2, false>(A, nslabs, num_sms, s);
+      else if (fast == 7) launch_tile16<8, 512, 3, 2, false>(A, nslabs, num_sms, s);
+      else launch_tile16<8, 416, 4, 2, false>(A, nslabs, num_sms, s);
+      if (kernels_used) *kernels_used |= per_region < 200.0 ? FARMS_POOLK_TILE16_SPARSE : FARMS_POOLK_TILE16_DENSE;
+      A.work_counter = work_counter + 2;
+      launch_tile16<16, 960, 4, 1, true>(A, nslabs, num_sms, s);
+      if (kernels_used) *kernels_used |= FARMS_POOLK_TILE16_SECOND;
+      launches++;
     } else if (fast == 4) {
       // two-phase kernel (k_pool_warp), same dense / sparse split and flagged second pass
       const double per_region = flow_per_slab * 17424.0 / ((double)g.W * (double)g.H);

@@ -19,15 +19,18 @@ IO_INPUT_ON_DEVICE, IO_OUTPUT_ON_DEVICE = 1, 2
 FLAG_DEBUG_DET = 1
 FLAG_EXACT_POOLING = 2
 FLAG_GENERIC_POOLING = FLAG_EXACT_POOLING
+FLAG_SERIAL_SEMANTICS = 4
 POOLK_TILE_DENSE, POOLK_TILE_SPARSE, POOLK_TILE_SECOND, POOLK_TILE_ONE_CTA, POOLK_BITS, POOLK_ANY = 1, 2, 4, 8, 16, 32
 POOLK_WARP_DENSE, POOLK_WARP_SPARSE, POOLK_WARP_SECOND = 64, 128, 256
-POOL_VARIANTS = {"tile": 1, "bits": 2, "tile1": 3, "warp": 4}
+POOLK_TILE16_DENSE, POOLK_TILE16_SPARSE, POOLK_TILE16_SECOND = 512, 1024, 2048
+POOL_VARIANTS = {"tile": 1, "bits": 2, "tile1": 3, "warp": 4, "tile16": 5, "tile16x4": 6, "tile16x3": 7}
 
 EXPORTS = [
     "farms_abi_version", "farms_create", "farms_destroy", "farms_reset", "farms_last_error", "farms_normalize_filtersize", "farms_get_params",
     "farms_process_host", "farms_process_device", "farms_num_events", "farms_get_timings", "farms_set_t0",
     "farms_state_export", "farms_state_fold", "farms_slice_surface", "farms_pack4_f32",
     "farms_slice_surface_host", "farms_state_fold_host",
+    "farms_host_alloc", "farms_host_free", "farms_host_register", "farms_host_unregister",
     "farms_comm_unique_id", "farms_comm_create", "farms_comm_destroy", "farms_comm_info", "farms_comm_process",
 ]
 

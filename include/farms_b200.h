@@ -51,8 +51,10 @@ typedef struct {
   uint32_t reorder_slack_us;/* extra history (us) kept across batch boundaries for streams whose
                                timestamps are not perfectly sorted; 0 = default (1000)            */
   /* Tuning / test selectors (0 = the library's own choice; never read from the environment): */
-  uint32_t pool_variant;    /* fast pooling kernel: 0/1 staged-list k_pool_tile, 2 bit-table k_pool_bits, 3 the
-                               one-CTA-per-SM instantiation of k_pool_tile, 4 two-phase k_pool_warp (all parity-tested) */
+  uint32_t pool_variant;    /* fast pooling kernel: 0 = default (7); 1 k_pool_tile (20-byte staged records, 2 slabs
+                               per round), 2 bit-table k_pool_bits, 3 k_pool_tile with one CTA per SM, 4 two-phase
+                               k_pool_warp, 5 / 6 / 7 k_pool_tile16 (16-byte packed records) with 2 / 4 / 3 slabs per
+                               round.  All are parity-tested against the oracle; 7 measured fastest.          */
   uint32_t fit_chunk;       /* events per plane-fit chunk (SAE snapshot interval); 0 = from the sensor size  */
   uint32_t slab_target;     /* flow events per (tile region, time slab) the slab length is chosen for; 0 = 70 */
   uint32_t reserved[4];
@@ -64,6 +66,14 @@ typedef struct {
                                          path keeps FP32 ring partials; its scale decisions are exact
                                          either way, see csrc/pooling.cu)                           */
 #define FARMS_FLAG_GENERIC_POOLING FARMS_FLAG_EXACT_POOLING
+#define FARMS_FLAG_SERIAL_SEMANTICS 4u /* the semantics of the reference's DEFAULT driver vFlowManager::run
+                                         (src/vFlow.cpp:465-826) instead of runFileCopy: the first event of the
+                                         stream only sets t0 -- it is not inserted into the surface of active events
+                                         and leaves its RAW timestamp as its pixel's lastEventTime (:531-558); and
+                                         lastEventTime[x][y] is written only AFTER pooling (:790), so an event's own
+                                         pixel is pooled with the time of the PREVIOUS event there (the own-flow
+                                         fallback of :1085-1094 becomes reachable).  Implies exact pooling.  The
+                                         reference computes these numbers but writes no file in that mode.        */
 
 /* Per-event results, structure of arrays, n entries each, caller-allocated.  Any pointer may be
  * NULL (that column is skipped).  Columns follow the reference's batch output row
@@ -116,6 +126,9 @@ typedef struct {
 #define FARMS_POOLK_WARP_DENSE 64u   /* k_pool_warp<8 warps, 480-record slots, 2 slabs per round, 2 CTAs/SM>  */
 #define FARMS_POOLK_WARP_SPARSE 128u /* k_pool_warp<8, 352, 4, 2>                                            */
 #define FARMS_POOLK_WARP_SECOND 256u /* k_pool_warp<16, 768, 4, 1>, flagged second pass                      */
+#define FARMS_POOLK_TILE16_DENSE 512u    /* k_pool_tile16 (16-byte packed staged records), dense streams      */
+#define FARMS_POOLK_TILE16_SPARSE 1024u  /* k_pool_tile16<8, 416, 4, 2>, thin slabs                           */
+#define FARMS_POOLK_TILE16_SECOND 2048u  /* k_pool_tile16<16, 960, 4, 1>, flagged second pass                 */
 
 /* ---- lifetime: replaces `vFlowManager vFlowM(...)` (src/main.cpp:186) ---- */
 int farms_create(farms_ctx **out, const farms_config *cfg);
@@ -177,6 +190,14 @@ int farms_state_fold_host(farms_ctx *ctx, const uint32_t *last_t, const uint8_t 
  * float4-per-event device buffer that goes over NVLink in a single NCCL gather. */
 int farms_pack4_f32(farms_ctx *ctx, const double *d_a, const double *d_b, const double *d_c, const double *d_d,
                     uint64_t n, float *d_out4);
+
+/* ---- pinned host memory for callers without CUDA of their own (the FARMS_Flow command line): with pinned buffers
+ * farms_process_host overlaps its host<->device copies with the kernels; pageable buffers work but serialise.
+ * farms_host_register pins memory the caller already owns (e.g. the text reader's malloc'ed arrays). ---- */
+void *farms_host_alloc(uint64_t bytes);            /* NULL on failure */
+void farms_host_free(void *p);
+int farms_host_register(void *p, uint64_t bytes);  /* FARMS_OK, or FARMS_ERR_CUDA (the buffer stays usable, pageable) */
+int farms_host_unregister(void *p);
 
 /* ---- time-sliced multi-GPU runs (no counterpart in the reference) --------------------------------
  * One farms_ctx per GPU -- one process per GPU, or one host thread per GPU -- joined into a farms_comm.  The recording

@@ -42,6 +42,9 @@ struct farms_oracle {
    * to compute_true_flow's.  A cell leaves the set when an event without flow overwrites it (vFlow.cpp:398-402)
    * or when its latest event is 500 us old, which is final only while timestamps are non-decreasing: the first
    * decreasing timestamp switches the oracle back to the plain scan for good. */
+  /* ---- serial mode (farms_oracle_set_serial): the semantics of vFlowManager::run, vFlow.cpp:465-826 ---- */
+  int serial;
+  uint64_t events_seen;
   int fast;
   uint32_t tmax;
   uint64_t seq;
@@ -127,6 +130,12 @@ int farms_oracle_set_fast(farms_oracle *o, int on) {
 }
 
 int farms_oracle_is_fast(const farms_oracle *o) { return o ? o->fast : 0; }
+
+int farms_oracle_set_serial(farms_oracle *o, int on) {
+  if (!o || o->events_seen) return -1;
+  o->serial = on ? 1 : 0;
+  return 0;
+}
 
 void farms_oracle_state(const farms_oracle *o, double *last_time, uint8_t *hit, double *len,
                         double *theta) {
@@ -495,7 +504,31 @@ int farms_oracle_process(farms_oracle *o, const int32_t *X, const int32_t *Y, co
       o->t0 = T[e];
       o->have_t0 = 1;
     }
-    uint32_t time_ = T[e] - o->t0; /* :241 (unsigned wrap) */
+    if (o->serial && o->events_seen == 0) {
+      /* vFlow.cpp:531-558: the first line only sets t0; its pixel's lastEventTime keeps the RAW timestamp, the
+       * event enters neither the surface of active events nor the flow surfaces, and no flow is computed */
+      o->events_seen = 1;
+      o->last_time[(size_t)x * H + y] = (double)T[e];
+      if (out) {
+        if (out->t_rel) out->t_rel[e] = 0;
+        if (out->pol) out->pol[e] = POL[e] < 0 ? 0 : POL[e];
+        if (out->global_r) out->global_r[e] = 0;
+        if (out->global_theta) out->global_theta[e] = 0;
+        if (out->vx) out->vx[e] = 0;
+        if (out->vy) out->vy[e] = 0;
+        if (out->local_r) out->local_r[e] = 0;
+        if (out->local_theta) out->local_theta[e] = 0;
+        if (out->scale) out->scale[e] = 0;
+        if (out->valid) out->valid[e] = 0;
+        if (out->best_window) out->best_window[e] = -1;
+        if (out->inliers) out->inliers[e] = 0;
+        if (out->det) out->det[e] = NAN;
+      }
+      continue;
+    }
+    o->events_seen++;
+    uint32_t time_ = T[e] - o->t0; /* :241 / :570 (unsigned wrap) */
+    if (o->serial) o->fast = 0; /* the filter assumes lastEventTime is written before pooling */
     if (o->fast) {
       if (time_ < o->tmax) o->fast = 0; /* timestamps decreased: the filter's expiry is no longer final */
       else o->tmax = time_;
@@ -507,8 +540,8 @@ int farms_oracle_process(farms_oracle *o, const int32_t *X, const int32_t *Y, co
     cur.x = x;
     cur.y = y;
     cur.t = (double)time_;
-    o->last_time[f] = (double)time_; /* :264 */
-    o->sae[f] = cur;                 /* :267 */
+    if (!o->serial) o->last_time[f] = (double)time_; /* :264; the serial loop only does it after pooling (:790) */
+    o->sae[f] = cur;                 /* :267 / :595-610 (cSurf = surfaceOfL) */
     o->hit[f] = 1;
 
     double vx, vy, det;

@@ -54,6 +54,16 @@ void farms_oracle_destroy(farms_oracle *o);
 int farms_oracle_set_fast(farms_oracle *o, int on);
 int farms_oracle_is_fast(const farms_oracle *o);
 
+/* Serial mode (call before the first event): the semantics of the reference's DEFAULT driver vFlowManager::run
+ * (vFlow.cpp:465-826) instead of runFileCopy.  Differences: the first event only sets t0 -- it is
+ * not inserted into the surface of active events and leaves its RAW timestamp in lastEventTime (:531-558); and
+ * lastEventTime[x][y] is updated only AFTER pooling (:790), so an event's own pixel is pooled with the time of the
+ * PREVIOUS event there (the fallback of :1085-1094 becomes reachable).  The reference writes no file in this
+ * mode (:487-489, 727-765), so these are the outputs it computes but never emits: PARITY UNPINNED for this mode
+ * (nothing of the reference's can be compared); the restatement shares every function with the batch mode.
+ * The `numEvents + 1` loop bound (:565) and the filesize/18 cap (:511) are file-level and live in the CLI. */
+int farms_oracle_set_serial(farms_oracle *o, int on);
+
 /* Process n more events in order.  State persists between calls; t0 is the first timestamp ever
  * seen (vFlow.cpp:194).  Returns 0, or -1 if an event lies outside the sensor. */
 int farms_oracle_process(farms_oracle *o, const int32_t *x, const int32_t *y, const uint32_t *t,

@@ -34,12 +34,13 @@ def oracle_lib():
         L.farms_oracle_state.argtypes = [C.c_void_p] * 5
         L.farms_oracle_set_fast.argtypes = [C.c_void_p, C.c_int]
         L.farms_oracle_is_fast.argtypes = [C.c_void_p]
+        L.farms_oracle_set_serial.argtypes = [C.c_void_p, C.c_int]
         _olib = L
     return _olib
 
 
 class Oracle:
-    def __init__(self, width, height, filtersize, inlier_check, fast=False):
+    def __init__(self, width, height, filtersize, inlier_check, fast=False, serial=False):
         """fast=True: the oracle's filtered pooling walk (oracle/farms_oracle.h: bit-identical outputs, ~10-20x
         faster on dense streams; the plain scan stays the witness it is checked against)."""
         self._h = oracle_lib().farms_oracle_create(width, height, filtersize, inlier_check)
@@ -47,6 +48,8 @@ class Oracle:
         self.npx = width * height
         if fast:
             assert oracle_lib().farms_oracle_set_fast(self._h, 1) == 0
+        if serial:
+            assert oracle_lib().farms_oracle_set_serial(self._h, 1) == 0
 
     def is_fast(self):
         return bool(oracle_lib().farms_oracle_is_fast(self._h))
@@ -78,8 +81,8 @@ class Oracle:
         return lt, hit
 
 
-def run_oracle(width, height, filtersize, inlier_check, x, y, t, p=None, fast=False):
-    return Oracle(width, height, filtersize, inlier_check, fast=fast).process(x, y, t, p)
+def run_oracle(width, height, filtersize, inlier_check, x, y, t, p=None, fast=False, serial=False):
+    return Oracle(width, height, filtersize, inlier_check, fast=fast, serial=serial).process(x, y, t, p)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -234,6 +234,7 @@ def test_cli_time_sliced_over_several_contexts_equals_one_run(tmp_path, monkeypa
     for b in (base1, base3):
         np.savetxt(b + ".txt", arr, fmt="%d")
     common = ["--width", str(s.width), "--height", str(s.height), "--filtersize", str(s.filtersize)]
+    common += ["--SERIAL", "0"]
     r1 = subprocess.run([CLI] + common + ["--filename", base1], capture_output=True, text=True)
     assert r1.returncode == 0, r1.stderr
     r3 = subprocess.run([CLI] + common + ["--filename", base3, "--gpus", "3", "--same-device", "1"],

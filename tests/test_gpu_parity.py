@@ -120,7 +120,7 @@ def test_fast_pooling_equals_exact_pooling_on_long_dense_streams(config, n, star
     assert np.array_equal(fast["global_r"][~v], exact["global_r"][~v])
 
 
-@pytest.mark.parametrize("impl", ["bits", "tile1", "warp", "tile"])
+@pytest.mark.parametrize("impl", ["bits", "tile1", "warp", "tile", "tile16", "tile16x4", "tile16x3"])
 def test_alternative_pooling_kernels_match_oracle_and_exact_kernel(impl):
     """k_pool_bits (farms_config.pool_variant 2: prefix bit tables over the staged records, a measured alternative
     to the default staged-list kernel) and the one-CTA-per-SM instantiation of k_pool_tile (variant 3) obey the same
@@ -131,7 +131,10 @@ def test_alternative_pooling_kernels_match_oracle_and_exact_kernel(impl):
     assert_parity(rep)
     want = {"bits": farms_b200.POOLK_BITS, "tile1": farms_b200.POOLK_TILE_ONE_CTA,
             "warp": farms_b200.POOLK_WARP_DENSE | farms_b200.POOLK_WARP_SPARSE,
-            "tile": farms_b200.POOLK_TILE_DENSE | farms_b200.POOLK_TILE_SPARSE}[impl]
+            "tile": farms_b200.POOLK_TILE_DENSE | farms_b200.POOLK_TILE_SPARSE,
+            "tile16": farms_b200.POOLK_TILE16_DENSE | farms_b200.POOLK_TILE16_SPARSE,
+            "tile16x4": farms_b200.POOLK_TILE16_DENSE | farms_b200.POOLK_TILE16_SPARSE,
+            "tile16x3": farms_b200.POOLK_TILE16_DENSE | farms_b200.POOLK_TILE16_SPARSE}[impl]
     assert f.timings()["pool_kernels"] & want
     s, x, y, t, p = synth_stream(4, 2_000_000, 2000)
     fast = farms_b200.Farms(s.width, s.height, s.filtersize, 5, pool_variant=impl).process(x, y, t)
@@ -171,6 +174,11 @@ LONG = [
     # config, events, pooling variant, first-pass kernel the stream must exercise
     (4, 2_000_000, "tile", "POOLK_TILE_DENSE"),  # (no slot overflows on this stream: the dense test below has them)
     (4, 2_000_000, "warp", "POOLK_WARP_DENSE"),
+    (4, 2_000_000, 0, "POOLK_TILE16_DENSE"),      # the library's default = what bench.py times (tile16x3)
+    (4, 2_000_000, "tile16", "POOLK_TILE16_DENSE"),
+    (4, 2_000_000, "tile16x4", "POOLK_TILE16_DENSE"),
+    (3, 2_000_000, 0, None),
+    (2, 1_000_000, 0, None),
     (3, 2_000_000, "tile", None),
     (3, 2_000_000, "warp", None),
     (2, 1_000_000, "tile", None),
@@ -208,7 +216,7 @@ def test_steady_state_parity_with_the_oracle(config, n, variant, first):
         assert tm["pool_kernels"] & getattr(farms_b200, first), tm
 
 
-@pytest.mark.parametrize("variant", ["tile", "warp"])
+@pytest.mark.parametrize("variant", ["tile", "warp", "tile16x4", "tile16x3"])
 def test_dense_stream_second_pass_and_general_kernel_against_the_oracle(variant):
     """Time-compressed 1280x720 stream (2.5x the density): the 512-record slots of the first pass overflow for a
     good share of the rounds, so the flagged second pass <16,768,4,1> and k_pool_any both pool a substantial number
@@ -224,13 +232,15 @@ def test_dense_stream_second_pass_and_general_kernel_against_the_oracle(variant)
     rep["timings"] = {k: tm[k] for k in ("pool_kernels", "pool_events_first", "pool_events_second", "pool_events_general")}
     print(json.dumps(rep))
     assert_parity(rep)
-    dense, second = ((farms_b200.POOLK_TILE_DENSE, farms_b200.POOLK_TILE_SECOND) if variant == "tile" else
-                     (farms_b200.POOLK_WARP_DENSE, farms_b200.POOLK_WARP_SECOND))
+    dense, second = {"tile": (farms_b200.POOLK_TILE_DENSE, farms_b200.POOLK_TILE_SECOND),
+                     "warp": (farms_b200.POOLK_WARP_DENSE, farms_b200.POOLK_WARP_SECOND),
+                     "tile16x4": (farms_b200.POOLK_TILE16_DENSE, farms_b200.POOLK_TILE16_SECOND),
+                     "tile16x3": (farms_b200.POOLK_TILE16_DENSE, farms_b200.POOLK_TILE16_SECOND)}[variant]
     assert tm["pool_kernels"] & dense and tm["pool_kernels"] & second
     assert tm["pool_events_second"] > 1000, tm
 
 
-@pytest.mark.parametrize("variant", ["tile", "warp"])
+@pytest.mark.parametrize("variant", ["tile", "warp", "tile16x4", 0])
 @pytest.mark.parametrize("w,h", [(20, 160), (48, 256), (33, 300)])
 def test_tall_sensors_fast_path(w, h, variant):
     """height >= width + 100: the reference bounds window rows by width-1 (src/vFlow.cpp:1000), so owner tiles
@@ -248,5 +258,26 @@ def test_tall_sensors_fast_path(w, h, variant):
     assert_parity(rep)
     tm = f.timings()
     assert tm["pool_kernels"] & (farms_b200.POOLK_TILE_DENSE | farms_b200.POOLK_TILE_SPARSE |
-                                 farms_b200.POOLK_WARP_DENSE | farms_b200.POOLK_WARP_SPARSE)
+                                 farms_b200.POOLK_WARP_DENSE | farms_b200.POOLK_WARP_SPARSE |
+                                 farms_b200.POOLK_TILE16_DENSE | farms_b200.POOLK_TILE16_SPARSE)
     assert tm["pool_events_first"] > 0
+
+
+@pytest.mark.parametrize("config,n,max_batch", [(1, 30000, 0), (3, 60000, 17000), (4, 150000, 0)])
+def test_serial_semantics_match_the_oracle_serial_mode(config, n, max_batch):
+    """FARMS_FLAG_SERIAL_SEMANTICS = the reference's default driver vFlowManager::run (src/vFlow.cpp:465-826): first
+    event only sets t0 (raw time left in lastEventTime), lastEventTime written after pooling.  The reference writes
+    nothing in that mode, so the check is against the oracle's restatement of it (parity unpinned for this mode)."""
+    import farms_b200
+    s, x, y, t, p = synth_stream(config, n, 0)
+    ref = run_oracle(s.width, s.height, s.filtersize, 5, x, y, t, p, serial=True)
+    f = farms_b200.Farms(s.width, s.height, s.filtersize, 5, flags=farms_b200.FLAG_SERIAL_SEMANTICS, max_batch=max_batch)
+    got = f.process(x, y, t)
+    rep = compare(got, ref, f"cfg{config} serial semantics")
+    print(json.dumps(rep))
+    assert rep["valid_ref"] > 1000
+    assert_parity(rep)
+    assert got["valid"][0] == 0 and got["best_window"][0] == -1
+    # and it really is a different computation from the batch semantics
+    batch = run_oracle(s.width, s.height, s.filtersize, 5, x, y, t, p)
+    assert np.count_nonzero(batch["global_r"] != ref["global_r"]) > 100

@@ -161,3 +161,73 @@ def test_fast_oracle_mode_on_aliasing_shapes():
         fast = run_oracle(w, h, 5, 5, x, y, t, p, fast=True)
         for k in slow:
             assert np.array_equal(slow[k].view(np.uint8), fast[k].view(np.uint8)), (w, h, k)
+
+
+def _pool_numpy(w, h, x, y, t_rel, lr, lth, valid, serial, first_raw_t=None):
+    """Independent numpy restatement of computeTrueFlow over per-event local flows (vFlow.cpp:952-1094), in the
+    batch or the serial update order of lastEventTime.  Small streams only."""
+    length = np.zeros((w * h,))
+    theta = np.zeros((w * h,))
+    last = np.zeros((w * h,))
+    out_r, out_th, out_scale = np.zeros(len(x)), np.zeros(len(x)), np.zeros(len(x), np.int32)
+    npx = w * h
+    for e in range(len(x)):
+        f = int(x[e]) * h + int(y[e])
+        if serial and e == 0:
+            last[f] = first_raw_t
+            continue
+        te = float(t_rel[e])
+        if not serial:
+            last[f] = te
+        if valid[e]:
+            length[f], theta[f] = lr[e], lth[e]
+            best, bestv = 0.0, None
+            for k, s in enumerate(range(0, 51, 5)):
+                sl = sx = sy = n = 0.0
+                for i in range(max(0, x[e] - s), min(x[e] + s, w - 1) + 1):
+                    for j in range(max(0, y[e] - s), min(y[e] + s, w - 1) + 1):
+                        g = i * h + j
+                        if g >= npx:
+                            continue
+                        if length[g] > 0 and abs(te - last[g]) < 500:
+                            sl += length[g]
+                            sx += length[g] * np.cos(theta[g])
+                            sy += length[g] * np.sin(theta[g])
+                            n += 1
+                if n > 0 and sl / n > best:
+                    best, bestv = sl / n, (sx / n, sy / n, s)
+            if bestv is None:
+                bestv = (length[f] * np.cos(theta[f]), length[f] * np.sin(theta[f]), 0)
+            out_r[e] = np.hypot(bestv[0], bestv[1])
+            out_th[e] = np.arctan2(bestv[1], bestv[0])
+            out_scale[e] = bestv[2]
+        else:
+            length[f] = theta[f] = 0.0
+        last[f] = te
+    return out_r, out_th, out_scale
+
+
+@pytest.mark.parametrize("serial", [False, True])
+def test_serial_mode_of_the_oracle_against_an_independent_pooling(serial):
+    """vFlowManager::run semantics (vFlow.cpp:465-826): first event only sets t0 and leaves its raw timestamp in
+    lastEventTime; lastEventTime is written after pooling.  The oracle's serial mode is checked against a numpy
+    restatement of the pooling fed with the oracle's own per-event local flows."""
+    from helpers import Oracle
+    w, h = 40, 30
+    x, y, t, p = sweeps(w, h, slopes=((25, 9), (-6, 9)), jitter=2, gap=120)
+    n = 700
+    x, y, t, p = x[:n], y[:n], t[:n], p[:n]
+    r = Oracle(w, h, 5, 5, serial=serial).process(x, y, t, p)
+    if serial:
+        assert r["valid"][0] == 0 and r["t_rel"][0] == 0 and r["best_window"][0] == -1
+    gr, gth, sc = _pool_numpy(w, h, x, y, r["t_rel"], r["local_r"], r["local_theta"], r["valid"], serial, float(t[0]))
+    v = r["valid"].astype(bool)
+    assert v.sum() > 200
+    assert np.allclose(r["global_r"][v], gr[v], rtol=1e-12)
+    assert np.allclose(r["global_theta"][v], gth[v], atol=1e-12)
+    assert np.array_equal(r["scale"][v], sc[v])
+    if serial:
+        # the serial order changes results: events whose pixel was last hit more than 500 us ago do not pool themselves
+        b = Oracle(w, h, 5, 5).process(x, y, t, p)
+        both = v & b["valid"].astype(bool)
+        assert np.count_nonzero(r["global_r"][both] != b["global_r"][both]) > 10

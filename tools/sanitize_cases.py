@@ -30,7 +30,7 @@ def build(case):
         s = Synth(1)
         x, y, t, p = s.first(25_000, 0)
         return s.width, s.height, s.filtersize, x, y, t, {}
-    if case in ("bits", "tile1"):
+    if case in ("bits", "tile1", "tile", "warp", "tile16", "tile16x4"):
         s = Synth(2)
         x, y, t, p = s.first(100_000, 0)
         return s.width, s.height, s.filtersize, x, y, squeeze(t, 4.0), {"pool_variant": case}
