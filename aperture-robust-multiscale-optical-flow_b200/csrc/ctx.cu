@@ -531,6 +531,12 @@ int farms_process_impl(farms_ctx *c, const uint16_t *x, const uint16_t *y, const
   tm.pool_candidates = counters[1];
   tm.pool_kernels = c->pool_kernels;
   for (int k = 0; k < 3; k++) tm.pool_events[k] = counters[2 + k];
+#ifdef FARMS_CHECKED
+  {
+    const unsigned int a = farms_chk_index(s), b = farms_chk_planefit(s), d = farms_chk_pooling(s);
+    if (a | b | d) return fail(c, FARMS_ERR_STATE, "self-check failed: index %u, plane fit %u, pooling %u (csrc/*.cu FARMS_CHK codes)", a, b, d);
+  }
+#endif
   return FARMS_OK;
 }
 
@@ -540,6 +546,14 @@ namespace {
 extern "C" {
 
 int farms_abi_version(void) { return FARMS_B200_ABI_VERSION; }
+
+int farms_build_is_checked(void) {
+#ifdef FARMS_CHECKED
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 int farms_normalize_filtersize(int fs, int32_t *radius, int32_t *plane_size) {
   if (fs < 5) fs = 3;        // src/vFlow.cpp:33

@@ -31,6 +31,23 @@
 // dense slabs a 500-us window can reach back from the slab of its event, at most: ceil(499 / 128)
 #define FARMS_SLAB_LOOKBACK 4
 
+// ---- self-checking build (make checked -> libfarms_b200_checked.so, -DFARMS_CHECKED) ----
+// compute-sanitizer is closed on the B200 pool this was developed on, so the index arithmetic of the kernels carries
+// its own bounds checks: FARMS_CHK records the first violated check (a code per site) in a per-file device word
+// instead of making the access; farms_process_* then fails with FARMS_ERR_STATE naming the code.  Compiled out of
+// the product build.
+#ifdef FARMS_CHECKED
+#define FARMS_CHK_DECL static __device__ unsigned int g_farms_chk[2];
+#define FARMS_CHK(cond, code) ((cond) ? true : (atomicCAS(&g_farms_chk[0], 0u, (unsigned int)(code)), false))
+#else
+#define FARMS_CHK_DECL
+#define FARMS_CHK(cond, code) (true)
+#endif
+// first failed check of each kernel file (0 = none), clearing it; only meaningful in the checked build
+unsigned int farms_chk_pooling(cudaStream_t s);
+unsigned int farms_chk_planefit(cudaStream_t s);
+unsigned int farms_chk_index(cudaStream_t s);
+
 struct FitParams {
   int W, H, r, P, min_inl;
 };

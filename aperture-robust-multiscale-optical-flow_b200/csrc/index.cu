@@ -9,6 +9,8 @@
 
 namespace {
 
+FARMS_CHK_DECL
+
 __global__ void k_ingest(const uint16_t *__restrict__ x, const uint16_t *__restrict__ y,
                          const uint64_t *__restrict__ t, uint64_t t0, size_t n, int W, int H,
                          uint16_t *__restrict__ ex, uint16_t *__restrict__ ey, uint32_t *__restrict__ et,
@@ -46,6 +48,7 @@ __global__ void k_links(const uint32_t *__restrict__ skeys, const uint32_t *__re
   if (s >= m) return;
   const uint32_t key = skeys[s];
   const uint32_t j = svals[s];
+  if (!FARMS_CHK((size_t)j < m && (s == 0 || skeys[s - 1] <= key), 301)) return;  // sorted by pixel, indices in range
   int2 pp;
   if (s > 0 && skeys[s - 1] == key) {
     uint32_t pj = svals[s - 1];
@@ -171,4 +174,17 @@ void launch_slice_surface(const uint16_t *x, const uint16_t *y, const uint64_t *
 void launch_unpack_surface(const unsigned long long *packed, size_t npx, uint32_t *last_t, uint8_t *hit,
                            cudaStream_t s) {
   k_unpack_surface<<<nb(npx, 256), 256, 0, s>>>(packed, npx, last_t, hit);
+}
+
+unsigned int farms_chk_index(cudaStream_t s) {
+#ifdef FARMS_CHECKED
+  unsigned int v[2] = {0, 0}, z[2] = {0, 0};
+  cudaMemcpyFromSymbolAsync(v, g_farms_chk, sizeof v, 0, cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  if (v[0]) cudaMemcpyToSymbolAsync(g_farms_chk, z, sizeof z, 0, cudaMemcpyHostToDevice, s);
+  return v[0];
+#else
+  (void)s;
+  return 0;
+#endif
 }

@@ -12,6 +12,8 @@
 
 namespace {
 
+FARMS_CHK_DECL
+
 #define MAXSTAMP_D 4294967296.0  // include/vFlow.h:27
 #define TSTOSEC_D 1e-6           // include/vFlow.h:28
 
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(256) k_fit_gather(const uint2 *__restrict__ sa
       int j = (int)cell[a].y;
       uint32_t tv = cell[a].x;
       while (j > i) {  // later events of this chunk: step back along the pixel's history
+        if (!FARMS_CHK(j < i1, 201)) break;  // a surface index beyond the chunk would be a stale snapshot
         const int2 pp = prevp[j];
         j = pp.x;
         tv = (uint32_t)pp.y;
@@ -344,6 +347,7 @@ __global__ void __launch_bounds__(256) k_fit_gather(const uint2 *__restrict__ sa
   const int brel = b - ob;
   const bool mine = live && best >= 0 && brel >= 0 && brel < N1;
   uint32_t *rec = recs + (size_t)gid * WORDS;
+  (void)FARMS_CHK(!live || (gid >= 0 && i0 + gid < i1), 202);
   unsigned long long hm = 0ull;
 #pragma unroll
   for (int k = 0; k < N1; k++) {
@@ -562,4 +566,17 @@ void launch_sae_export(const uint2 *sae, size_t npx, uint32_t *last_t, uint8_t *
 
 void launch_sae_fold(uint2 *sae, size_t npx, const uint32_t *last_t, const uint8_t *hit, cudaStream_t s) {
   k_sae_fold<<<nb(npx, 256), 256, 0, s>>>(sae, npx, last_t, hit);
+}
+
+unsigned int farms_chk_planefit(cudaStream_t s) {
+#ifdef FARMS_CHECKED
+  unsigned int v[2] = {0, 0}, z[2] = {0, 0};
+  cudaMemcpyFromSymbolAsync(v, g_farms_chk, sizeof v, 0, cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  if (v[0]) cudaMemcpyToSymbolAsync(g_farms_chk, z, sizeof z, 0, cudaMemcpyHostToDevice, s);
+  return v[0];
+#else
+  (void)s;
+  return 0;
+#endif
 }

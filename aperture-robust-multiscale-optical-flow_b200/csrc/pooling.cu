@@ -35,6 +35,8 @@
 
 namespace {
 
+FARMS_CHK_DECL
+
 // ------------------------------------------------------------------------------------------------
 // index construction
 // ------------------------------------------------------------------------------------------------
@@ -155,7 +157,7 @@ __device__ __forceinline__ void finish_event(const PoolArgs &A, int lane, double
   const int srcl = bk < 0 ? 0 : bk;
   const double wx = __shfl_sync(0xffffffffu, myx, srcl, WIDTH), wy = __shfl_sync(0xffffffffu, myy, srcl, WIDTH),
                wn = __shfl_sync(0xffffffffu, myn, srcl, WIDTH);
-  if (lane == 0 && write) {
+  if (lane == 0 && write && FARMS_CHK(out_index >= 0 && (size_t)out_index < A.m - (size_t)A.h, 122)) {
     double bvx, bvy;
     if (bk < 0) {  // :1085-1094 fallback: the event's own flow
       bvx = own_cx;
@@ -249,6 +251,7 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
             const size_t cb = (size_t)d * NT + (size_t)tx * nty;
             const uint32_t s = A.cell_start[cb + tylo], e = A.cell_start[cb + tyhi + 1];
             ncand += (lane == 0) ? (e - s) : 0;
+            (void)FARMS_CHK(cb + tyhi + 1 <= A.ncells && e >= s && e <= mi, 131);
             for (uint32_t p = s + lane; p < e; p += 32) {
               const uint4 c = A.rec[p];
               const int cx = (int)(c.x & 0xffffu), cy = (int)(c.x >> 16);
@@ -260,6 +263,7 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
               if (ok) {
                 const int dx = abs(cx - k - xi), dy = abs(cy + k * H - yi);
                 const int ring = (max(dx, dy) + FARMS_WINDOW_JUMP - 1) / FARMS_WINDOW_JUMP;
+                (void)FARMS_CHK(ring >= 0 && ring < FARMS_NSCALES, 132);
                 acc[warp][0][ring][lane] += pay_len[p];
                 acc[warp][1][ring][lane] += pay_cx[p];
                 acc[warp][2][ring][lane] += pay_cy[p];
@@ -334,10 +338,18 @@ struct TileSmem {
   unsigned int ntg[NSL], tnext, item;
 };
 
+struct Region;
+[[maybe_unused]] __device__ __forceinline__ bool xi_in_region(uint32_t xy, const Region &R);
+
 struct Region {  // pixels an owner tile can reach, as physical rectangles
   int rx0, rx1, ry0, ry1;  // rows < H (k = 0)
   int ax0, ax1, ay1;       // aliased part (k = 1): physical x in [ax0, ax1], y in [0, ay1]; empty if ay1 < 0
 };
+
+[[maybe_unused]] __device__ __forceinline__ bool xi_in_region(uint32_t xy, const Region &R) {  // (checked build) a target lies in its tile
+  const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
+  return x >= R.rx0 && x <= R.rx1 && y >= R.ry0;
+}
 
 // Stage the flow events of the dense slabs s0 .. s1 inside region R into their ring slots (slab s -> slot
 // s mod ring) in ONE pass over the concatenation of their index runs, preserving index order inside every slab
@@ -556,7 +568,7 @@ __device__ __forceinline__ bool finish_event_checked(const PoolArgs &A, int sub,
   // mean vector much shorter than the mean length: the FP32 sums cancelled, let the exact path do it
   const double bl = (double)best * (double)bn;
   safe = safe && (wx * wx + wy * wy) > 1e-4 * bl * bl;
-  if (sub == 0 && safe) {
+  if (sub == 0 && safe && FARMS_CHK(out_index >= 0 && (size_t)out_index < A.m - (size_t)A.h, 121)) {
     // k_pool_finish divides by the count and takes sqrt / atan2 (src/vFlow.cpp:365-366)
     A.global_r[out_index] = wx;
     A.global_theta[out_index] = wy;
@@ -910,6 +922,9 @@ void launch_tile(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
 // Staged records are 16 bytes instead of 20 (coordinates relative to the tile's region in one byte each, the index
 // relative to the slab's first event in 24 bits, the life span in 24 bits; a slab that does not fit 24 bits is
 // flagged as overflowed and left to the exact path), so the queues cost no slot capacity.
+#ifndef FARMS_SOLOS_MAX_NSL
+#define FARMS_SOLOS_MAX_NSL 3
+#endif
 constexpr int WQ_DEPTH = 32;   // queue entries per lane before a drain is forced
 constexpr int WP_PAD = 32;     // zeroed test records behind a slot's last record (span 0 never passes)
 
@@ -944,18 +959,22 @@ __device__ void stage_slabs_packed(const PoolArgs &A, SM &S, int s0, int s1, con
   const int nrun = nrun0 + nrun1;
   const int nsl = s1 - s0 + 1, nruns = nsl * nrun;
   __syncthreads();  // previous users of the run tables, of wcount and of these slots are done
+  (void)FARMS_CHK(nsl >= 1 && nsl <= RING && nrun <= TK_MAXRUN && s0 >= 0 && s1 < A.nslabs, 103);
   for (int q = tid; q < nruns; q += THREADS) {
     const int sl = q / nrun, c = q - sl * nrun;
     uint32_t a, b;
     if (c < nrun0) {
       const size_t cb = (size_t)(s0 + sl) * NT + (size_t)(tx0 + c) * nty;
+      (void)FARMS_CHK(cb + ty1 + 1 <= A.ncells && ty0 <= ty1 + 1, 104);
       a = A.cell_start[cb + ty0];
       b = A.cell_start[cb + ty1 + 1];
     } else {
       const size_t cb = (size_t)(s0 + sl) * NT + (size_t)(atx0 + c - nrun0) * nty;
+      (void)FARMS_CHK(cb + (R.ay1 >> ts) + 1 <= A.ncells, 105);
       a = A.cell_start[cb];
       b = A.cell_start[cb + (R.ay1 >> ts) + 1];
     }
+    (void)FARMS_CHK(b >= a, 106);
     S.run_s[q] = a;
     S.run_o[q + 1] = b - a;  // lengths first, offsets below
     S.run_info[q] = (uint8_t)(sl | (c >= nrun0 ? 0x80 : 0));
@@ -1016,11 +1035,13 @@ __device__ void stage_slabs_packed(const PoolArgs &A, SM &S, int s0, int s1, con
         }
         lo_hint = lo;
         const uint32_t pos = S.run_s[lo] + (f - S.run_o[lo]);
-        rec[e] = A.rec[pos];
-        cxv[e] = pay_cx[pos];
-        cyv[e] = pay_cy[pos];
-        info[e] = S.run_info[lo];
-        pass[e] = true;
+        if (FARMS_CHK(lo >= 0 && lo < nruns && pos < A.cell_start[A.ncells], 101)) {
+          rec[e] = A.rec[pos];
+          cxv[e] = pay_cx[pos];
+          cyv[e] = pay_cy[pos];
+          info[e] = S.run_info[lo];
+          pass[e] = true;
+        }
       }
     }
 #pragma unroll
@@ -1069,8 +1090,11 @@ __device__ void stage_slabs_packed(const PoolArgs &A, SM &S, int s0, int s1, con
         const int slot = (s0 + sl) % RING;
         const uint32_t rel = rec[e].z - S.slot_base[slot], span = rec[e].w - rec[e].z;
         if ((rel | span) >> 24) S.overflow[slot] = 1;  // does not fit the packed record: leave the slab to the exact path
-        S.ta[slot * STRIDE + o] = make_uint2(rec[e].x | (rel << 16), ((rel >> 16) & 0xffu) | (span << 8));
-        S.pb[slot * STRIDE + o] = make_float2(__double2float_rn(cxv[e]), __double2float_rn(cyv[e]));
+        if (FARMS_CHK(slot >= 0 && slot < RING && (rec[e].x & 0xffu) < 132u && ((rec[e].x >> 8) & 0xffu) < 132u &&
+                          (rec[e].x >> 16) == 0u && rec[e].z >= S.slot_base[slot], 102)) {
+          S.ta[slot * STRIDE + o] = make_uint2(rec[e].x | (rel << 16), ((rel >> 16) & 0xffu) | (span << 8));
+          S.pb[slot * STRIDE + o] = make_float2(__double2float_rn(cxv[e]), __double2float_rn(cyv[e]));
+        }
       }
     }
     out_base += all0 + all1;
@@ -1557,7 +1581,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
             // fast-path conditions: not a halo event, window rows stay below 2H, staging complete
             const bool ok = (int)r.z >= A.h && min(yi + FARMS_MAX_WINDOW, W - 1) <= 2 * H - 1 && !S.ovf[w] &&
                             (!SECOND || !A.done[pos]);
-            if (ok) S.tlist[w][atomicAdd(&S.ntg[w], 1u)] = pos;
+            if (ok) {
+              const unsigned int slot_t = atomicAdd(&S.ntg[w], 1u);
+              if (FARMS_CHK(slot_t < (unsigned int)TK_MAXT && pos < A.cell_start[A.ncells], 111)) S.tlist[w][slot_t] = pos;
+            }
 
           }
         __syncthreads();
@@ -1568,7 +1595,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
         // round then ends half a task later instead of a whole one.
         // (Rounds of many slabs -- the sparse-stream variant -- keep the plain pairing: there an odd target shares
         // its warp with an idle half.)
-        constexpr bool SOLOS = NSL <= 2;
+        constexpr bool SOLOS = NSL <= FARMS_SOLOS_MAX_NSL;
         uint32_t pstart[NSL + 1], sstart[NSL + 1], npair[NSL];
         uint32_t P = 0;
 #pragma unroll
@@ -1612,8 +1639,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
           }
           const uint32_t nt = S.ntg[w];
           const bool have = solo ? half == 0 : kk < nt;  // this half owns a target's result
+          (void)FARMS_CHK(nt >= 1 && nt <= (uint32_t)TK_MAXT && w >= 0 && w < NSL, 112);
           const uint32_t tpos = S.tlist[w][kk < nt ? kk : nt - 1];
           const uint4 r = A.rec[tpos];
+          (void)FARMS_CHK((int)r.z >= A.h && (size_t)r.z < A.m && xi_in_region(r.x, R), 113);
           const int xi = (int)(r.x & 0xffffu), yi = (int)(r.x >> 16);
           const uint32_t ii = r.z;
           // the event's window in region coordinates; staged records all lie inside the sensor and inside the
@@ -1632,7 +1661,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
             for (int q0 = sub + (solo ? 64 * half : 0); q0 < n; q0 += solo ? 128 : 64) {
               uint2 c[4];
 #pragma unroll
-              for (int u = 0; u < 4; u++) c[u] = recs[q0 + 16 * u];  // padded (span 0): no bounds check
+              for (int u = 0; u < 4; u++) {
+                (void)FARMS_CHK(q0 + 16 * u < STRIDE && slot >= 0 && slot < SM::RING, 114);
+                c[u] = recs[q0 + 16 * u];  // padded (span 0): no bounds check in the product build
+              }
 #pragma unroll
               for (int u = 0; u < 4; u++) {
                 const uint32_t d4 = __vabsdiffu4(c[u].x, tw);  // |dx| in byte 0, |dy| in byte 1
@@ -1642,6 +1674,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
                 if (ok) {
                   const uint32_t m = max(d4 & 0xffu, (d4 >> 8) & 0xffu);
                   const uint32_t ring = ((m + FARMS_WINDOW_JUMP - 1) * 205u) >> 10;  // /5 for values <= 54
+                  (void)FARMS_CHK(ring < (uint32_t)FARMS_NSCALES && q0 + 16 * u < n, 115);
                   const float2 f = pays[q0 + 16 * u];
                   float fl;
                   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(fl) : "f"(f.x * f.x + f.y * f.y));
@@ -1715,6 +1748,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
                     const uint32_t mch = max(d4 & 0xffu, (d4 >> 8) & 0xffu);
                     const int ring = (int)(((mch + FARMS_WINDOW_JUMP - 1) * 205u) >> 10);
                     const uint32_t j = base + rel;
+                    (void)FARMS_CHK(ring < FARMS_NSCALES && (size_t)j < A.m && j <= ii, 116);
                     double4 v = dacc[ring * 16 + sub];
                     v.x += A.ev_len[j];
                     v.y += A.ev_lcx[j];
@@ -2429,4 +2463,17 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
   if (kernels_used) *kernels_used |= FARMS_POOLK_ANY;
   launches++;
   return launches;
+}
+
+unsigned int farms_chk_pooling(cudaStream_t s) {
+#ifdef FARMS_CHECKED
+  unsigned int v[2] = {0, 0}, z[2] = {0, 0};
+  cudaMemcpyFromSymbolAsync(v, g_farms_chk, sizeof v, 0, cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  if (v[0]) cudaMemcpyToSymbolAsync(g_farms_chk, z, sizeof z, 0, cudaMemcpyHostToDevice, s);
+  return v[0];
+#else
+  (void)s;
+  return 0;
+#endif
 }

@@ -138,6 +138,9 @@ const char *farms_last_error(const farms_ctx *ctx); /* never NULL; "" when no er
  * equivalent of constructing a new vFlowManager for the next recording. */
 int farms_reset(farms_ctx *ctx);
 int farms_abi_version(void);
+/* 1 for libfarms_b200_checked.so (make checked: kernels compiled with -DFARMS_CHECKED carry their own bounds checks
+ * and farms_process_* fails with FARMS_ERR_STATE when one trips), 0 for the product build */
+int farms_build_is_checked(void);
 
 /* The reference's filter-size normalisation (src/vFlow.cpp:32-38) as a pure host function: returns the
  * normalised filtersize and stores fRad and planeSize.  Needs no device. */

@@ -205,7 +205,7 @@ def test_cli_binary_side_format_carries_the_same_columns_as_the_text_files(tmp_p
     assert L.farms_bin_write_events((base + ".evb").encode(), len(x), x16.ctypes.data, y16.ctypes.data, t64.ctypes.data,
                                     p8.ctypes.data) == 0
     out = subprocess.run([CLI, "--width", str(s.width), "--height", str(s.height), "--filtersize", str(s.filtersize),
-                          "--filename", base, "--binary", "1", "--numEvents", "30000"], capture_output=True, text=True)
+                          "--filename", base, "--binary", "1", "--SERIAL", "0", "--numEvents", "30000"], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     n = 30000
     raw = open(base + "_FARMSOut_.bin", "rb").read()
@@ -373,3 +373,27 @@ def test_slice_surface_rejects_out_of_range_events():
     with pytest.raises(farms_b200.FarmsError) as e:
         f.slice_surface(x, y, t, 0, lt, hit)
     assert e.value.code == farms_b200.ERR_RANGE
+
+
+def test_cli_serial_mode_runs_the_serial_semantics(tmp_path):
+    """--SERIAL 1 (the reference's default, src/main.cpp:31): vFlowManager::run semantics (src/vFlow.cpp:465-826)
+    incl. its numEvents + 1 loop bound (:565); rows go to the file that mode names (:486) -- the reference itself
+    writes nothing there, so the comparison is with the oracle's serial mode."""
+    from helpers import synth_stream
+    s, x, y, t, p = synth_stream(1, 6000, 0)
+    base = str(tmp_path / "ser")
+    np.savetxt(base + ".txt", np.stack([x.astype(np.int64), y.astype(np.int64), t.astype(np.int64), p.astype(np.int64)], 1), fmt="%d")
+    r = subprocess.run([CLI, "--width", str(s.width), "--height", str(s.height), "--filtersize", str(s.filtersize),
+                        "--filename", base, "--numEvents", "4000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Running serially" in r.stdout or "SERIAL" not in r.stdout
+    rows = np.loadtxt(base + "_FARMSOut_bench_500us.txt")
+    n = 4000 + 2  # the first line + (numEvents + 1) processed lines
+    assert rows.shape == (n, 11)
+    ref = run_oracle(s.width, s.height, s.filtersize, 5, x[:n], y[:n], t[:n], p[:n], serial=True)
+    assert np.array_equal(rows[:, 2].astype(np.int64), ref["t_rel"].astype(np.int64))
+    assert np.array_equal(rows[:, 10].astype(np.int64), ref["scale"].astype(np.int64))
+    v = ref["valid"].astype(bool)
+    assert v.sum() > 500
+    assert np.allclose(rows[v, 4], ref["global_r"][v], rtol=2e-5)
+    assert np.allclose(rows[~v, 4], 0)

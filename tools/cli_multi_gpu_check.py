@@ -42,7 +42,7 @@ with tempfile.TemporaryDirectory() as d:
                                         p.ctypes.data) == 0
         t0 = time.time()
         out = subprocess.run([os.path.join(PKG, "FARMS_Flow"), "--width", "1280", "--height", "720", "--filtersize", "5",
-                              "--filename", base, "--binary", "1", "--gpus", str(g)], capture_output=True, text=True)
+                              "--filename", base, "--binary", "1", "--SERIAL", "0", "--gpus", str(g)], capture_output=True, text=True)
         assert out.returncode == 0, out.stderr
         print(f"--gpus {g}: wall {time.time() - t0:.2f} s;", [ln for ln in out.stdout.splitlines() if "Benchmark" in ln or "farms_b200" in ln])
         res[g] = load(base + "_FARMSOut_.bin")

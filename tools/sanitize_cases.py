@@ -40,6 +40,15 @@ def build(case):
     if case == "aliased":    # width > height: logical rows >= H alias the next column
         x, y, t, p = sweeps(150, 40, slopes=((9, 2), (-7, 3)), gap=150)
         return 150, 40, 5, x, y, t.astype(np.uint64), {}
+    if case == "serial":     # FARMS_FLAG_SERIAL_SEMANTICS
+        import farms_b200
+        s = Synth(1)
+        x, y, t, p = s.first(40_000, 0)
+        return s.width, s.height, s.filtersize, x, y, t, {"flags": farms_b200.FLAG_SERIAL_SEMANTICS}
+    if case in ("long4", "long3"):  # steady-state density, default kernels, several internal batches
+        s = Synth(4 if case == "long4" else 3)
+        x, y, t, p = s.first(1_500_000, 0)
+        return s.width, s.height, s.filtersize, x, y, t, {"max_batch": 400_000}
     if case == "exact":      # k_pool_any for every event
         import farms_b200
         s = Synth(3)
@@ -52,15 +61,18 @@ def main():
     import farms_b200
     case = sys.argv[1]
     w, h, fs, x, y, t, kw = build(case)
-    f = farms_b200.Farms(w, h, fs, 5, max_batch=70_000, **kw)
+    kw.setdefault("max_batch", 70_000)
+    f = farms_b200.Farms(w, h, fs, 5, **kw)
     got = f.process(x, y, t)
     tm = f.timings()
-    rep = {"case": case, "events": len(x), "valid": int(got["valid"].sum()),
+    rep = {"case": case, "checked_build": bool(farms_b200.lib().farms_build_is_checked()), "events": len(x),
+           "valid": int(got["valid"].sum()),
            "pool_kernels": tm["pool_kernels"], "pool_events": [tm["pool_events_first"], tm["pool_events_second"],
                                                                tm["pool_events_general"]]}
     if "--check" in sys.argv:
         from helpers import assert_parity, compare, run_oracle
-        r = compare(got, run_oracle(w, h, fs, 5, x, y, t, fast=True), case)
+        serial = bool(kw.get("flags", 0) & farms_b200.FLAG_SERIAL_SEMANTICS)
+        r = compare(got, run_oracle(w, h, fs, 5, x, y, t, fast=not serial, serial=serial), case)
         assert_parity(r)
         rep["oracle"] = "parity ok"
     print("sanitize_case", json.dumps(rep))

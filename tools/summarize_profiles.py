@@ -60,6 +60,14 @@ def launches(path, out, command):
             gbs = a[2] / max(a[1], 1e-9) / 1e6
             f.write(f"{k[:58]:58s} {a[0]:8d} {a[1]:10.3f} {100*a[1]/tot:6.1f}% {a[2]/1e9:9.3f} {gbs:8.1f} {gbs/PEAK:6.3f}\n")
         f.write(f"{'total':58s} {sum(a[0] for a in agg.values()):8d} {tot:10.3f}\n")
+    # machine-readable copy for bench.py's `roofline_kernels` (kernels above 0.1 % of the step)
+    kj = {"source": f"{out} ({command})",
+          "kernels": [{"kernel": k, "launches": a[0], "ms": a[1], "share": a[1] / tot, "dram_bytes": a[2],
+                       "gbs": a[2] / max(a[1], 1e-9) / 1e6}
+                      for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]) if a[1] / tot > 1e-3]}
+    import os
+    with open(os.path.join(os.path.dirname(out) or ".", "kernels.json"), "w") as f:
+        json.dump(kj, f, indent=1)
 
 
 def kernel(rep, out, title, index=0):
