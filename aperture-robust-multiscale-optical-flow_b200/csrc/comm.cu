@@ -93,16 +93,24 @@ struct LocalGroup {
   float *root_dst = nullptr;
   int failed = 0;
 
-  void barrier() {
+  // false if some rank has failed (it will never arrive): the others must not wait for it
+  bool barrier() {
     std::unique_lock<std::mutex> lk(mu);
+    if (failed) return false;
     const uint64_t gen = generation;
     if (++arrived == nranks) {
       arrived = 0;
       generation++;
       cv.notify_all();
     } else {
-      cv.wait(lk, [&] { return generation != gen; });
+      cv.wait(lk, [&] { return generation != gen || failed; });
     }
+    return !failed;
+  }
+  void fail() {
+    std::lock_guard<std::mutex> lk(mu);
+    failed = 1;
+    cv.notify_all();
   }
 };
 
@@ -341,10 +349,22 @@ void farms_comm_destroy(farms_comm *cm) {
   delete cm;
 }
 
+static int comm_process_impl(farms_comm *cm, const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t n,
+                             uint64_t n_halo, uint64_t n_surface, uint64_t t0, uint32_t flags, const farms_out *out,
+                             const farms_gather *gather);
+
 int farms_comm_process(farms_comm *cm, const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t n,
                        uint64_t n_halo, uint64_t n_surface, uint64_t t0, uint32_t flags, const farms_out *out,
                        const farms_gather *gather) {
   if (!cm || !cm->ctx) return FARMS_ERR_ARG;
+  const int rc = comm_process_impl(cm, x, y, t, n, n_halo, n_surface, t0, flags, out, gather);
+  if (rc != FARMS_OK && cm->group) cm->group->fail();  // in-process ranks waiting at a barrier give up too
+  return rc;
+}
+
+static int comm_process_impl(farms_comm *cm, const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t n,
+                             uint64_t n_halo, uint64_t n_surface, uint64_t t0, uint32_t flags, const farms_out *out,
+                             const farms_gather *gather) {
   farms_ctx *c = cm->ctx;
   c->err.clear();
   if (n_halo > n || n_surface > n || (n && (!x || !y || !t))) return farms_fail(c, FARMS_ERR_ARG, "bad slice arguments");
@@ -397,7 +417,7 @@ int farms_comm_process(farms_comm *cm, const uint16_t *x, const uint16_t *y, con
         memcpy(&G->meta[4 * cm->rank], &cm->h_meta[4 * cm->rank], 4 * sizeof(uint64_t));
         if (gather && cm->rank == gather->root) G->root_dst = gather->dst;
       }
-      G->barrier();
+      if (!G->barrier()) return farms_fail(c, FARMS_ERR_COMM, "another rank of the group failed");
       for (int r = 0; r < R; r++) {
         memcpy(&cm->h_meta[4 * r], &G->meta[4 * r], 4 * sizeof(uint64_t));
         if (r >= cm->rank) continue;  // only earlier slices are folded
@@ -405,7 +425,7 @@ int farms_comm_process(farms_comm *cm, const uint16_t *x, const uint16_t *y, con
         CUC(cudaMemcpyAsync(cm->all_hit + (size_t)r * npx, G->surf_hit[r], npx, cudaMemcpyDefault, s));
       }
       CUC(cudaStreamSynchronize(s));
-      G->barrier();  // every rank has read the published surfaces
+      if (!G->barrier()) return farms_fail(c, FARMS_ERR_COMM, "another rank of the group failed");  // all have read the surfaces
     } else {
       NcclApi *N = nccl_api();
       CUC(cudaMemcpyAsync(cm->d_meta + 4 * cm->rank, cm->h_meta + 4 * cm->rank, 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
@@ -465,7 +485,8 @@ int farms_comm_process(farms_comm *cm, const uint16_t *x, const uint16_t *y, con
         if ((rc = post_receives(cm, cm->recv_posted))) return rc;
     }
     CUC(cudaStreamSynchronize(cm->cstream));
-    if (cm->local && R > 1) cm->group->barrier();  // the root's buffer is complete when every rank has passed here
+    // the root's buffer is complete when every rank has passed here
+    if (cm->local && R > 1 && !cm->group->barrier()) return farms_fail(c, FARMS_ERR_COMM, "another rank of the group failed");
   }
   cm->gather = nullptr;
   return FARMS_OK;

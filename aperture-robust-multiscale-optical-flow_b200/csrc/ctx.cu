@@ -336,8 +336,9 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   which = radix_sort_pairs(w.keyA, w.valA, w.keyB, w.valB, m, bits_for(ncells + 1), c->sort_temp.p, s, L);
   skeys = which ? w.keyB : w.keyA;
   svals = which ? w.valB : w.valA;
+  CU(cudaMemsetAsync(c->d_work, 0, 8 * sizeof(unsigned int), s));
   launch_build_records(skeys, svals, m, w.ex, w.ey, w.et, w.nextp, w.len, w.lcx, w.lcy, monotone, w.rec,
-                       w.pay, (uint32_t *)c->cell_start.p, (uint32_t)ncells, s);
+                       w.pay, (uint32_t *)c->cell_start.p, (uint32_t)ncells, (uint32_t)hh, c->d_work + 4, s);
   *L += 2;
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev[EV_BIN], s));
@@ -346,7 +347,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaMemsetAsync(w.gr, 0, n_out * 8, s));
   CU(cudaMemsetAsync(w.gth, 0, n_out * 8, s));
   CU(cudaMemsetAsync(w.scale, 0, n_out, s));
-  CU(cudaMemsetAsync(c->d_work, 0, 4 * sizeof(unsigned int), s));
+  
   CU(cudaMemsetAsync(w.done, 0, m, s));
   CU(cudaMemsetAsync(w.fin, 0, n_out * sizeof(uint32_t), s));
   {
@@ -628,7 +629,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   ok &= cudaMalloc((void **)&c->hlcy, HALO_CAP * 8) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->d_err, sizeof(int)) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess;
-  ok &= cudaMalloc((void **)&c->d_work, 4 * sizeof(unsigned int)) == cudaSuccess;
+  ok &= cudaMalloc((void **)&c->d_work, 8 * sizeof(unsigned int)) == cudaSuccess;
   ok &= cudaMalloc((void **)&c->d_small, 64) == cudaSuccess;
   ok &= cudaMallocHost((void **)&c->h_small, 256) == cudaSuccess;
   if (!ok) return bail(FARMS_ERR_NOMEM);

@@ -126,8 +126,9 @@ void launch_cell_keys(const uint16_t *ex, const uint16_t *ey, const uint32_t *em
 void launch_build_records(const uint32_t *skeys, const uint32_t *sidx, size_t m, const uint16_t *ex,
                           const uint16_t *ey, const uint32_t *et, const int32_t *nextp, const double *len,
                           const double *lcx, const double *lcy, int monotone, uint4 *rec, double *pay,
-                          uint32_t *cell_start, uint32_t ncells, cudaStream_t s);
-// returns the number of kernels launched.  work_counter: four zeroed words; done: m zeroed bytes; fin: m - h zeroed words.
+                          uint32_t *cell_start, uint32_t ncells, uint32_t h, unsigned int *n_targets, cudaStream_t s);
+// returns the number of kernels launched.  work_counter: eight zeroed words (three work counters, then the per-batch
+// words of PoolArgs::batch_words, whose [1] launch_build_records fills); done: m zeroed bytes; fin: m - h zeroed words.
 // cand_count: four counters {candidates inspected, events pooled by the first fast pass, by the flagged second pass,
 // by k_pool_any}; kernels_used: FARMS_POOLK_* bits of the kernels launched are OR-ed in.
 int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_start, const uint32_t *slab_ids,

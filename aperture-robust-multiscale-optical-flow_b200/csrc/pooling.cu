@@ -71,11 +71,16 @@ __global__ void k_build_records(const uint32_t *__restrict__ skeys, const uint32
                                 const uint32_t *__restrict__ et, const int32_t *__restrict__ nextp,
                                 const double *__restrict__ len, const double *__restrict__ lcx,
                                 const double *__restrict__ lcy, int monotone, uint4 *__restrict__ rec,
-                                double *__restrict__ pay, uint32_t *__restrict__ cell_start, uint32_t ncells) {
+                                double *__restrict__ pay, uint32_t *__restrict__ cell_start, uint32_t ncells,
+                                uint32_t h, unsigned int *__restrict__ n_targets) {
   size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= m) return;
+  const bool entry = pos < m && skeys[pos] < ncells;  // no flow: not part of the index
+  {  // events the pooling kernels must produce: index entries that are not halo
+    const unsigned bal = __ballot_sync(0xffffffffu, entry && sidx[pos] >= h);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_targets, (unsigned int)__popc(bal));
+  }
+  if (!entry) return;
   const uint32_t k = skeys[pos];
-  if (k >= ncells) return;  // no flow: not part of the index
   const uint32_t j = sidx[pos];
   uint32_t end = (uint32_t)nextp[j];
   const uint32_t tj = et[j];
@@ -119,6 +124,9 @@ struct PoolArgs {
   double *global_r, *global_theta;
   uint8_t *scale;
   unsigned int *work_counter;
+  // per batch, zeroed by the host: [0] some round's staging overflowed (the second pass has work), [1] events of
+  // this batch that must be pooled (index entries that are not halo), [2] of those, finished by the fast passes
+  unsigned int *batch_words;
   unsigned long long *cand_count;
   unsigned long long *path_count;  // events pooled by: [0] first fast pass, [1] flagged second pass, [2] k_pool_any
 };
@@ -186,6 +194,7 @@ __global__ void __launch_bounds__(PW * 32) k_pool_any(PoolArgs A) {
   const uint32_t mi = A.cell_start[A.ncells];
   const double *pay_len = A.pay, *pay_cx = A.pay + m, *pay_cy = A.pay + 2 * m;
   unsigned long long ncand = 0, npooled = 0;
+  if (A.batch_words[1] == A.batch_words[2]) return;  // the fast passes finished every event of the batch
 
   constexpr unsigned int CHUNK = 32;  // index positions per grab: few atomics even when almost nothing is left to pool
   for (unsigned int base = 0, chunk_end = 0;; base += 32) {
@@ -592,6 +601,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
   unsigned long long ncand = 0;
   unsigned int npooled = 0;
 
+  if (SECOND && A.batch_words[0] == 0u) return;  // no round overflowed in the first pass: nothing to do
+
   for (;;) {
     __syncthreads();
     if (tid == 0) S.item = atomicAdd(A.work_counter, 1u);
@@ -679,7 +690,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
         int o = 0;
         for (int s = S.dlo[tid]; s <= S.dhi[tid]; s++) o |= S.overflow[s % (TK_LB + NSL)];
         S.ovf[tid] = o;
-        if (!SECOND && o && nraw[tid]) atomicOr(&A.item_ovf[item], 1u << ((d + tid - d_begin) >> TK_OVF_SHIFT));
+        if (!SECOND && o && nraw[tid]) {
+          atomicOr(&A.item_ovf[item], 1u << ((d + tid - d_begin) >> TK_OVF_SHIFT));
+          A.batch_words[0] = 1u;
+        }
       }
 
       for (uint32_t t0 = 0; t0 < nmax; t0 += TK_MAXT) {
@@ -886,7 +900,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile(PoolArgs A, int 
     }
   }
   if ((lane & 15) == 0 && ncand) atomicAdd(A.cand_count, ncand);
-  if ((lane & 15) == 0 && npooled) atomicAdd(A.path_count + (SECOND ? 1 : 0), (unsigned long long)npooled);
+  if ((lane & 15) == 0 && npooled) {
+    atomicAdd(A.path_count + (SECOND ? 1 : 0), (unsigned long long)npooled);
+    atomicAdd(A.batch_words + 2, npooled);
+  }
 }
 
 template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND>
@@ -1154,6 +1171,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_warp(PoolArgs A, int 
   unsigned long long ncand = 0;
   unsigned int npooled = 0;
 
+  if (SECOND && A.batch_words[0] == 0u) return;  // no round overflowed in the first pass: nothing to do
+
   for (;;) {
     __syncthreads();
     if (tid == 0) S.item = atomicAdd(A.work_counter, 1u);
@@ -1240,7 +1259,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_warp(PoolArgs A, int 
         int o = 0;
         for (int s = S.dlo[tid]; s <= S.dhi[tid]; s++) o |= S.overflow[s % RING];
         S.ovf[tid] = o;
-        if (!SECOND && o && nraw[tid]) atomicOr(&A.item_ovf[item], 1u << ((d + tid - d_begin) >> TK_OVF_SHIFT));
+        if (!SECOND && o && nraw[tid]) {
+          atomicOr(&A.item_ovf[item], 1u << ((d + tid - d_begin) >> TK_OVF_SHIFT));
+          A.batch_words[0] = 1u;
+        }
       }
 
       for (uint32_t t0 = 0; t0 < nmax; t0 += TK_MAXT) {
@@ -1421,7 +1443,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_warp(PoolArgs A, int 
     }
   }
   if (lane == 0 && ncand) atomicAdd(A.cand_count, ncand);
-  if (lane == 0 && npooled) atomicAdd(A.path_count + (SECOND ? 1 : 0), (unsigned long long)npooled);
+  if (lane == 0 && npooled) {
+    atomicAdd(A.path_count + (SECOND ? 1 : 0), (unsigned long long)npooled);
+    atomicAdd(A.batch_words + 2, npooled);
+  }
 }
 
 template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND>
@@ -1475,6 +1500,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
   const unsigned int nitems = (unsigned int)otx_n * oty_n * nseg;
   unsigned long long ncand = 0;
   unsigned int npooled = 0;
+
+  if (SECOND && A.batch_words[0] == 0u) return;  // no round overflowed in the first pass: nothing to do
 
   for (;;) {
     __syncthreads();
@@ -1563,7 +1590,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
         int o = 0;
         for (int s = S.dlo[tid]; s <= S.dhi[tid]; s++) o |= S.overflow[s % (TK_LB + NSL)];
         S.ovf[tid] = o;
-        if (!SECOND && o && nraw[tid]) atomicOr(&A.item_ovf[item], 1u << ((d + tid - d_begin) >> TK_OVF_SHIFT));
+        if (!SECOND && o && nraw[tid]) {
+          atomicOr(&A.item_ovf[item], 1u << ((d + tid - d_begin) >> TK_OVF_SHIFT));
+          A.batch_words[0] = 1u;
+        }
       }
 
       for (uint32_t t0 = 0; t0 < nmax; t0 += TK_MAXT) {
@@ -1783,7 +1813,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
     }
   }
   if ((lane & 15) == 0 && ncand) atomicAdd(A.cand_count, ncand);
-  if ((lane & 15) == 0 && npooled) atomicAdd(A.path_count + (SECOND ? 1 : 0), (unsigned long long)npooled);
+  if ((lane & 15) == 0 && npooled) {
+    atomicAdd(A.path_count + (SECOND ? 1 : 0), (unsigned long long)npooled);
+    atomicAdd(A.batch_words + 2, npooled);
+  }
 }
 
 template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND>
@@ -2326,7 +2359,10 @@ __global__ void __launch_bounds__(BP_THREADS, 2) k_pool_bits(PoolArgs A, int otx
     }
   }
   if (ncand) atomicAdd(A.cand_count, ncand);
-  if (npooled) atomicAdd(A.path_count, (unsigned long long)npooled);
+  if (npooled) {
+    atomicAdd(A.path_count, (unsigned long long)npooled);
+    atomicAdd(A.batch_words + 2, npooled);
+  }
 }
 
 // Second half of the fast path's output: mean vector = sums / count, then length and angle (src/vFlow.cpp:365-366).
@@ -2367,9 +2403,9 @@ void launch_cell_keys(const uint16_t *ex, const uint16_t *ey, const uint32_t *em
 void launch_build_records(const uint32_t *skeys, const uint32_t *sidx, size_t m, const uint16_t *ex,
                           const uint16_t *ey, const uint32_t *et, const int32_t *nextp, const double *len,
                           const double *lcx, const double *lcy, int monotone, uint4 *rec, double *pay,
-                          uint32_t *cell_start, uint32_t ncells, cudaStream_t s) {
+                          uint32_t *cell_start, uint32_t ncells, uint32_t h, unsigned int *n_targets, cudaStream_t s) {
   if (m) k_build_records<<<nb(m, 256), 256, 0, s>>>(skeys, sidx, m, ex, ey, et, nextp, len, lcx, lcy, monotone, rec,
-                                                   pay, cell_start, ncells);
+                                                   pay, cell_start, ncells, h, n_targets);
 }
 
 int pool_tile_smem_bytes() { return (int)sizeof(BitsSmem); }
@@ -2391,6 +2427,7 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
   int launches = 0;
   PoolArgs A;
   A.own_ok = own_ok;
+  A.batch_words = work_counter + 3;
   A.path_count = cand_count + 1;
   A.rec = rec; A.pay = pay; A.cell_start = cell_start; A.slab_ids = slab_ids; A.done = done;
   A.slab_first = slab_first; A.fin = fin; A.item_ovf = item_ovf;
