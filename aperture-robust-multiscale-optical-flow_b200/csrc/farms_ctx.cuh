@@ -16,7 +16,10 @@ constexpr size_t HALO_CAP = 8ull << 20;       // events carried across a batch b
 #endif
 constexpr int FIT_CHUNK_MAX = 1 << FARMS_FIT_CHUNK_LOG2;  // events per SAE snapshot at most
 constexpr int FIT_CHUNK_MIN = 1 << 13;
-constexpr int FIT_WAYS = 4;  // plane-fit chunks in flight
+#ifndef FARMS_FIT_WAYS
+#define FARMS_FIT_WAYS 4
+#endif
+constexpr int FIT_WAYS = FARMS_FIT_WAYS;  // plane-fit chunks in flight
 constexpr size_t CSR_BUDGET = 96ull << 20;    // max (slab, tile) cells of the pooling index per batch
 
 enum { EV_START, EV_H2D, EV_INGEST, EV_INDEX, EV_FIT, EV_BIN, EV_POOL, EV_END, EV_COUNT };

@@ -175,7 +175,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip exact-pooling / other-config / sliced-parity extras")
     ap.add_argument("--parity-events", type=int, default=2_000_000)
-    ap.add_argument("--pool-variant", default="", help="A/B runs: tile | bits | tile1 | warp (default: the library's choice)")
+    ap.add_argument("--pool-variant", default="", help="A/B runs: tile | bits | tile1 | warp | tile16 ... (default: the library's choice)")
+    ap.add_argument("--fit-chunk", type=int, default=0, help="A/B runs: events per plane-fit chunk (default: the library's choice)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -342,7 +343,7 @@ def main():
     sl.to_device()
     n_all, n_owned = sl.n, sl.n_owned
     total_events = all_counts(n_owned)
-    f = farms_b200.Farms(W, H, FS, 5, device=local_rank, pool_variant=args.pool_variant or 0)
+    f = farms_b200.Farms(W, H, FS, 5, device=local_rank, pool_variant=args.pool_variant or 0, fit_chunk=args.fit_chunk)
     cm = new_comm(f)
     dev_out = {k: torch.empty(n_owned, dtype=tdt[farms_b200.OUT_DTYPES[k]], device=dev) for k in DEV_COLUMNS}
     gathered = torch.empty((total_events, 4), dtype=torch.float32, device=dev) if rank == 0 else torch.zeros(1, device=dev)
@@ -444,7 +445,7 @@ def main():
     peak, peak_src = measured_peak()
     nbatches = max(1, -(-n_all // (16 << 20)))
     if stage_avg.get("pool_ms", 0) >= stage_avg.get("fit_ms", 0):
-        kname, kms, balg, nl = "k_pool_tile", stage_avg["pool_ms"], B_ALG_POOL, nbatches
+        kname, kms, balg, nl = "k_pool_tile16", stage_avg["pool_ms"], B_ALG_POOL, nbatches
     else:
         kname, kms, balg, nl = "k_fit_gather", stage_avg["fit_ms"], B_ALG_FIT, nbatches
     achieved = balg * n_all / (kms * 1e-3) / 1e9 if kms > 0 else 0.0

@@ -62,9 +62,10 @@ typedef struct {
 
 #define FARMS_FLAG_DEBUG_DET 1u       /* also produce the determinant column (farms_out.det)       */
 #define FARMS_FLAG_EXACT_POOLING 2u   /* pool every event with the general FP64 kernel: slower, sums
-                                         accurate to ~1e-15 instead of ~1e-7 relative (the default fast
-                                         path keeps FP32 ring partials; its scale decisions are exact
-                                         either way, see csrc/pooling.cu)                           */
+                                         accurate to ~1e-15 instead of ~1e-7..2e-6 relative.  The default fast
+                                         path keeps FP32 ring partials: its scale decision is accepted only when
+                                         the winning mean beats every rival by a 2e-5 margin, otherwise the event is
+                                         pooled again in FP64 (see csrc/pooling.cu)                         */
 #define FARMS_FLAG_GENERIC_POOLING FARMS_FLAG_EXACT_POOLING
 #define FARMS_FLAG_SERIAL_SEMANTICS 4u /* the semantics of the reference's DEFAULT driver vFlowManager::run
                                          (src/vFlow.cpp:465-826) instead of runFileCopy: the first event of the
