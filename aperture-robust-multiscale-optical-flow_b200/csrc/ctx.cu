@@ -692,6 +692,37 @@ int farms_process_device(farms_ctx *c, const uint16_t *x, const uint16_t *y, con
   return farms_process_impl(c, x, y, t, n, out, true, true, 0, nullptr);
 }
 
+int farms_reserve(farms_ctx *c, uint64_t n, int host_io) {
+  if (!c) return FARMS_ERR_ARG;
+  if (n == 0) return FARMS_OK;
+  CU(cudaSetDevice(c->cfg.device));
+  const uint64_t maxb = c->cfg.max_batch ? c->cfg.max_batch : DEFAULT_MAX_BATCH;
+  const size_t nb = (size_t)std::min<uint64_t>(n, maxb);
+  // a later batch carries the halo of the one before: room for it, as run_batch would make on demand
+  const size_t m = nb + (n > maxb ? std::min<size_t>(HALO_CAP, nb) / 4 : 0);
+  int rc;
+  const int nsets = (host_io && n > 0) ? 2 : 1;
+  for (int k = 0; k < nsets; k++)
+    if ((rc = alloc_working(c, c->ws[k], m + m / 8 + 1024))) return rc;
+  const size_t scratch_bytes = (plane_fit_scratch_bytes(c->r, (size_t)c->fit_chunk) + 255) & ~(size_t)255;
+  if ((rc = ensure(c, c->fit_scratch, FIT_WAYS * scratch_bytes))) return rc;
+  if (host_io && c->cap_in < nb) {
+    CU(cudaDeviceSynchronize());
+    for (int k = 0; k < 2; k++) {
+      if (c->in_x[k]) { cudaFree(c->in_x[k]); cudaFree(c->in_y[k]); cudaFree(c->in_t[k]); }
+      c->in_x[k] = nullptr; c->in_y[k] = nullptr; c->in_t[k] = nullptr;
+    }
+    c->cap_in = 0;
+    for (int k = 0; k < 2; k++) {
+      CU(cudaMalloc((void **)&c->in_x[k], nb * 2));
+      CU(cudaMalloc((void **)&c->in_y[k], nb * 2));
+      CU(cudaMalloc((void **)&c->in_t[k], nb * 8));
+    }
+    c->cap_in = nb;
+  }
+  return FARMS_OK;
+}
+
 uint64_t farms_num_events(const farms_ctx *c) { return c ? c->total_events : 0; }
 
 int farms_get_timings(const farms_ctx *c, farms_timings *out) {

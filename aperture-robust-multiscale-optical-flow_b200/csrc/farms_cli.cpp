@@ -351,6 +351,13 @@ int main(int argc, char **argv) {
 
   farms_timings tm_sliced;
   uint64_t sliced_events = 0;
+  // device working memory up front, like the reference's surfaces (allocated in its constructor, outside its timer)
+  if (o.gpus <= 1 && farms_reserve(ctx, n, 1) != FARMS_OK) {
+    std::fprintf(stderr, "error: %s\n", farms_last_error(ctx));
+    farms_text_free(&ev);
+    farms_destroy(ctx);
+    return 1;
+  }
   const auto a = std::chrono::system_clock::now();
   if (o.gpus > 1) {
     std::string serr;

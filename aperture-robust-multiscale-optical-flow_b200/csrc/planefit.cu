@@ -253,8 +253,14 @@ struct FitRec {
   static constexpr int G = R == 1 ? 8 : R == 2 ? 10 : 16, EPW = 32 / G;
 };
 
+#ifndef FARMS_GATHER_MINB
+#define FARMS_GATHER_MINB 1
+#endif
+#ifndef FARMS_SOLVE_MINB
+#define FARMS_SOLVE_MINB 4  // 128 registers (196 bytes of spills) instead of 168: 16 warps per SM, fit stage -6 %
+#endif
 template <int R>
-__global__ void __launch_bounds__(256) k_fit_gather(const uint2 *__restrict__ sae, const int2 *__restrict__ prevp,
+__global__ void __launch_bounds__(256, FARMS_GATHER_MINB) k_fit_gather(const uint2 *__restrict__ sae, const int2 *__restrict__ prevp,
                                                     const uint16_t *__restrict__ ex, const uint16_t *__restrict__ ey,
                                                     const uint32_t *__restrict__ et, int i0, int i1, int W, int H,
                                                     uint32_t *__restrict__ recs) {
@@ -379,7 +385,7 @@ __global__ void __launch_bounds__(256) k_fit_gather(const uint2 *__restrict__ sa
 }
 
 template <int R>
-__global__ void __launch_bounds__(128) k_fit_solve(const uint32_t *__restrict__ recs, const uint16_t *__restrict__ ex,
+__global__ void __launch_bounds__(128, FARMS_SOLVE_MINB) k_fit_solve(const uint32_t *__restrict__ recs, const uint16_t *__restrict__ ex,
                                                    const uint16_t *__restrict__ ey, const uint32_t *__restrict__ et,
                                                    int i0, int i1, FitParams fp, FitOut fo,
                                                    unsigned long long *__restrict__ valid_count) {

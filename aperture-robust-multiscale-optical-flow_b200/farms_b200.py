@@ -27,7 +27,7 @@ POOL_VARIANTS = {"tile": 1, "bits": 2, "tile1": 3, "warp": 4, "tile16": 5, "tile
 
 EXPORTS = [
     "farms_abi_version", "farms_build_is_checked", "farms_create", "farms_destroy", "farms_reset", "farms_last_error", "farms_normalize_filtersize", "farms_get_params",
-    "farms_process_host", "farms_process_device", "farms_num_events", "farms_get_timings", "farms_set_t0",
+    "farms_process_host", "farms_process_device", "farms_reserve", "farms_num_events", "farms_get_timings", "farms_set_t0",
     "farms_state_export", "farms_state_fold", "farms_slice_surface", "farms_pack4_f32",
     "farms_slice_surface_host", "farms_state_fold_host",
     "farms_host_alloc", "farms_host_free", "farms_host_register", "farms_host_unregister",

@@ -166,6 +166,11 @@ int farms_process_device(farms_ctx *ctx, const uint16_t *x, const uint16_t *y, c
                          const uint8_t *p, uint64_t n, const farms_out *out);
 
 /* replaces `getNumEvents()` (include/vFlow.h:108): events processed so far */
+/* Optional: allocate the device working memory for calls of up to n events now (host_io != 0: also the staging
+ * buffers of farms_process_host), so that the first farms_process_* call does not pay for it.  The reference
+ * allocates its surfaces in the constructor (src/vFlow.cpp:47-93), outside its loop timer. */
+int farms_reserve(farms_ctx *ctx, uint64_t n, int host_io);
+
 uint64_t farms_num_events(const farms_ctx *ctx);
 int farms_get_timings(const farms_ctx *ctx, farms_timings *out);
 
