@@ -152,6 +152,19 @@ int copy_out(farms_ctx *c, T *dst, const T *src, size_t n, bool to_device, cudaS
   return 0;
 }
 
+// stage times of the batch whose events were recorded in set c->stage_pending (all completed by now)
+int collect_stage_times(farms_ctx *c, float *stage_ms) {
+  if (c->stage_pending < 0) return 0;
+  static const int order[] = {EV_H2D, EV_INGEST, EV_INDEX, EV_FIT, EV_BIN, EV_POOL, EV_END};
+  float ms = 0;
+  for (int k = 1; k < 7; k++) {
+    CU(cudaEventElapsedTime(&ms, c->evb[c->stage_pending][order[k - 1]], c->evb[c->stage_pending][order[k]]));
+    stage_ms[k] += ms;
+  }
+  c->stage_pending = -1;
+  return 0;
+}
+
 // the output columns that exist once the plane fit of a batch is done (everything but globalR / globalTheta / scale)
 int copy_fit_columns(farms_ctx *c, WorkSet &w, const farms_out *out, size_t hh, size_t n_out, size_t out_off,
                      bool out_device, cudaStream_t st) {
@@ -195,7 +208,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
     CU(cudaMemcpyAsync(w.lcx, c->hlcx, h * 8, cudaMemcpyDeviceToDevice, s));
     CU(cudaMemcpyAsync(w.lcy, c->hlcy, h * 8, cudaMemcpyDeviceToDevice, s));
   }
-  CU(cudaEventRecord(c->ev[EV_H2D], s));
+  CU(cudaEventRecord(c->evb[c->ev_set][EV_H2D], s));
 
   // ---- K1 ingest ----
   CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), s));
@@ -210,10 +223,16 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   }
   launch_halo_keys(w.ex, w.ey, h, c->H, w.keyA, w.valA, s);
   inclusive_max_scan_u32(w.et + h, w.em + h, n, c->last_M, c->scan_temp.p, s, L);
+  // where the history kept for the next batch starts (events younger than 500 us + slack at the end of this one):
+  // known as soon as the running maximum of the timestamps is, and read back at the mid-batch synchronisation
+  const uint32_t window = FARMS_KILL_OLD_FLOW_TIME + (c->cfg.reorder_slack_us ? c->cfg.reorder_slack_us : DEFAULT_SLACK_US);
+  k_tail_start<<<1, 1, 0, s>>>(w.em, (uint32_t)m, window, c->d_small + 12);
+  k_publish<<<1, 32, 0, s>>>(c->h_small + 48, c->d_small + 12, 2);
+  *L += 2;
   CU(cudaMemcpyAsync(w.pixkeep, w.keyA, m * 4, cudaMemcpyDeviceToDevice, s));
   *L += 2;
   k_publish<<<1, 32, 0, s>>>(c->h_small + 8, (const uint32_t *)c->d_err, 1);  // read at the mid-batch sync below
-  CU(cudaEventRecord(c->ev[EV_INGEST], s));
+  CU(cudaEventRecord(c->evb[c->ev_set][EV_INGEST], s));
   CU(cudaEventRecord(c->ev_ingest[set], s));  // the input staging buffers of this set are free again
 
   // ---- K2 history index: stable sort by pixel, prev/next links ----
@@ -222,7 +241,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   launch_links(skeys, svals, w.et, c->sae, m, w.prevp, w.nextp, s);
   *L += 1;
   CU(cudaGetLastError());
-  CU(cudaEventRecord(c->ev[EV_INDEX], s));
+  CU(cudaEventRecord(c->evb[c->ev_set][EV_INDEX], s));
 
 
   // ---- K3 plane fit, chunk by chunk against the chunk-end SAE snapshot ----
@@ -264,7 +283,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   launch_sae_finalize(c->sae, w.pixkeep, w.nextp, (int)m, s);
   *L += 1;
   CU(cudaGetLastError());
-  CU(cudaEventRecord(c->ev[EV_FIT], s));
+  CU(cudaEventRecord(c->evb[c->ev_set][EV_FIT], s));
 
   // ---- the columns the plane fit produced can leave now, under the pooling of this batch ----
   const bool early_copy = out && n_out && out_stream != s && !c->serial;  // (serial: the ghost row is fixed later)
@@ -285,6 +304,15 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaStreamSynchronize(s));
   // (k_ingest clamps an out-of-range event to pixel (0,0), so the kernels above were safe to run)
   if (((int *)c->h_small)[8]) return fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
+  const size_t ts = c->h_small[48];
+  const uint32_t last_M = c->h_small[49];
+  // more than HALO_CAP events inside the pooling window (+ slack): truncating the halo would silently lose
+  // contributors for the next batch, so this is an error (timestamps in the wrong unit, or a pathological burst) --
+  // raised before the pooling stage, whose cost grows with the number of events per pixel inside the window
+  if (m - ts > HALO_CAP)
+    return fail(c, FARMS_ERR_STATE, "%zu events within the last %u us exceed the %zu-event history kept across batches",
+                m - ts, window, HALO_CAP);
+  if ((rc = collect_stage_times(c, stage_ms))) return rc;  // of the previous batch: its events have all completed
   if (c->serial) {
     if (ghost == 0) {
       c->ghost_seen = true;
@@ -341,7 +369,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
                        w.pay, (uint32_t *)c->cell_start.p, (uint32_t)ncells, (uint32_t)hh, c->d_work + 4, s);
   *L += 2;
   CU(cudaGetLastError());
-  CU(cudaEventRecord(c->ev[EV_BIN], s));
+  CU(cudaEventRecord(c->evb[c->ev_set][EV_BIN], s));
 
   // ---- K4b pooling ----
   CU(cudaMemsetAsync(w.gr, 0, n_out * 8, s));
@@ -360,7 +388,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
                        (int)hh, w.len, w.lcx, w.lcy, (int)nslabs, g, fast, flow_frac * (double)m / (double)nslabs, w.gr, w.gth, w.scale,
                        c->d_work, c->d_counters + 1, c->num_sms, s, &c->pool_kernels, c->serial ? w.own : nullptr);
   CU(cudaGetLastError());
-  CU(cudaEventRecord(c->ev[EV_POOL], s));
+  CU(cudaEventRecord(c->evb[c->ev_set][EV_POOL], s));
 
   // ---- results of the new events ----
   if (hook && hook->fn && n_out) {
@@ -382,21 +410,9 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
     c->d2h_pending[set] = true;
   }
 
-  // ---- new tail -> halo store ----
-  const uint32_t window = FARMS_KILL_OLD_FLOW_TIME + (c->cfg.reorder_slack_us ? c->cfg.reorder_slack_us : DEFAULT_SLACK_US);
-  k_tail_start<<<1, 1, 0, s>>>(w.em, (uint32_t)m, window, c->d_small);
-  *L += 1;
-  k_publish<<<1, 32, 0, s>>>(c->h_small, c->d_small, 2);
-  CU(cudaEventRecord(c->ev[EV_END], s));
-  CU(cudaStreamSynchronize(s));
-  size_t ts = c->h_small[0];
-  c->last_M = c->h_small[1];
-  if (c->serial && c->h_small[44]) c->ghost_prev_pending = false;  // the ghost's pixel has had its next event
-  // more than HALO_CAP events inside the pooling window (+ slack): truncating the halo would silently lose
-  // contributors for the next batch, so this is an error (timestamps in the wrong unit, or a pathological burst)
-  if (m - ts > HALO_CAP)
-    return fail(c, FARMS_ERR_STATE, "%zu events within the last %u us exceed the %zu-event history kept across batches",
-                m - ts, window, HALO_CAP);
+  // ---- new tail -> halo store (no host synchronisation: the host goes on to enqueue the next batch) ----
+  CU(cudaEventRecord(c->evb[c->ev_set][EV_END], s));
+  c->last_M = last_M;
   const size_t nh = m - ts;
   CU(cudaMemcpyAsync(c->hx, w.ex + ts, nh * 2, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemcpyAsync(c->hy, w.ey + ts, nh * 2, cudaMemcpyDeviceToDevice, s));
@@ -406,14 +422,8 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaMemcpyAsync(c->hlcx, w.lcx + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemcpyAsync(c->hlcy, w.lcy + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
   c->halo = nh;
-
-  // stage times of this batch (the events were all recorded before the synchronisation above)
-  float ms = 0;
-  static const int order[] = {EV_H2D, EV_INGEST, EV_INDEX, EV_FIT, EV_BIN, EV_POOL, EV_END};
-  for (int k = 1; k < 7; k++) {
-    CU(cudaEventElapsedTime(&ms, c->ev[order[k - 1]], c->ev[order[k]]));
-    stage_ms[k] += ms;
-  }
+  c->stage_pending = c->ev_set;  // its stage times are read at the next synchronisation
+  c->ev_set ^= 1;
   return 0;
 }
 
@@ -445,6 +455,7 @@ int farms_process_impl(farms_ctx *c, const uint16_t *x, const uint16_t *y, const
   CU(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), s));
   c->valid_seen = 0;
   c->pool_kernels = 0;
+  c->stage_pending = -1;
   float stage[8] = {0};
   CU(cudaEventRecord(c->ev[EV_START], s));
   const uint64_t nbatch = (n + maxb - 1) / maxb;
@@ -480,6 +491,7 @@ int farms_process_impl(farms_ctx *c, const uint16_t *x, const uint16_t *y, const
   auto drain = [&]() {
     cudaDeviceSynchronize();
     c->d2h_pending[0] = c->d2h_pending[1] = false;
+    c->stage_pending = -1;
   };
   if (!in_device) {
     int rc = upload(0);
@@ -515,6 +527,10 @@ int farms_process_impl(farms_ctx *c, const uint16_t *x, const uint16_t *y, const
   c->d2h_pending[0] = c->d2h_pending[1] = false;
   CU(cudaEventRecord(c->ev[EV_END], s));
   CU(cudaStreamSynchronize(s));
+  {
+    int rc = collect_stage_times(c, stage);
+    if (rc) return rc;
+  }
   float total = 0;
   CU(cudaEventElapsedTime(&total, c->ev[EV_START], c->ev[EV_END]));
   CU(cudaMemcpyAsync(c->h_small + 16, c->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -608,7 +624,9 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   }
   if (cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   for (int i = 0; i < EV_COUNT; i++)
-    if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(FARMS_ERR_CUDA);
+    if (cudaEventCreate(&c->ev[i]) != cudaSuccess || cudaEventCreate(&c->evb[0][i]) != cudaSuccess ||
+        cudaEventCreate(&c->evb[1][i]) != cudaSuccess)
+      return bail(FARMS_ERR_CUDA);
   {
     cudaEvent_t *evs[] = {&c->ev_h2d[0], &c->ev_h2d[1], &c->ev_ingest[0], &c->ev_ingest[1], &c->ev_pool[0],
                           &c->ev_pool[1], &c->ev_d2h[0], &c->ev_d2h[1], &c->ev_c0, &c->ev_c1, &c->ev_fitdone[0],
@@ -658,8 +676,11 @@ void farms_destroy(farms_ctx *c) {
   for (void *p : ps)
     if (p) cudaFree(p);
   if (c->h_small) cudaFreeHost(c->h_small);
-  for (int i = 0; i < EV_COUNT; i++)
+  for (int i = 0; i < EV_COUNT; i++) {
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->evb[0][i]) cudaEventDestroy(c->evb[0][i]);
+    if (c->evb[1][i]) cudaEventDestroy(c->evb[1][i]);
+  }
   cudaEvent_t evs[] = {c->ev_h2d[0], c->ev_h2d[1], c->ev_ingest[0], c->ev_ingest[1], c->ev_pool[0], c->ev_pool[1],
                        c->ev_d2h[0], c->ev_d2h[1], c->ev_c0, c->ev_c1, c->ev_fitdone[0], c->ev_fitdone[1]};
   for (cudaEvent_t e : evs)

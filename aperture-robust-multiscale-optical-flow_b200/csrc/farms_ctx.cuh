@@ -63,7 +63,9 @@ struct farms_ctx {
   // with two / four slabs per round
   int pool_impl = 7;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[EV_COUNT]{};
+  cudaEvent_t ev[EV_COUNT]{};          // EV_START / EV_END of a whole call
+  cudaEvent_t evb[2][EV_COUNT]{};      // stage events of the internal batches, two sets used alternately
+  int ev_set = 0, stage_pending = -1;  // set being recorded; set whose stage times have not been read yet
   std::string err;
   bool have_t0 = false;
   uint64_t t0 = 0;

@@ -397,3 +397,21 @@ def test_cli_serial_mode_runs_the_serial_semantics(tmp_path):
     assert v.sum() > 500
     assert np.allclose(rows[v, 4], ref["global_r"][v], rtol=2e-5)
     assert np.allclose(rows[~v, 4], 0)
+
+
+def test_history_overflow_is_an_error_not_a_silent_truncation():
+    """More than 8 Mi events inside the 500 us + slack window (here: one timestamp for all of them) cannot be carried
+    across a batch boundary; the library says so instead of dropping contributors."""
+    import farms_b200
+    n = 9_000_000
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 64, n).astype(np.uint16)
+    y = rng.integers(0, 64, n).astype(np.uint16)
+    t = np.full(n, 1000, np.uint64)
+    f = farms_b200.Farms(64, 64, 5, 5)
+    with pytest.raises(farms_b200.FarmsError) as e:
+        f.process(x, y, t, columns=["valid"])
+    assert e.value.code == farms_b200.ERR_STATE
+    f.reset()  # the context stays usable
+    s = f.process(x[:1000], y[:1000], np.arange(1000, 2000, dtype=np.uint64), columns=["valid"])
+    assert len(s["valid"]) == 1000
