@@ -365,8 +365,20 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   skeys = which ? w.keyB : w.keyA;
   svals = which ? w.valB : w.valA;
   CU(cudaMemsetAsync(c->d_work, 0, 8 * sizeof(unsigned int), s));
+  // sorted timestamps: a per-microsecond table "first event at or after time u" replaces the binary search for the
+  // 500-us age bound of every pooling record (skipped for batches spanning more than 2^26 us: the search is used)
+  const uint32_t tt_base = c->h_small[4];
+  const uint64_t tt_span = (uint64_t)c->h_small[5] - c->h_small[4] + FARMS_KILL_OLD_FLOW_TIME + 2;
+  const uint32_t *time_table = nullptr;
+  if (monotone && tt_span <= (1ull << 26)) {
+    if ((rc = ensure(c, c->time_table, tt_span * sizeof(uint32_t)))) return rc;
+    launch_time_table(w.et, m, tt_base, (uint32_t *)c->time_table.p, (uint32_t)tt_span, s);
+    time_table = (const uint32_t *)c->time_table.p;
+    *L += 2;
+  }
   launch_build_records(skeys, svals, m, w.ex, w.ey, w.et, w.nextp, w.len, w.lcx, w.lcy, monotone, w.rec,
-                       w.pay, (uint32_t *)c->cell_start.p, (uint32_t)ncells, (uint32_t)hh, c->d_work + 4, s);
+                       w.pay, (uint32_t *)c->cell_start.p, (uint32_t)ncells, (uint32_t)hh, c->d_work + 4, time_table,
+                       tt_base, (uint32_t)tt_span, s);
   *L += 2;
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->evb[c->ev_set][EV_BIN], s));
@@ -672,7 +684,7 @@ void farms_destroy(farms_ctx *c) {
   void *ps[] = {c->sae, c->hx, c->hy, c->ht, c->hm, c->hlen, c->hlcx, c->hlcy, c->d_err, c->d_counters, c->d_work,
                 c->d_small, c->in_x[0], c->in_y[0], c->in_t[0], c->in_x[1], c->in_y[1], c->in_t[1], c->sort_temp.p,
                 c->scan_temp.p, c->cell_start.p, c->fit_scratch.p, c->surf_tmp.p, c->item_ovf.p, c->io_x.p, c->io_y.p,
-                c->io_t.p, c->io_surf_t.p, c->io_surf_hit.p};
+                c->io_t.p, c->io_surf_t.p, c->io_surf_hit.p, c->time_table.p};
   for (void *p : ps)
     if (p) cudaFree(p);
   if (c->h_small) cudaFreeHost(c->h_small);

@@ -97,7 +97,7 @@ struct farms_ctx {
   uint16_t *in_x[2] = {nullptr, nullptr}, *in_y[2] = {nullptr, nullptr};
   uint64_t *in_t[2] = {nullptr, nullptr};
   // misc
-  DevBuf sort_temp, scan_temp, cell_start, fit_scratch, surf_tmp, item_ovf;
+  DevBuf sort_temp, scan_temp, cell_start, fit_scratch, surf_tmp, item_ovf, time_table;
   DevBuf io_x, io_y, io_t, io_surf_t, io_surf_hit;  // staging of the host-array state helpers
   int *d_err = nullptr;
   unsigned long long *d_counters = nullptr;  // [0] valid events, [1] pool candidates, [2..4] events per pooling path

@@ -126,7 +126,11 @@ void launch_cell_keys(const uint16_t *ex, const uint16_t *ey, const uint32_t *em
 void launch_build_records(const uint32_t *skeys, const uint32_t *sidx, size_t m, const uint16_t *ex,
                           const uint16_t *ey, const uint32_t *et, const int32_t *nextp, const double *len,
                           const double *lcx, const double *lcy, int monotone, uint4 *rec, double *pay,
-                          uint32_t *cell_start, uint32_t ncells, uint32_t h, unsigned int *n_targets, cudaStream_t s);
+                          uint32_t *cell_start, uint32_t ncells, uint32_t h, unsigned int *n_targets,
+                          const uint32_t *time_table, uint32_t tt_base, uint32_t tt_size, cudaStream_t s);
+// time_table[u] = first index with et >= tt_base + u (sorted timestamps); tt_size entries
+void launch_time_table(const uint32_t *et, size_t m, uint32_t tt_base, uint32_t *time_table, uint32_t tt_size,
+                       cudaStream_t s);
 // returns the number of kernels launched.  work_counter: eight zeroed words (three work counters, then the per-batch
 // words of PoolArgs::batch_words, whose [1] launch_build_records fills); done: m zeroed bytes; fin: m - h zeroed words.
 // cand_count: four counters {candidates inspected, events pooled by the first fast pass, by the flagged second pass,

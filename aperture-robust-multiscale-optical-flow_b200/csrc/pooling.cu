@@ -62,6 +62,27 @@ __global__ void k_cell_keys(const uint16_t *__restrict__ ex, const uint16_t *__r
   idx[j] = (uint32_t)j;
 }
 
+__global__ void k_fill_u32(uint32_t *__restrict__ p, uint32_t n, uint32_t v) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// one writer per table entry: the first event of every distinct timestamp fills the entries since the previous one
+__global__ void k_time_table(const uint32_t *__restrict__ et, size_t m, uint32_t tt_base,
+                             uint32_t *__restrict__ table, uint32_t tt_size) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const uint32_t t = et[j];
+  uint32_t from;  // first table offset this event is the answer for
+  if (j == 0) from = 0;
+  else {
+    const uint32_t tp = et[j - 1];
+    if (tp == t) return;
+    from = tp - tt_base + 1;
+  }
+  for (uint32_t u = from; u <= t - tt_base && u < tt_size; u++) table[u] = (uint32_t)j;
+}
+
 // rec[pos] = {x | y<<16, t, idx, end}; pay = SoA {len, lcx, lcy}; CSR cell_start over cell keys.
 // end = min(next event at the same pixel, first event that is >= 500 us younger): for sorted timestamps
 // "j is a contributor of i" is exactly  idx <= i < end.  (For unsorted input end = next and k_pool_any
@@ -72,7 +93,8 @@ __global__ void k_build_records(const uint32_t *__restrict__ skeys, const uint32
                                 const double *__restrict__ len, const double *__restrict__ lcx,
                                 const double *__restrict__ lcy, int monotone, uint4 *__restrict__ rec,
                                 double *__restrict__ pay, uint32_t *__restrict__ cell_start, uint32_t ncells,
-                                uint32_t h, unsigned int *__restrict__ n_targets) {
+                                uint32_t h, unsigned int *__restrict__ n_targets,
+                                const uint32_t *__restrict__ time_table, uint32_t tt_base, uint32_t tt_size) {
   size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool entry = pos < m && skeys[pos] < ncells;  // no flow: not part of the index
   {  // events the pooling kernels must produce: index entries that are not halo
@@ -84,7 +106,12 @@ __global__ void k_build_records(const uint32_t *__restrict__ skeys, const uint32
   const uint32_t j = sidx[pos];
   uint32_t end = (uint32_t)nextp[j];
   const uint32_t tj = et[j];
-  if (monotone) {
+  if (monotone && time_table) {
+    // first index u with et[u] >= tj + 500: one look-up in the per-microsecond table (k_time_table)
+    const uint64_t off = (uint64_t)tj + FARMS_KILL_OLD_FLOW_TIME - tt_base;
+    const uint32_t lo = off < tt_size ? time_table[off] : (uint32_t)m;
+    if (lo < end) end = lo;
+  } else if (monotone) {
     // first index u > j with et[u] >= tj + 500
     uint32_t lo = j + 1, hi = end < (uint32_t)m ? end : (uint32_t)m;
     const uint64_t lim = (uint64_t)tj + FARMS_KILL_OLD_FLOW_TIME;
@@ -2403,9 +2430,20 @@ void launch_cell_keys(const uint16_t *ex, const uint16_t *ey, const uint32_t *em
 void launch_build_records(const uint32_t *skeys, const uint32_t *sidx, size_t m, const uint16_t *ex,
                           const uint16_t *ey, const uint32_t *et, const int32_t *nextp, const double *len,
                           const double *lcx, const double *lcy, int monotone, uint4 *rec, double *pay,
-                          uint32_t *cell_start, uint32_t ncells, uint32_t h, unsigned int *n_targets, cudaStream_t s) {
+                          uint32_t *cell_start, uint32_t ncells, uint32_t h, unsigned int *n_targets,
+                          const uint32_t *time_table, uint32_t tt_base, uint32_t tt_size, cudaStream_t s) {
   if (m) k_build_records<<<nb(m, 256), 256, 0, s>>>(skeys, sidx, m, ex, ey, et, nextp, len, lcx, lcy, monotone, rec,
-                                                   pay, cell_start, ncells, h, n_targets);
+                                                   pay, cell_start, ncells, h, n_targets, time_table, tt_base, tt_size);
+}
+
+// time_table[u] = first event index whose timestamp is >= tt_base + u (sorted timestamps, integer microseconds), m
+// past the last event: turns "first event at least 500 us younger" (the age bound of src/vFlow.cpp:1002 folded into
+// the index interval of a pooling record) into one look-up instead of a 20-step binary search per flow event.
+void launch_time_table(const uint32_t *et, size_t m, uint32_t tt_base, uint32_t *time_table, uint32_t tt_size,
+                       cudaStream_t s) {
+  if (!m || !tt_size) return;
+  k_fill_u32<<<nb(tt_size, 256), 256, 0, s>>>(time_table, tt_size, (uint32_t)m);
+  k_time_table<<<nb(m, 256), 256, 0, s>>>(et, m, tt_base, time_table, tt_size);
 }
 
 int pool_tile_smem_bytes() { return (int)sizeof(BitsSmem); }

@@ -207,8 +207,11 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_sec / len(rates),
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "timer": "reference's own loop timer (src/vFlow.cpp:214-423)"},
+                "config": {"workload": workload, "l2": "inputs_larger_than_l2"},  # the same object as the B200 arm's
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+                                 "timer": "reference's own loop timer (src/vFlow.cpp:214-423)",
+                                 "steady_state_note": "2 M-event prefix of this workload (45 % valid): 7.3 k events/s "
+                                                      "(BASELINE.md section 5); the cold prefix timed here is ~9x faster",
                                  "sample": f"first {args.cpu_sample} events of the workload stream per step "
                                            "(cold surface; the reference is single-threaded and cannot use more cores)"},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -478,13 +481,14 @@ def main():
             "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64 plane fit and scale decisions; pooling sums f32 ring partials combined in f64 (exact f64 re-pool when undecided)",
             "data": "synthetic",
-            "config": {"workload": workload, "events_per_step_total": total_events, "l2": "inputs_larger_than_l2",
-                       "slicing": f"time slices of {sl.D} us per GPU + {HALO_US} us causal halo (farms_comm_process, "
-                                  f"transport {cm.transport()})" if world > 1 else "none",
-                       "generator_s": sl.gen_s,
-                       "value_starts_from": "x/y/t resident in HBM (SURVEY 8(d) counts from pinned host memory: that is `e2e`)",
-                       "delivered": "all 11-column outputs on the owning GPU (f64) + float4 contract columns of every "
-                                    "rank gathered on rank 0"},
+            "config": {"workload": workload, "l2": "inputs_larger_than_l2"},
+            "run": {"events_per_step_total": total_events,
+                    "slicing": f"time slices of {sl.D} us per GPU + {HALO_US} us causal halo (farms_comm_process, "
+                               f"transport {cm.transport()})" if world > 1 else "none",
+                    "generator_s": sl.gen_s,
+                    "value_starts_from": "x/y/t resident in HBM (SURVEY 8(d) counts from pinned host memory: that is `e2e`)",
+                    "delivered": "all 11-column outputs on the owning GPU (f64) + float4 contract columns of every "
+                                 "rank gathered on rank 0"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_run),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "stages_ms_per_step": {k: stage_avg[k] for k in ("total_ms", "ingest_ms", "index_ms", "fit_ms", "bin_ms",
