@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--parity-events", type=int, default=2_000_000)
     ap.add_argument("--pool-variant", default="", help="A/B runs: tile | bits | tile1 | warp | tile16 ... (default: the library's choice)")
     ap.add_argument("--fit-chunk", type=int, default=0, help="A/B runs: events per plane-fit chunk (default: the library's choice)")
+    ap.add_argument("--max-batch", type=int, default=0, help="A/B runs: events per internal batch (default: 16 Mi)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -346,7 +347,8 @@ def main():
     sl.to_device()
     n_all, n_owned = sl.n, sl.n_owned
     total_events = all_counts(n_owned)
-    f = farms_b200.Farms(W, H, FS, 5, device=local_rank, pool_variant=args.pool_variant or 0, fit_chunk=args.fit_chunk)
+    f = farms_b200.Farms(W, H, FS, 5, device=local_rank, pool_variant=args.pool_variant or 0, fit_chunk=args.fit_chunk,
+                         max_batch=args.max_batch)
     cm = new_comm(f)
     dev_out = {k: torch.empty(n_owned, dtype=tdt[farms_b200.OUT_DTYPES[k]], device=dev) for k in DEV_COLUMNS}
     gathered = torch.empty((total_events, 4), dtype=torch.float32, device=dev) if rank == 0 else torch.zeros(1, device=dev)
@@ -446,7 +448,7 @@ def main():
 
     # roofline of the dominant kernel (the stage with the most device time)
     peak, peak_src = measured_peak()
-    nbatches = max(1, -(-n_all // (16 << 20)))
+    nbatches = max(1, -(-n_all // (args.max_batch or (16 << 20))))
     if stage_avg.get("pool_ms", 0) >= stage_avg.get("fit_ms", 0):
         kname, kms, balg, nl = "k_pool_tile16", stage_avg["pool_ms"], B_ALG_POOL, nbatches
     else:
