@@ -8,7 +8,9 @@
 #include "../../include/farms_b200.h"
 #include "farms_dev.cuh"
 
-constexpr uint64_t DEFAULT_MAX_BATCH = 16ull << 20;
+// events per internal batch: 32 Mi measured best at 1280x720 (200 M events: 8 Mi 397, 16 Mi 410, 32 Mi 419, 64 Mi 420
+// Mevents/s device-resident; end to end 16 Mi 396, 32 Mi 400, 64 Mi 392: longer pipeline fill and drain)
+constexpr uint64_t DEFAULT_MAX_BATCH = 32ull << 20;
 constexpr uint32_t DEFAULT_SLACK_US = 1000;
 constexpr size_t HALO_CAP = 8ull << 20;       // events carried across a batch boundary at most
 #ifndef FARMS_FIT_CHUNK_LOG2

@@ -1715,34 +1715,44 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
             const uint2 *recs = &S.ta[slot * STRIDE];
             const float2 *pays = &S.pb[slot * STRIDE];
             ncand += (sub == 0 && have) ? n : 0;
-            for (int q0 = sub + (solo ? 64 * half : 0); q0 < n; q0 += solo ? 128 : 64) {
+            // one staged record against this half-warp's event: test, and on a pass add it to the lane's ring partials
+            auto pool_one = [&](const uint2 c, const int q) {
+              const uint32_t d4 = __vabsdiffu4(c.x, tw);  // |dx| in byte 0, |dy| in byte 1
+              const uint32_t rel = __funnelshift_r(c.x, c.y, 16) & 0x00ffffffu;
+              // still the latest event of its pixel AND younger than 500 us  <=>  idx <= ii < end
+              const bool ok = (iir - rel) < (c.y >> 8) && ((d4 + 0x4d4du) & 0x8080u) == 0u;
+              if (ok) {
+                const uint32_t m = max(d4 & 0xffu, (d4 >> 8) & 0xffu);
+                const uint32_t ring = ((m + FARMS_WINDOW_JUMP - 1) * 205u) >> 10;  // /5 for values <= 54
+                (void)FARMS_CHK(ring < (uint32_t)FARMS_NSCALES && q < n, 115);
+                const float2 f = pays[q];
+                float fl;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(fl) : "f"(f.x * f.x + f.y * f.y));
+                float4 v = S.acc[warp][ring][lane];
+                v.x += fl;
+                v.y += f.x;
+                v.z += f.y;
+                v.w += 1.f;
+                S.acc[warp][ring][lane] = v;
+              }
+            };
+            // groups of 16 records: four per trip while four remain, the last one to three singly (a slot holds
+            // ~260 records: a fifth trip of four groups would test 60 padding records)
+            const int ngroups = (n + 15) >> 4, nfull = (ngroups & ~3) << 4;
+            for (int q0 = sub + (solo ? 64 * half : 0); q0 < nfull; q0 += solo ? 128 : 64) {
               uint2 c[4];
 #pragma unroll
               for (int u = 0; u < 4; u++) {
                 (void)FARMS_CHK(q0 + 16 * u < STRIDE && slot >= 0 && slot < SM::RING, 114);
-                c[u] = recs[q0 + 16 * u];  // padded (span 0): no bounds check in the product build
+                c[u] = recs[q0 + 16 * u];
               }
 #pragma unroll
-              for (int u = 0; u < 4; u++) {
-                const uint32_t d4 = __vabsdiffu4(c[u].x, tw);  // |dx| in byte 0, |dy| in byte 1
-                const uint32_t rel = __funnelshift_r(c[u].x, c[u].y, 16) & 0x00ffffffu;
-                // still the latest event of its pixel AND younger than 500 us  <=>  idx <= ii < end
-                const bool ok = (iir - rel) < (c[u].y >> 8) && ((d4 + 0x4d4du) & 0x8080u) == 0u;
-                if (ok) {
-                  const uint32_t m = max(d4 & 0xffu, (d4 >> 8) & 0xffu);
-                  const uint32_t ring = ((m + FARMS_WINDOW_JUMP - 1) * 205u) >> 10;  // /5 for values <= 54
-                  (void)FARMS_CHK(ring < (uint32_t)FARMS_NSCALES && q0 + 16 * u < n, 115);
-                  const float2 f = pays[q0 + 16 * u];
-                  float fl;
-                  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(fl) : "f"(f.x * f.x + f.y * f.y));
-                  float4 v = S.acc[warp][ring][lane];
-                  v.x += fl;
-                  v.y += f.x;
-                  v.z += f.y;
-                  v.w += 1.f;
-                  S.acc[warp][ring][lane] = v;
-                }
-              }
+              for (int u = 0; u < 4; u++) pool_one(c[u], q0 + 16 * u);
+            }
+            // (a solo target's two halves take alternate tail groups; the last group reads into the zeroed padding)
+            for (int q0 = nfull + sub + (solo ? 16 * half : 0); q0 < n; q0 += solo ? 32 : 16) {
+              (void)FARMS_CHK(q0 < STRIDE, 117);
+              pool_one(recs[q0], q0);
             }
           }
           __syncwarp();

@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--parity-events", type=int, default=2_000_000)
     ap.add_argument("--pool-variant", default="", help="A/B runs: tile | bits | tile1 | warp | tile16 ... (default: the library's choice)")
     ap.add_argument("--fit-chunk", type=int, default=0, help="A/B runs: events per plane-fit chunk (default: the library's choice)")
-    ap.add_argument("--max-batch", type=int, default=0, help="A/B runs: events per internal batch (default: 16 Mi)")
+    ap.add_argument("--max-batch", type=int, default=0, help="A/B runs: events per internal batch (default: 32 Mi)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -448,7 +448,7 @@ def main():
 
     # roofline of the dominant kernel (the stage with the most device time)
     peak, peak_src = measured_peak()
-    nbatches = max(1, -(-n_all // (args.max_batch or (16 << 20))))
+    nbatches = max(1, -(-n_all // (args.max_batch or (32 << 20))))
     if stage_avg.get("pool_ms", 0) >= stage_avg.get("fit_ms", 0):
         kname, kms, balg, nl = "k_pool_tile16", stage_avg["pool_ms"], B_ALG_POOL, nbatches
     else:

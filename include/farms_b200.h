@@ -47,7 +47,7 @@ typedef struct {
   int32_t inlier_check;     /* --inlierCheck = minEvtsOnPlane (default 5, src/main.cpp:24)         */
   int32_t device;           /* CUDA device ordinal                                                 */
   uint32_t flags;           /* FARMS_FLAG_*                                                        */
-  uint64_t max_batch;       /* events per internal device batch; 0 = default (16 Mi)               */
+  uint64_t max_batch;       /* events per internal device batch; 0 = default (32 Mi)               */
   uint32_t reorder_slack_us;/* extra history (us) kept across batch boundaries for streams whose
                                timestamps are not perfectly sorted; 0 = default (1000)            */
   /* Tuning / test selectors (0 = the library's own choice; never read from the environment): */
