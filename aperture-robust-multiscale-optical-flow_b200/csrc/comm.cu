@@ -18,8 +18,10 @@
 //          protocol (several ranks on one device, which NCCL refuses).
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <mutex>
@@ -39,6 +41,7 @@ struct NcclApi {
   decltype(&ncclCommInitRank) CommInitRank = nullptr;
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
   decltype(&ncclSend) Send = nullptr;
   decltype(&ncclRecv) Recv = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
@@ -69,7 +72,7 @@ NcclApi *nccl_api() {
   api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, name)); \
   if (!api.field) api.error = std::string("libnccl lacks ") + name;
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
-    SYM(AllGather, "ncclAllGather") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart")
+    SYM(AllGather, "ncclAllGather") SYM(Broadcast, "ncclBroadcast") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
   });
@@ -137,13 +140,23 @@ struct farms_comm {
   size_t sendcap = 0;
   cudaEvent_t ev_packed[2]{}, ev_sent[2]{};
   bool sent_pending[2] = {false, false};
+  // gather over peer memory (NCCL transport): the root's destination buffer mapped into this process with CUDA IPC
+  // (or its plain address when root and this rank share a process); outputs then travel as copy-engine writes over
+  // NVLink, which need no SM while the pooling kernel owns them all.  Falls back to ncclSend/ncclRecv.
+  unsigned char *d_ipc = nullptr, *h_ipc = nullptr;  // 128-byte descriptor broadcast from the root
+  unsigned char ipc_cached[64] = {0};                // handle of the mapping held in ipc_base
+  void *ipc_base = nullptr;
+  float *peer_dst = nullptr;                         // root's dst as seen from this rank, or null (fallback)
+  int gather_path = 0;                               // of the last call: 0 none, 1 nccl send/recv, 2 peer memory
   // state of the call in flight (read by the batch hook)
   const farms_gather *gather = nullptr;
   std::vector<uint64_t> n_all, n_halo, first_out;  // per rank
   uint64_t maxb = 0;
   uint64_t batches_seen = 0;     // batches with outputs this rank has packed
   uint64_t recv_posted = 0;      // root: batch indices [0, recv_posted) have their receives posted
-  float last_gather_ms = 0.f;
+  // host wall clock of the phases of the last farms_comm_process call (each ends with a synchronisation):
+  // upload + slice surface, exchange + fold, event loop, drain of the output transfers
+  float phase_ms[4] = {0.f, 0.f, 0.f, 0.f};
 };
 
 namespace {
@@ -210,7 +223,7 @@ int gather_hook(void *user, farms_ctx *c, const FarmsBatchView *v) {
     // own outputs: packed straight into the destination
     launch_pack4(v->gr, v->gth, v->lr, v->lth, v->n_out, (float4 *)(g->dst + 4 * (my_first + v->out_off)), v->stream);
     CUC(cudaGetLastError());
-    if (!cm->local && cm->nranks > 1) {
+    if (!cm->local && cm->nranks > 1 && cm->gather_path == 1) {
       // the peers run in step with this rank: by now they have (nearly) finished the previous batch, so its
       // receive kernels do not sit on SMs waiting for data
       const uint64_t upto = cm->batches_seen;  // batches before this one
@@ -233,12 +246,87 @@ int gather_hook(void *user, farms_ctx *c, const FarmsBatchView *v) {
     // one process: the root's buffer is directly addressable (peer access / same device)
     CUC(cudaMemcpyAsync(cm->group->root_dst + 4 * (my_first + v->out_off), cm->sendbuf[b], v->n_out * 16,
                         cudaMemcpyDefault, cm->cstream));
+  } else if (cm->gather_path == 2) {
+    // the root's buffer is mapped here: a copy-engine write over NVLink, no SM on either side
+    CUC(cudaMemcpyAsync(cm->peer_dst + 4 * (my_first + v->out_off), cm->sendbuf[b], v->n_out * 16, cudaMemcpyDefault,
+                        cm->cstream));
   } else {
     NC(nccl_api()->Send(cm->sendbuf[b], 4 * v->n_out, ncclFloat, g->root, cm->nccl, cm->cstream));
   }
   CUC(cudaEventRecord(cm->ev_sent[b], cm->cstream));
   cm->sent_pending[b] = true;
   cm->batches_seen++;
+  return 0;
+}
+
+// Agree on the gather path (NCCL transport).  The root describes its destination buffer -- IPC handle of the
+// allocation, offset of dst inside it, its process id and the raw address -- and broadcasts the 128 bytes; every
+// other rank maps it (cudaIpcOpenMemHandle, cached across calls; the plain address if it shares the root's
+// process).  An all-gather of one flag per rank then settles it: peer memory only if EVERY rank succeeded.
+struct IpcDesc {
+  cudaIpcMemHandle_t handle;  // 64 bytes
+  uint64_t offset, address, pid, ok;
+};
+static_assert(sizeof(IpcDesc) <= 128, "IPC descriptor fits the broadcast buffer");
+
+int setup_gather_path(farms_comm *cm, const farms_gather *g) {
+  NcclApi *N = nccl_api();
+  cudaStream_t s = cm->ctx->stream;
+  IpcDesc *d = reinterpret_cast<IpcDesc *>(cm->h_ipc);
+  memset(d, 0, sizeof *d);
+  if (cm->rank == g->root) {
+    // base of the allocation dst lives in (the handle names whole allocations): driver entry point via the runtime
+    typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn &&
+        reinterpret_cast<range_fn>(fn)(&base, &size, (unsigned long long)(uintptr_t)g->dst) == 0 &&
+        cudaIpcGetMemHandle(&d->handle, (void *)(uintptr_t)base) == cudaSuccess) {
+      d->offset = (uint64_t)((uintptr_t)g->dst - (uintptr_t)base);
+      d->ok = 1;
+    }
+    cudaGetLastError();
+    d->address = (uint64_t)(uintptr_t)g->dst;
+    d->pid = (uint64_t)getpid();
+  }
+  CUC(cudaMemcpyAsync(cm->d_ipc, cm->h_ipc, 128, cudaMemcpyHostToDevice, s));
+  NC(N->Broadcast(cm->d_ipc, cm->d_ipc, 128, ncclChar, g->root, cm->nccl, s));
+  CUC(cudaMemcpyAsync(cm->h_ipc, cm->d_ipc, 128, cudaMemcpyDeviceToHost, s));
+  CUC(cudaStreamSynchronize(s));
+  cm->peer_dst = nullptr;
+  uint64_t mine = 1;
+  if (cm->rank != g->root) {
+    mine = 0;
+    if (d->pid == (uint64_t)getpid()) {  // root is a thread of this process: its address is ours
+      cm->peer_dst = (float *)(uintptr_t)d->address;
+      mine = 1;
+    } else if (d->ok) {
+      if (!cm->ipc_base || memcmp(cm->ipc_cached, &d->handle, 64) != 0) {
+        if (cm->ipc_base) cudaIpcCloseMemHandle(cm->ipc_base);
+        cm->ipc_base = nullptr;
+        if (cudaIpcOpenMemHandle(&cm->ipc_base, d->handle, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess)
+          memcpy(cm->ipc_cached, &d->handle, 64);
+        else
+          cm->ipc_base = nullptr;
+        cudaGetLastError();
+      }
+      if (cm->ipc_base) {
+        cm->peer_dst = (float *)((char *)cm->ipc_base + d->offset);
+        mine = 1;
+      }
+    }
+  }
+  // every rank must take the same path
+  cm->h_meta[4 * cm->rank + 3] = mine;
+  CUC(cudaMemcpyAsync(cm->d_meta + 4 * cm->rank + 3, cm->h_meta + 4 * cm->rank + 3, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  NC(N->AllGather(cm->d_meta + 4 * cm->rank, cm->d_meta, 4, ncclUint64, cm->nccl, s));
+  CUC(cudaMemcpyAsync(cm->h_meta, cm->d_meta, (size_t)cm->nranks * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  CUC(cudaStreamSynchronize(s));
+  bool all = true;
+  for (int r = 0; r < cm->nranks; r++) all = all && cm->h_meta[4 * r + 3] != 0;
+  cm->gather_path = all ? 2 : 1;
   return 0;
 }
 
@@ -281,7 +369,8 @@ int farms_comm_create(farms_comm **out, farms_ctx *ctx, int nranks, int rank, co
             cudaMalloc((void **)&cm->all_t, (size_t)nranks * npx * 4) == cudaSuccess &&
             cudaMalloc((void **)&cm->all_hit, (size_t)nranks * npx) == cudaSuccess &&
             cudaMalloc((void **)&cm->d_meta, (size_t)nranks * 4 * sizeof(uint64_t)) == cudaSuccess &&
-            cudaMallocHost((void **)&cm->h_meta, (size_t)nranks * 4 * sizeof(uint64_t)) == cudaSuccess;
+            cudaMallocHost((void **)&cm->h_meta, (size_t)nranks * 4 * sizeof(uint64_t)) == cudaSuccess &&
+            cudaMalloc((void **)&cm->d_ipc, 128) == cudaSuccess && cudaMallocHost((void **)&cm->h_ipc, 128) == cudaSuccess;
   if (!ok) return bail(FARMS_ERR_NOMEM);
   cm->n_all.assign(nranks, 0);
   cm->n_halo.assign(nranks, 0);
@@ -341,6 +430,9 @@ void farms_comm_destroy(farms_comm *cm) {
   for (void *p : ps)
     if (p) cudaFree(p);
   if (cm->h_meta) cudaFreeHost(cm->h_meta);
+  if (cm->h_ipc) cudaFreeHost(cm->h_ipc);
+  if (cm->d_ipc) cudaFree(cm->d_ipc);
+  if (cm->ipc_base) cudaIpcCloseMemHandle(cm->ipc_base);
   for (int b = 0; b < 2; b++) {
     if (cm->ev_packed[b]) cudaEventDestroy(cm->ev_packed[b]);
     if (cm->ev_sent[b]) cudaEventDestroy(cm->ev_sent[b]);
@@ -377,6 +469,10 @@ static int comm_process_impl(farms_comm *cm, const uint16_t *x, const uint16_t *
   CUC(cudaSetDevice(c->cfg.device));
   cudaStream_t s = c->stream;
   const int R = cm->nranks;
+  using clk = std::chrono::steady_clock;
+  auto ms_since = [](clk::time_point a) { return std::chrono::duration<float, std::milli>(clk::now() - a).count(); };
+  clk::time_point tp = clk::now();
+  cm->phase_ms[0] = cm->phase_ms[1] = cm->phase_ms[2] = cm->phase_ms[3] = 0.f;
   int rc = farms_set_t0(c, t0);
   if (rc) return rc;
   cm->maxb = c->cfg.max_batch ? c->cfg.max_batch : DEFAULT_MAX_BATCH;
@@ -407,6 +503,8 @@ static int comm_process_impl(farms_comm *cm, const uint16_t *x, const uint16_t *
   if (R > 1) {
     // farms_slice_surface synchronises the compute stream: the uploads above are done when it returns
     if ((rc = farms_slice_surface(c, dx, dy, dt, n_surface, t0, cm->surf_t, cm->surf_hit))) return rc;
+    cm->phase_ms[0] = ms_since(tp);
+    tp = clk::now();
     const size_t npx = c->npx;
     if (cm->local) {
       LocalGroup *G = cm->group;
@@ -451,13 +549,22 @@ static int comm_process_impl(farms_comm *cm, const uint16_t *x, const uint16_t *
     if (gather && gather->counts) gather->counts[r] = cm->n_all[r] - cm->n_halo[r];
   }
 
+  if (R > 1) {
+    CUC(cudaStreamSynchronize(s));
+    cm->phase_ms[1] = ms_since(tp);
+  }
+  tp = clk::now();
   // ---- the event loop of this slice, outputs leaving batch by batch ----
   FarmsBatchHook hook;
   cm->gather = gather;
   cm->batches_seen = 0;
   cm->recv_posted = 0;
   cm->sent_pending[0] = cm->sent_pending[1] = false;
+  cm->gather_path = 0;
   if (gather) {
+    if (!cm->local && R > 1) {
+      if ((rc = setup_gather_path(cm, gather))) return rc;
+    }
     hook.fn = gather_hook;
     hook.user = cm;
     if (cm->rank != gather->root) {
@@ -477,8 +584,15 @@ static int comm_process_impl(farms_comm *cm, const uint16_t *x, const uint16_t *
   const bool stays_on_device = in_device || (R > 1 && n);
   rc = farms_process_impl(c, dx, dy, dt, n, out, stays_on_device, out_device, n_halo, gather ? &hook : nullptr);
   if (rc) return rc;
+  cm->phase_ms[2] = ms_since(tp);
+  tp = clk::now();
   if (gather) {
-    if (!cm->local && R > 1 && cm->rank == gather->root) {
+    if (!cm->local && R > 1 && cm->gather_path == 2) {
+      // peer-memory path: every rank's copies are done when its side stream is; one tiny collective tells the root
+      CUC(cudaStreamSynchronize(cm->cstream));
+      NC(nccl_api()->AllGather(cm->d_meta + 4 * cm->rank, cm->d_meta, 4, ncclUint64, cm->nccl, s));
+      CUC(cudaStreamSynchronize(s));
+    } else if (!cm->local && R > 1 && cm->rank == gather->root) {
       uint64_t most = 0;
       for (int r = 0; r < R; r++) most = std::max(most, batches_of(cm, r));
       for (; cm->recv_posted < most; cm->recv_posted++)
@@ -489,6 +603,13 @@ static int comm_process_impl(farms_comm *cm, const uint16_t *x, const uint16_t *
     if (cm->local && R > 1 && !cm->group->barrier()) return farms_fail(c, FARMS_ERR_COMM, "another rank of the group failed");
   }
   cm->gather = nullptr;
+  cm->phase_ms[3] = ms_since(tp);
+  return FARMS_OK;
+}
+
+int farms_comm_phases(const farms_comm *cm, float ms[4]) {
+  if (!cm || !ms) return FARMS_ERR_ARG;
+  for (int k = 0; k < 4; k++) ms[k] = cm->phase_ms[k];
   return FARMS_OK;
 }
 
@@ -496,7 +617,8 @@ int farms_comm_info(const farms_comm *cm, int32_t *nranks, int32_t *rank, int32_
   if (!cm) return FARMS_ERR_ARG;
   if (nranks) *nranks = cm->nranks;
   if (rank) *rank = cm->rank;
-  if (transport) *transport = cm->nranks == 1 ? 0 : cm->local ? 2 : 1;
+  // 0 none, 1 NCCL (gather by send/recv), 2 in-process, 3 NCCL + gather over peer memory (CUDA IPC / shared address)
+  if (transport) *transport = cm->nranks == 1 ? 0 : cm->local ? 2 : cm->gather_path == 2 ? 3 : 1;
   return FARMS_OK;
 }
 

@@ -31,7 +31,7 @@ EXPORTS = [
     "farms_state_export", "farms_state_fold", "farms_slice_surface", "farms_pack4_f32",
     "farms_slice_surface_host", "farms_state_fold_host",
     "farms_host_alloc", "farms_host_free", "farms_host_register", "farms_host_unregister",
-    "farms_comm_unique_id", "farms_comm_create", "farms_comm_destroy", "farms_comm_info", "farms_comm_process",
+    "farms_comm_unique_id", "farms_comm_create", "farms_comm_destroy", "farms_comm_info", "farms_comm_process", "farms_comm_phases",
 ]
 
 
@@ -243,10 +243,17 @@ class Comm:
 
     __del__ = close
 
+    def phases(self):
+        """Host wall clock (ms) of the last process() call: slice upload + surface, exchange + fold, event loop, drain."""
+        a = (C.c_float * 4)()
+        lib().farms_comm_phases.argtypes = [C.c_void_p, C.c_void_p]
+        lib().farms_comm_phases(self._h, a)
+        return {"surface_ms": a[0], "exchange_ms": a[1], "event_loop_ms": a[2], "drain_ms": a[3]}
+
     def transport(self):
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
         lib().farms_comm_info(self._h, C.byref(a), C.byref(b), C.byref(c))
-        return {0: "none", 1: "nccl", 2: "local"}[c.value]
+        return {0: "none", 1: "nccl", 2: "local", 3: "nccl+peer-memory gather"}[c.value]
 
     def process(self, x, y, t, n_halo, n_surface, t0, out=None, gather_dst=None, root=0, device=False):
         """One collective time-sliced pass.  x, y, t: this rank's slice including its halo -- numpy arrays

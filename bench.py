@@ -360,6 +360,9 @@ def main():
         f.reset()
         cm.process(sl.dx, sl.dy, sl.dt, sl.n_halo, sl.n_surf, sl.t0, out=dev_out, gather_dst=gathered, device=True)
         tm = f.timings()
+        if dist:
+            for k, v in cm.phases().items():
+                stage[k] = stage.get(k, 0) + v
         launches[0] += tm["kernel_launches"] + (2 + rank if dist else 0)
         for k, v in tm.items():
             stage[k] = stage.get(k, 0) + v
@@ -495,6 +498,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "stages_ms_per_step": {k: stage_avg[k] for k in ("total_ms", "ingest_ms", "index_ms", "fit_ms", "bin_ms",
                                                               "pool_ms") if k in stage_avg},
+            "comm_phases_ms_per_step_rank0": ({k: stage_avg[k] for k in ("surface_ms", "exchange_ms", "event_loop_ms", "drain_ms")
+                                              if k in stage_avg} if world > 1 else None),
             "pool_paths_events_per_step": {k: int(stage_avg.get(k, 0)) for k in ("pool_events_first", "pool_events_second",
                                                                                  "pool_events_general")},
             "pool_kernels": int(f.timings()["pool_kernels"]),

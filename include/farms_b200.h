@@ -241,7 +241,14 @@ typedef struct {
 int farms_comm_unique_id(void *id128);
 int farms_comm_create(farms_comm **out, farms_ctx *ctx, int nranks, int rank, const void *id128, uint32_t flags);
 void farms_comm_destroy(farms_comm *comm);
-int farms_comm_info(const farms_comm *comm, int32_t *nranks, int32_t *rank, int32_t *transport /* 0 none, 1 NCCL, 2 local */);
+/* transport: 0 none (one rank), 1 NCCL incl. the gather (ncclSend/ncclRecv), 2 in-process, 3 NCCL for the exchange
+ * and the gather written into the root's buffer over peer memory (CUDA IPC mapping, copy-engine writes over NVLink:
+ * no SM needed while the pooling kernel owns them; chosen when every rank can map the buffer; as of the last call) */
+int farms_comm_info(const farms_comm *comm, int32_t *nranks, int32_t *rank, int32_t *transport);
+/* host wall clock (ms) of the phases of the last farms_comm_process call on this rank: [0] slice made device-resident
+ * + its "last event per pixel" surface, [1] surface exchange + fold, [2] the event loop, [3] drain of the output
+ * transfers */
+int farms_comm_phases(const farms_comm *comm, float ms[4]);
 /* out: n - n_halo entries per column (any column, or out itself, may be NULL); io_flags: FARMS_IO_* */
 int farms_comm_process(farms_comm *comm, const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t n,
                        uint64_t n_halo, uint64_t n_surface, uint64_t t0, uint32_t io_flags, const farms_out *out,
