@@ -1727,7 +1727,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
                 (void)FARMS_CHK(ring < (uint32_t)FARMS_NSCALES && q < n, 115);
                 const float2 f = pays[q];
                 float fl;
-                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(fl) : "f"(f.x * f.x + f.y * f.y));
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(fl) : "f"(__fmaf_rn(f.y, f.y, f.x * f.x)));  // (file builds with -fmad=false)
                 float4 v = S.acc[warp][ring][lane];
                 v.x += fl;
                 v.y += f.x;
