@@ -340,15 +340,25 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
     const double target = c->cfg.slab_target ? (double)c->cfg.slab_target : 70.0;
     while (g.slab_shift < FARMS_SLAB_SHIFT_MAX && per_region_us * (double)(1u << g.slab_shift) < target) g.slab_shift++;
   }
-  CU(cudaMemsetAsync(c->d_small, 0, 8, s));
-  launch_slab_flags(w.em, w.et, m, g.slab_shift, w.flags, c->d_small + 1, s);
+  CU(cudaMemsetAsync(c->d_small, 0, 12, s));
+  launch_slab_flags(w.em, w.et, m, hh, g.slab_shift, w.flags, c->d_small + 1, c->d_small + 2, s);
   exclusive_scan_u32(w.flags, w.flags, m, c->scan_temp.p, s, L);
   k_nslabs<<<1, 1, 0, s>>>(w.em, w.flags, (uint32_t)m, g.slab_shift, c->d_small);
   *L += 2;
   k_publish<<<1, 32, 0, s>>>(c->h_small, c->d_small, 2);
+  k_publish<<<1, 32, 0, s>>>(c->h_small + 10, c->d_small + 2, 1);
+  *L += 1;
   CU(cudaStreamSynchronize(s));
   const size_t nslabs = c->h_small[0];
   const int monotone = c->h_small[1] == 0;
+  // History older than 500 us + slack behind the running maximum was dropped at an earlier batch boundary (or was
+  // never there: a time slice's halo).  A new event whose timestamp steps back further than the slack could have
+  // had contributors in it, so the result would depend on where the batches were cut: an error, not a silent loss.
+  if (c->history_cut && c->h_small[10] > window - FARMS_KILL_OLD_FLOW_TIME)
+    return fail(c, FARMS_ERR_STATE,
+                "a timestamp runs %u us behind the stream's maximum, more than reorder_slack_us = %u allows across "
+                "a batch boundary (raise reorder_slack_us or max_batch)",
+                c->h_small[10], window - FARMS_KILL_OLD_FLOW_TIME);
   g.tile_shift = 4;
   for (;;) {
     g.ntx = (c->W + (1 << g.tile_shift) - 1) >> g.tile_shift;
@@ -434,6 +444,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   CU(cudaMemcpyAsync(c->hlcx, w.lcx + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemcpyAsync(c->hlcy, w.lcy + ts, nh * 8, cudaMemcpyDeviceToDevice, s));
   c->halo = nh;
+  if (ts > 0) c->history_cut = true;
   c->stage_pending = c->ev_set;  // its stage times are read at the next synchronisation
   c->ev_set ^= 1;
   return 0;
@@ -449,6 +460,7 @@ int farms_process_impl(farms_ctx *c, const uint16_t *x, const uint16_t *y, const
   if (n == 0) return FARMS_OK;
   if (!x || !y || !t) return fail(c, FARMS_ERR_ARG, "null event array");
   if (n_skip > n) return fail(c, FARMS_ERR_ARG, "n_skip exceeds n");
+  if (n_skip) c->history_cut = true;  // a time slice: what lies before its halo is not here
   CU(cudaSetDevice(c->cfg.device));
   cudaStream_t s = c->stream;
   if (!c->have_t0) {  // src/vFlow.cpp:194
@@ -777,6 +789,7 @@ int farms_reset(farms_ctx *c) {
   c->total_events = 0;
   c->last_M = 0;
   c->halo = 0;
+  c->history_cut = false;
   c->err.clear();
   return FARMS_OK;
 }

@@ -79,6 +79,7 @@ struct farms_ctx {
   uint32_t last_M = 0;
   unsigned long long valid_seen = 0;  // flow events counted so far in the current process call
   size_t halo = 0;  // events in the halo store
+  bool history_cut = false;  // events older than the halo were dropped (or, for a time slice, never supplied)
   size_t cap_in = 0;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   cudaEvent_t ev_h2d[2]{}, ev_ingest[2]{}, ev_pool[2]{}, ev_d2h[2]{}, ev_fitdone[2]{}, ev_c0 = nullptr, ev_c1 = nullptr;

@@ -97,8 +97,8 @@ void launch_halo_keys(const uint16_t *ex, const uint16_t *ey, size_t h, int H, u
                       cudaStream_t s);
 void launch_links(const uint32_t *skeys, const uint32_t *svals, const uint32_t *et, const uint2 *sae, size_t m,
                   int2 *prevp, int32_t *nextp, cudaStream_t s);
-void launch_slab_flags(const uint32_t *em, const uint32_t *et, size_t m, int slab_shift, uint32_t *flags, uint32_t *nonmono,
-                       cudaStream_t s);
+void launch_slab_flags(const uint32_t *em, const uint32_t *et, size_t m, size_t h, int slab_shift, uint32_t *flags,
+                       uint32_t *nonmono, uint32_t *regress, cudaStream_t s);
 void launch_slice_surface(const uint16_t *x, const uint16_t *y, const uint64_t *t, size_t n, uint32_t index_base,
                           uint64_t t0, int W, int H, unsigned long long *packed, int *err_flag, cudaStream_t s);
 void launch_unpack_surface(const unsigned long long *packed, size_t npx, uint32_t *last_t, uint8_t *hit,

@@ -87,16 +87,25 @@ __global__ void k_serial_fix(const int2 *__restrict__ prevp, const uint32_t *__r
   }
 }
 
-// flags[j] = 1 where a new time slab starts; *nonmono != 0 if any timestamp runs backwards.
-__global__ void k_slab_flags(const uint32_t *__restrict__ em, const uint32_t *__restrict__ et, size_t m, int slab_shift,
-                             uint32_t *__restrict__ flags, uint32_t *__restrict__ nonmono) {
+// flags[j] = 1 where a new time slab starts; *nonmono != 0 if any timestamp runs backwards; *regress = the largest
+// step back (running maximum - own time, us) among the NEW events j >= h of the batch.
+__global__ void k_slab_flags(const uint32_t *__restrict__ em, const uint32_t *__restrict__ et, size_t m, size_t h,
+                             int slab_shift, uint32_t *__restrict__ flags, uint32_t *__restrict__ nonmono,
+                             uint32_t *__restrict__ regress) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool bad = false;
+  uint32_t back = 0, back_new = 0;
   if (j < m) {
     flags[j] = (j > 0 && (em[j] >> slab_shift) != (em[j - 1] >> slab_shift)) ? 1u : 0u;
-    bad = em[j] != et[j];
+    back = em[j] - et[j];
+    back_new = j >= h ? back : 0u;
   }
-  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(nonmono, 1u);
+  if (__any_sync(0xffffffffu, back != 0)) {  // (never taken on a sorted stream)
+    back_new = __reduce_max_sync(0xffffffffu, back_new);
+    if ((threadIdx.x & 31) == 0) {
+      atomicOr(nonmono, 1u);
+      if (back_new) atomicMax(regress, back_new);
+    }
+  }
 }
 
 __global__ void k_slice_surface(const uint16_t *__restrict__ x, const uint16_t *__restrict__ y,
@@ -163,9 +172,9 @@ void launch_links(const uint32_t *skeys, const uint32_t *svals, const uint32_t *
                   int2 *prevp, int32_t *nextp, cudaStream_t s) {
   if (m) k_links<<<nb(m, 256), 256, 0, s>>>(skeys, svals, et, sae, m, prevp, nextp);
 }
-void launch_slab_flags(const uint32_t *em, const uint32_t *et, size_t m, int slab_shift, uint32_t *flags, uint32_t *nonmono,
-                       cudaStream_t s) {
-  if (m) k_slab_flags<<<nb(m, 256), 256, 0, s>>>(em, et, m, slab_shift, flags, nonmono);
+void launch_slab_flags(const uint32_t *em, const uint32_t *et, size_t m, size_t h, int slab_shift, uint32_t *flags,
+                       uint32_t *nonmono, uint32_t *regress, cudaStream_t s) {
+  if (m) k_slab_flags<<<nb(m, 256), 256, 0, s>>>(em, et, m, h, slab_shift, flags, nonmono, regress);
 }
 void launch_slice_surface(const uint16_t *x, const uint16_t *y, const uint64_t *t, size_t n, uint32_t index_base,
                           uint64_t t0, int W, int H, unsigned long long *packed, int *err_flag, cudaStream_t s) {

@@ -31,7 +31,8 @@ typedef enum {
                               index out of bounds: src/vFlow.cpp:264-267)                           */
   FARMS_ERR_CUDA = -3,     /* CUDA runtime failure; farms_last_error() has the text                 */
   FARMS_ERR_NOMEM = -4,    /* host or device allocation failed                                     */
-  FARMS_ERR_STATE = -5,    /* call order violated (e.g. results before any submit)                 */
+  FARMS_ERR_STATE = -5,    /* call order violated, or the stream cannot be carried across a batch boundary
+                              exactly (history overflow, timestamps behind by more than reorder_slack_us) */
   FARMS_ERR_COMM = -6      /* NCCL failure (or libnccl.so.2 cannot be loaded); farms_last_error() has the text */
 } farms_status;
 
@@ -49,7 +50,9 @@ typedef struct {
   uint32_t flags;           /* FARMS_FLAG_*                                                        */
   uint64_t max_batch;       /* events per internal device batch; 0 = default (32 Mi)               */
   uint32_t reorder_slack_us;/* extra history (us) kept across batch boundaries for streams whose
-                               timestamps are not perfectly sorted; 0 = default (1000)            */
+                               timestamps are not perfectly sorted; 0 = default (1000).  A timestamp that runs
+                               further behind the stream's maximum than this, after history was dropped at a
+                               batch boundary, is FARMS_ERR_STATE (never a silently different result)  */
   /* Tuning / test selectors (0 = the library's own choice; never read from the environment): */
   uint32_t pool_variant;    /* fast pooling kernel: 0 = default (7); 1 k_pool_tile (20-byte staged records, 2 slabs
                                per round), 2 bit-table k_pool_bits, 3 k_pool_tile with one CTA per SM, 4 two-phase

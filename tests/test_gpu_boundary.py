@@ -415,3 +415,23 @@ def test_history_overflow_is_an_error_not_a_silent_truncation():
     f.reset()  # the context stays usable
     s = f.process(x[:1000], y[:1000], np.arange(1000, 2000, dtype=np.uint64), columns=["valid"])
     assert len(s["valid"]) == 1000
+
+
+def test_timestamp_step_back_beyond_the_slack_is_an_error_across_batches():
+    """The reference orders by file position.  A timestamp that runs further behind the stream's maximum than
+    reorder_slack_us may have contributors in history that was dropped at an earlier batch boundary: one batch is
+    exact, several batches with too little slack are an error, several batches with enough slack are exact again
+    (ADVICE round 1)."""
+    import farms_b200
+    s, x, y, t, p = synth_stream(1, 60000, 0)
+    t2 = t.copy()
+    t2[45000] -= 5000
+    ref = run_oracle(s.width, s.height, s.filtersize, 5, x, y, t2, p)
+    one = farms_b200.Farms(s.width, s.height, s.filtersize, 5).process(x, y, t2)
+    assert_parity(compare(one, ref, "one batch, one event 5000 us late"))
+    f = farms_b200.Farms(s.width, s.height, s.filtersize, 5, max_batch=20000)
+    with pytest.raises(farms_b200.FarmsError) as e:
+        f.process(x, y, t2)
+    assert e.value.code == farms_b200.ERR_STATE and "reorder_slack_us" in str(e.value)
+    wide = farms_b200.Farms(s.width, s.height, s.filtersize, 5, max_batch=20000, reorder_slack_us=6000).process(x, y, t2)
+    assert_parity(compare(wide, ref, "three batches, slack 6000 us"))
