@@ -638,7 +638,7 @@ int farms_create(farms_ctx **out, const farms_config *cfg) {
   c->fit_chunk = FIT_CHUNK_MIN;
   while (c->fit_chunk < FIT_CHUNK_MAX && (size_t)c->fit_chunk * 6 < c->npx) c->fit_chunk *= 2;
   if (cfg->fit_chunk) c->fit_chunk = (int)std::min<uint32_t>(std::max<uint32_t>(cfg->fit_chunk, 1024u), 1u << 20);
-  if (cfg->pool_variant > 7) return bail(FARMS_ERR_ARG);
+  if (cfg->pool_variant > 8) return bail(FARMS_ERR_ARG);
   if (cfg->pool_variant) c->pool_impl = (int)cfg->pool_variant;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FARMS_ERR_CUDA);

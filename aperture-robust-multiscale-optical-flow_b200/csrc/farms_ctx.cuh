@@ -62,7 +62,7 @@ struct farms_ctx {
   int fit_chunk = FIT_CHUNK_MAX;
   // fast pooling kernel (farms_config.pool_variant): 7 = k_pool_tile16, three slabs per round (the default: measured
   // fastest), 1 = k_pool_tile, 2 = k_pool_bits, 3 = k_pool_tile one CTA per SM, 4 = k_pool_warp, 5 / 6 = k_pool_tile16
-  // with two / four slabs per round
+  // with two / four slabs per round, 8 = 7 with column-culled trips (measured 3 % slower)
   int pool_impl = 7;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[EV_COUNT]{};          // EV_START / EV_END of a whole call

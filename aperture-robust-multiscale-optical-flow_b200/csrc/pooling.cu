@@ -991,7 +991,9 @@ struct WarpSmem {
 };
 
 // stage_slabs for the packed layout (same one-pass ordered compaction over the concatenated index runs)
-template <class SM, int WARPS, int CAP, int NSL>
+// XCULL: also leave, per slot, where the staged records of each tile-column run begin (S.col_off: a target then
+// visits only the columns its window touches).
+template <class SM, int WARPS, int CAP, int NSL, bool XCULL = false>
 __device__ void stage_slabs_packed(const PoolArgs &A, SM &S, int s0, int s1, const Region &R, uint32_t i_round) {
   constexpr int THREADS = WARPS * 32, RING = TK_LB + NSL, STRIDE = SM::STRIDE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1067,6 +1069,7 @@ __device__ void stage_slabs_packed(const PoolArgs &A, SM &S, int s0, int s1, con
     uint4 rec[2];
     double cxv[2] = {0.0, 0.0}, cyv[2] = {0.0, 0.0};
     uint32_t info[2] = {0, 0};
+    int first_of[2] = {-1, -1};  // XCULL: the run whose first raw record this thread holds
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       const uint32_t f = r0 + e * THREADS + tid;
@@ -1078,6 +1081,7 @@ __device__ void stage_slabs_packed(const PoolArgs &A, SM &S, int s0, int s1, con
           if (S.run_o[mid] <= f) lo = mid; else hi = mid - 1;
         }
         lo_hint = lo;
+        if (XCULL && S.run_o[lo] == f) first_of[e] = lo;
         const uint32_t pos = S.run_s[lo] + (f - S.run_o[lo]);
         if (FARMS_CHK(lo >= 0 && lo < nruns && pos < A.cell_start[A.ncells], 101)) {
           rec[e] = A.rec[pos];
@@ -1126,6 +1130,17 @@ __device__ void stage_slabs_packed(const PoolArgs &A, SM &S, int s0, int s1, con
           if (S.slab_f[sl] == f) S.slab_pre[sl] = e ? g1 : g0;
     }
     __syncthreads();
+    if constexpr (XCULL) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        // the compacted position of a run's first raw record is where the run's staged records begin; empty runs
+        // just before it (possibly the tail of the previous slab) begin -- and end -- at the same place
+        for (int q = first_of[e]; q >= 0 && (q == first_of[e] || S.run_o[q] == S.run_o[first_of[e]]); q--) {
+          const int sl = q / nrun, c = q - sl * nrun;
+          S.col_off[(s0 + sl) % RING][c] = (uint16_t)min((e ? g1 : g0) - S.slab_pre[sl], (uint32_t)CAP);
+        }
+      }
+    }
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       const int sl = (int)(info[e] & 0x7fu);
@@ -1153,6 +1168,14 @@ __device__ void stage_slabs_packed(const PoolArgs &A, SM &S, int s0, int s1, con
     S.tag[slot] = s0 + tid;
     S.count[slot] = (int)min(raw, (uint32_t)CAP);
     if (raw > (uint32_t)CAP) S.overflow[slot] = 1;
+    if constexpr (XCULL) S.col_off[slot][nrun] = (uint16_t)min(raw, (uint32_t)CAP);
+  }
+  if constexpr (XCULL) {  // runs with no raw record at or after their start: they begin at the end of everything
+    for (int q = tid; q < nruns; q += THREADS)
+      if (S.run_o[q] >= total) {
+        const int sl = q / nrun, c = q - sl * nrun;
+        S.col_off[(s0 + sl) % RING][c] = (uint16_t)min(out_base - S.slab_pre[sl], (uint32_t)CAP);
+      }
   }
   // test records the unrolled pooling loop may touch past the end of a slot: span 0 never passes
   for (int q = tid; q < nsl * SM::PAD; q += THREADS) {
@@ -1492,7 +1515,7 @@ void launch_warp(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
   kern<<<grid, WARPS * 32, sizeof(SM), s>>>(A, otx, oty, nseg);
 }
 
-template <int WARPS, int CAP, int NSL>
+template <int WARPS, int CAP, int NSL, bool XCULL = false>
 struct PackedSmem {
   static constexpr int RING = TK_LB + NSL, PAD = TK_PAD, STRIDE = CAP + PAD;
   uint2 ta[RING * STRIDE];   // {x_rel | y_rel << 8 | idx_rel[15:0] << 16,  idx_rel[23:16] | span << 8}
@@ -1507,6 +1530,8 @@ struct PackedSmem {
   int tag[RING], count[RING], overflow[RING];
   int dlo[NSL], dhi[NSL], ovf[NSL];
   unsigned int ntg[NSL], tnext, item;
+  // XCULL: per slot, where the staged records of tile-column run c begin ([nrun] = the slot's count)
+  uint16_t col_off[XCULL ? TK_LB + NSL : 1][TK_MAXRUN + 2];
 };
 
 // k_pool_tile16: k_pool_tile on the 16-byte packed records of stage_slabs_packed (8-byte test record: one LDS.64,
@@ -1514,9 +1539,15 @@ struct PackedSmem {
 // four slabs per round at dense-stream slot sizes (twice the tasks per round, half the rounds).
 // SECOND: a later pass over the same items with larger slots; only rounds that still hold undone targets (their
 // staging overflowed the slots of the first pass: locally dense scenes) do any work.
-template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND>
+// XCULL: a slot keeps its records in tile-column runs (16 pixels wide, the order of the pooling index); a target
+// tests only the runs its 101-pixel window touches -- 7 or 8 of the region's 9 or 10 -- instead of the whole slot.
+// The two halves of a warp walk the union of their two ranges (same shared-memory addresses for both: separate
+// ranges measured 3 % slower than no culling at all, the record loads then cost two wavefronts), and the targets of
+// a round are listed in index order (tile column by tile column) so that the two targets of a pair mostly want the
+// same columns.
+template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND, bool XCULL>
 __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, int otx_n, int oty_n, int nseg) {
-  using SM = PackedSmem<WARPS, CAP, NSL>;
+  using SM = PackedSmem<WARPS, CAP, NSL, XCULL>;
   constexpr int STRIDE = SM::STRIDE;
   constexpr int THREADS = WARPS * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1611,7 +1642,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
       // staged slabs are a contiguous range ending at the last staged slab, so what is missing is a suffix
       int s_new = s_first;
       while (s_new <= s_last && S.tag[s_new % (TK_LB + NSL)] == s_new) s_new++;  // uniform: tags are read after a barrier
-      if (s_new <= s_last) stage_slabs_packed<SM, WARPS, CAP, NSL>(A, S, s_new, s_last, R, i_round);
+      if (s_new <= s_last) stage_slabs_packed<SM, WARPS, CAP, NSL, XCULL>(A, S, s_new, s_last, R, i_round);
       __syncthreads();
       if (tid < NSL) {
         int o = 0;
@@ -1629,21 +1660,38 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
         if (tid == 0) S.tnext = 0;
         __syncthreads();
 #pragma unroll
-        for (int w = 0; w < NSL; w++)
-          for (uint32_t f = t0 + tid; f < min(nraw[w], t0 + TK_MAXT); f += THREADS) {
-            const uint32_t n0 = tb[w][0] - ta[w][0];
-            const uint32_t pos = f < n0 ? ta[w][0] + f : ta[w][1] + (f - n0);
+        for (int w = 0; w < NSL; w++) {
+          const uint32_t lim = min(nraw[w], t0 + TK_MAXT), n0 = tb[w][0] - ta[w][0];
+          // fast-path conditions: not a halo event, window rows stay below 2H, staging complete
+          auto wanted = [&](const uint32_t pos) {
             const uint4 r = A.rec[pos];
             const int yi = (int)(r.x >> 16);
-            // fast-path conditions: not a halo event, window rows stay below 2H, staging complete
-            const bool ok = (int)r.z >= A.h && min(yi + FARMS_MAX_WINDOW, W - 1) <= 2 * H - 1 && !S.ovf[w] &&
-                            (!SECOND || !A.done[pos]);
-            if (ok) {
-              const unsigned int slot_t = atomicAdd(&S.ntg[w], 1u);
-              if (FARMS_CHK(slot_t < (unsigned int)TK_MAXT && pos < A.cell_start[A.ncells], 111)) S.tlist[w][slot_t] = pos;
+            return (int)r.z >= A.h && min(yi + FARMS_MAX_WINDOW, W - 1) <= 2 * H - 1 && !S.ovf[w] &&
+                   (!SECOND || !A.done[pos]);
+          };
+          if (XCULL) {  // a warp lists its 32 consecutive index positions in order
+            for (uint32_t fb = t0 + warp * 32; fb < lim; fb += THREADS) {
+              const uint32_t f = fb + lane;
+              const uint32_t pos = f < n0 ? ta[w][0] + f : ta[w][1] + (f - n0);
+              const bool ok = f < lim && wanted(pos);
+              const unsigned bal = __ballot_sync(0xffffffffu, ok);
+              unsigned int base = 0;
+              if (lane == 0 && bal) base = atomicAdd(&S.ntg[w], (unsigned int)__popc(bal));
+              base = __shfl_sync(0xffffffffu, base, 0);
+              const unsigned int slot_t = base + __popc(bal & ((1u << lane) - 1u));
+              if (ok && FARMS_CHK(slot_t < (unsigned int)TK_MAXT && pos < A.cell_start[A.ncells], 111))
+                S.tlist[w][slot_t] = pos;
             }
-
+          } else {
+            for (uint32_t f = t0 + tid; f < lim; f += THREADS) {
+              const uint32_t pos = f < n0 ? ta[w][0] + f : ta[w][1] + (f - n0);
+              if (wanted(pos)) {
+                const unsigned int slot_t = atomicAdd(&S.ntg[w], 1u);
+                if (FARMS_CHK(slot_t < (unsigned int)TK_MAXT && pos < A.cell_start[A.ncells], 111)) S.tlist[w][slot_t] = pos;
+              }
+            }
           }
+        }
         __syncthreads();
         // Tasks: first pairs of targets of the same slab (lanes 0-15 pool one event, lanes 16-31 the next; both
         // halves share their loop bounds), then "solo" targets pooled by the two halves together, each half taking
@@ -1708,13 +1756,36 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
 #pragma unroll
           for (int q = 0; q < FARMS_NSCALES; q++) S.acc[warp][q][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
           const int sl = S.dlo[w], sh = S.dhi[w];
+          // XCULL: the tile-column runs this target's window touches.  Runs 0 .. xr_n0-1 hold the region's columns for
+          // rows < H, the runs after them the columns of the aliased pixels (i + 1, j - H), whose PHYSICAL x is one
+          // more than the window coordinate they are tested with.
+          int xc_lo = 0, xc_hi = 0, xa_lo = 0, xa_hi = -1, nparts = 1;
+          if (XCULL) {
+            const int ts = A.g.tile_shift, tx0 = R.rx0 >> ts, tx1 = R.rx1 >> ts;
+            const int xr_n0 = R.ry1 >= R.ry0 ? tx1 - tx0 + 1 : 0;
+            xc_lo = max((xi - FARMS_MAX_WINDOW) >> ts, tx0) - tx0;
+            xc_hi = xr_n0 ? min((xi + FARMS_MAX_WINDOW) >> ts, tx1) - tx0 + 1 : 0;  // (one past the last run)
+            if (!xr_n0) xc_lo = 0;
+            if (R.ay1 >= 0) {
+              const int atx0 = R.ax0 >> ts, atx1 = R.ax1 >> ts;
+              xa_lo = xr_n0 + max((xi + 1 - FARMS_MAX_WINDOW) >> ts, atx0) - atx0;
+              xa_hi = xr_n0 + min((xi + 1 + FARMS_MAX_WINDOW) >> ts, atx1) - atx0 + 1;
+              nparts = 2;
+            }
+            // both halves walk the union of their two ranges: they then read the same records (one shared-memory
+            // wavefront per load instead of two) and the trip loops stay uniform across the warp
+            xc_lo = min(xc_lo, __shfl_xor_sync(0xffffffffu, xc_lo, 16));
+            xc_hi = max(xc_hi, __shfl_xor_sync(0xffffffffu, xc_hi, 16));
+            xa_lo = min(xa_lo, __shfl_xor_sync(0xffffffffu, xa_lo, 16));
+            xa_hi = max(xa_hi, __shfl_xor_sync(0xffffffffu, xa_hi, 16));
+          }
           for (int s = sl; s <= sh; s++) {
             const int slot = s % (TK_LB + NSL);
             const int n = S.count[slot];
             const uint32_t iir = ii - S.slot_base[slot];
             const uint2 *recs = &S.ta[slot * STRIDE];
             const float2 *pays = &S.pb[slot * STRIDE];
-            ncand += (sub == 0 && have) ? n : 0;
+            if (!XCULL) ncand += (sub == 0 && have) ? n : 0;
             // one staged record against this half-warp's event: test, and on a pass add it to the lane's ring partials
             auto pool_one = [&](const uint2 c, const int q) {
               const uint32_t d4 = __vabsdiffu4(c.x, tw);  // |dx| in byte 0, |dy| in byte 1
@@ -1738,21 +1809,33 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
             };
             // groups of 16 records: four per trip while four remain, the last one to three singly (a slot holds
             // ~260 records: a fifth trip of four groups would test 60 padding records)
-            const int ngroups = (n + 15) >> 4, nfull = (ngroups & ~3) << 4;
-            for (int q0 = sub + (solo ? 64 * half : 0); q0 < nfull; q0 += solo ? 128 : 64) {
-              uint2 c[4];
-#pragma unroll
-              for (int u = 0; u < 4; u++) {
-                (void)FARMS_CHK(q0 + 16 * u < STRIDE && slot >= 0 && slot < SM::RING, 114);
-                c[u] = recs[q0 + 16 * u];
+            for (int part = 0; part < nparts; part++) {  // XCULL: the window's columns, then its aliased columns
+              int beg = 0, end = n;
+              if (XCULL) {
+                beg = S.col_off[slot][part ? xa_lo : xc_lo];
+                end = max((int)S.col_off[slot][part ? xa_hi : xc_hi], beg);
+                (void)FARMS_CHK(end <= n && (part ? xa_hi : xc_hi) <= TK_MAXRUN, 118);
+                ncand += (sub == 0 && have) ? end - beg : 0;
               }
+              // (the last trip of four may read up to 15 records past `end`: zeroed padding, or records of the next
+              // column, which lies outside the window -- except where aliased runs follow: there only whole groups)
+              const int ngroups = (XCULL && nparts == 2 && part == 0) ? (end - beg) >> 4 : (end - beg + 15) >> 4;
+              const int nfull = beg + ((ngroups & ~3) << 4);
+              for (int q0 = beg + sub + (solo ? 64 * half : 0); q0 < nfull; q0 += solo ? 128 : 64) {
+                uint2 c[4];
 #pragma unroll
-              for (int u = 0; u < 4; u++) pool_one(c[u], q0 + 16 * u);
-            }
-            // (a solo target's two halves take alternate tail groups; the last group reads into the zeroed padding)
-            for (int q0 = nfull + sub + (solo ? 16 * half : 0); q0 < n; q0 += solo ? 32 : 16) {
-              (void)FARMS_CHK(q0 < STRIDE, 117);
-              pool_one(recs[q0], q0);
+                for (int u = 0; u < 4; u++) {
+                  (void)FARMS_CHK(q0 + 16 * u < STRIDE && slot >= 0 && slot < SM::RING, 114);
+                  c[u] = recs[q0 + 16 * u];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) pool_one(c[u], q0 + 16 * u);
+              }
+              // (a solo target's two halves take alternate tail groups)
+              for (int q0 = nfull + sub + (solo ? 16 * half : 0); q0 < end; q0 += solo ? 32 : 16) {
+                (void)FARMS_CHK(q0 < STRIDE, 117);
+                pool_one(recs[q0], q0);
+              }
             }
           }
           __syncwarp();
@@ -1856,12 +1939,12 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pool_tile16(PoolArgs A, in
   }
 }
 
-template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND>
+template <int WARPS, int CAP, int NSL, int CTAS, bool SECOND, bool XCULL = false>
 void launch_tile16(const PoolArgs &A0, int nslabs, int num_sms, cudaStream_t s) {
   PoolArgs A = A0;
-  using SM = PackedSmem<WARPS, CAP, NSL>;
+  using SM = PackedSmem<WARPS, CAP, NSL, XCULL>;
   static_assert(sizeof(SM) <= (CTAS == 2 ? 115712 : 232448), "shared memory of the tile kernel: 227 KB per CTA, 228 KB per SM");
-  auto kern = k_pool_tile16<WARPS, CAP, NSL, CTAS, SECOND>;
+  auto kern = k_pool_tile16<WARPS, CAP, NSL, CTAS, SECOND, XCULL>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   const int otx = (A.g.W + OT - 1) >> OT_SHIFT, oty = (A.g.H + OT - 1) >> OT_SHIFT;
@@ -2501,6 +2584,17 @@ int launch_pooling(const uint4 *rec, const double *pay, const uint32_t *cell_sta
       if (kernels_used) *kernels_used |= per_region < 200.0 ? FARMS_POOLK_TILE16_SPARSE : FARMS_POOLK_TILE16_DENSE;
       A.work_counter = work_counter + 2;
       launch_tile16<16, 960, 4, 1, true>(A, nslabs, num_sms, s);
+      if (kernels_used) *kernels_used |= FARMS_POOLK_TILE16_SECOND;
+      launches++;
+    } else if (fast == 8) {
+      // variant 7 with column-culled trips (XCULL)
+      const double per_region = flow_per_slab * 17424.0 / ((double)g.W * (double)g.H);
+      if (per_region < 200.0) launch_tile16<8, 416, 4, 2, false, true>(A, nslabs, num_sms, s);
+      else launch_tile16<8, 512, 3, 2, false, true>(A, nslabs, num_sms, s);
+      if (kernels_used)
+        *kernels_used |= (per_region < 200.0 ? FARMS_POOLK_TILE16_SPARSE : FARMS_POOLK_TILE16_DENSE) | FARMS_POOLK_TILE16_XCULL;
+      A.work_counter = work_counter + 2;
+      launch_tile16<16, 960, 4, 1, true, true>(A, nslabs, num_sms, s);
       if (kernels_used) *kernels_used |= FARMS_POOLK_TILE16_SECOND;
       launches++;
     } else if (fast == 4) {

@@ -22,8 +22,8 @@ FLAG_GENERIC_POOLING = FLAG_EXACT_POOLING
 FLAG_SERIAL_SEMANTICS = 4
 POOLK_TILE_DENSE, POOLK_TILE_SPARSE, POOLK_TILE_SECOND, POOLK_TILE_ONE_CTA, POOLK_BITS, POOLK_ANY = 1, 2, 4, 8, 16, 32
 POOLK_WARP_DENSE, POOLK_WARP_SPARSE, POOLK_WARP_SECOND = 64, 128, 256
-POOLK_TILE16_DENSE, POOLK_TILE16_SPARSE, POOLK_TILE16_SECOND = 512, 1024, 2048
-POOL_VARIANTS = {"tile": 1, "bits": 2, "tile1": 3, "warp": 4, "tile16": 5, "tile16x4": 6, "tile16x3": 7}
+POOLK_TILE16_DENSE, POOLK_TILE16_SPARSE, POOLK_TILE16_SECOND, POOLK_TILE16_XCULL = 512, 1024, 2048, 4096
+POOL_VARIANTS = {"tile": 1, "bits": 2, "tile1": 3, "warp": 4, "tile16": 5, "tile16x4": 6, "tile16x3": 7, "tile16c": 8}
 
 EXPORTS = [
     "farms_abi_version", "farms_build_is_checked", "farms_create", "farms_destroy", "farms_reset", "farms_last_error", "farms_normalize_filtersize", "farms_get_params",

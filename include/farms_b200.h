@@ -57,7 +57,8 @@ typedef struct {
   uint32_t pool_variant;    /* fast pooling kernel: 0 = default (7); 1 k_pool_tile (20-byte staged records, 2 slabs
                                per round), 2 bit-table k_pool_bits, 3 k_pool_tile with one CTA per SM, 4 two-phase
                                k_pool_warp, 5 / 6 / 7 k_pool_tile16 (16-byte packed records) with 2 / 4 / 3 slabs per
-                               round.  All are parity-tested against the oracle; 7 measured fastest.          */
+                               round, 8 = 7 with column-culled trips.  All are parity-tested against the oracle;
+                               7 measured fastest.                                                           */
   uint32_t fit_chunk;       /* events per plane-fit chunk (SAE snapshot interval); 0 = from the sensor size  */
   uint32_t slab_target;     /* flow events per (tile region, time slab) the slab length is chosen for; 0 = 70 */
   uint32_t reserved[4];
@@ -133,6 +134,7 @@ typedef struct {
 #define FARMS_POOLK_TILE16_DENSE 512u    /* k_pool_tile16 (16-byte packed staged records), dense streams      */
 #define FARMS_POOLK_TILE16_SPARSE 1024u  /* k_pool_tile16<8, 416, 4, 2>, thin slabs                           */
 #define FARMS_POOLK_TILE16_SECOND 2048u  /* k_pool_tile16<16, 960, 4, 1>, flagged second pass                 */
+#define FARMS_POOLK_TILE16_XCULL 4096u   /* the k_pool_tile16 launches were the column-culled ones (pool_variant 8) */
 
 /* ---- lifetime: replaces `vFlowManager vFlowM(...)` (src/main.cpp:186) ---- */
 int farms_create(farms_ctx **out, const farms_config *cfg);

@@ -120,7 +120,7 @@ def test_fast_pooling_equals_exact_pooling_on_long_dense_streams(config, n, star
     assert np.array_equal(fast["global_r"][~v], exact["global_r"][~v])
 
 
-@pytest.mark.parametrize("impl", ["bits", "tile1", "warp", "tile", "tile16", "tile16x4", "tile16x3"])
+@pytest.mark.parametrize("impl", ["bits", "tile1", "warp", "tile", "tile16", "tile16x4", "tile16x3", "tile16c"])
 def test_alternative_pooling_kernels_match_oracle_and_exact_kernel(impl):
     """k_pool_bits (farms_config.pool_variant 2: prefix bit tables over the staged records, a measured alternative
     to the default staged-list kernel) and the one-CTA-per-SM instantiation of k_pool_tile (variant 3) obey the same
@@ -134,7 +134,8 @@ def test_alternative_pooling_kernels_match_oracle_and_exact_kernel(impl):
             "tile": farms_b200.POOLK_TILE_DENSE | farms_b200.POOLK_TILE_SPARSE,
             "tile16": farms_b200.POOLK_TILE16_DENSE | farms_b200.POOLK_TILE16_SPARSE,
             "tile16x4": farms_b200.POOLK_TILE16_DENSE | farms_b200.POOLK_TILE16_SPARSE,
-            "tile16x3": farms_b200.POOLK_TILE16_DENSE | farms_b200.POOLK_TILE16_SPARSE}[impl]
+            "tile16x3": farms_b200.POOLK_TILE16_DENSE | farms_b200.POOLK_TILE16_SPARSE,
+            "tile16c": farms_b200.POOLK_TILE16_XCULL}[impl]
     assert f.timings()["pool_kernels"] & want
     s, x, y, t, p = synth_stream(4, 2_000_000, 2000)
     fast = farms_b200.Farms(s.width, s.height, s.filtersize, 5, pool_variant=impl).process(x, y, t)
@@ -177,6 +178,8 @@ LONG = [
     (4, 2_000_000, 0, "POOLK_TILE16_DENSE"),      # the library's default = what bench.py times (tile16x3)
     (4, 2_000_000, "tile16", "POOLK_TILE16_DENSE"),
     (4, 2_000_000, "tile16x4", "POOLK_TILE16_DENSE"),
+    (4, 2_000_000, "tile16c", "POOLK_TILE16_XCULL"),   # column-culled trips (width > height: aliased runs too)
+    (3, 2_000_000, "tile16c", "POOLK_TILE16_XCULL"),
     (3, 2_000_000, 0, None),
     (2, 1_000_000, 0, None),
     (3, 2_000_000, "tile", None),
@@ -216,7 +219,7 @@ def test_steady_state_parity_with_the_oracle(config, n, variant, first):
         assert tm["pool_kernels"] & getattr(farms_b200, first), tm
 
 
-@pytest.mark.parametrize("variant", ["tile", "warp", "tile16x4", "tile16x3"])
+@pytest.mark.parametrize("variant", ["tile", "warp", "tile16x4", "tile16x3", "tile16c"])
 def test_dense_stream_second_pass_and_general_kernel_against_the_oracle(variant):
     """Time-compressed 1280x720 stream (2.5x the density): the 512-record slots of the first pass overflow for a
     good share of the rounds, so the flagged second pass <16,768,4,1> and k_pool_any both pool a substantial number
@@ -235,12 +238,13 @@ def test_dense_stream_second_pass_and_general_kernel_against_the_oracle(variant)
     dense, second = {"tile": (farms_b200.POOLK_TILE_DENSE, farms_b200.POOLK_TILE_SECOND),
                      "warp": (farms_b200.POOLK_WARP_DENSE, farms_b200.POOLK_WARP_SECOND),
                      "tile16x4": (farms_b200.POOLK_TILE16_DENSE, farms_b200.POOLK_TILE16_SECOND),
-                     "tile16x3": (farms_b200.POOLK_TILE16_DENSE, farms_b200.POOLK_TILE16_SECOND)}[variant]
+                     "tile16x3": (farms_b200.POOLK_TILE16_DENSE, farms_b200.POOLK_TILE16_SECOND),
+                     "tile16c": (farms_b200.POOLK_TILE16_DENSE, farms_b200.POOLK_TILE16_SECOND)}[variant]
     assert tm["pool_kernels"] & dense and tm["pool_kernels"] & second
     assert tm["pool_events_second"] > 1000, tm
 
 
-@pytest.mark.parametrize("variant", ["tile", "warp", "tile16x4", 0])
+@pytest.mark.parametrize("variant", ["tile", "warp", "tile16x4", "tile16c", 0])
 @pytest.mark.parametrize("w,h", [(20, 160), (48, 256), (33, 300)])
 def test_tall_sensors_fast_path(w, h, variant):
     """height >= width + 100: the reference bounds window rows by width-1 (src/vFlow.cpp:1000), so owner tiles

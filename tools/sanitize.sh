@@ -12,7 +12,7 @@ cs=/usr/local/cuda/bin/compute-sanitizer
 timeout 300 $cs --tool memcheck --print-limit 20 python tools/sanitize_cases.py sparse > ${out}_memcheck_sparse.log 2>&1
 echo "compute-sanitizer memcheck sparse: exit=$? $(head -c 300 ${out}_memcheck_sparse.log | tr '\n' ' ')" >> ${out}_summary.txt
 export FARMS_B200_LIB=$PWD/aperture-robust-multiscale-optical-flow_b200/libfarms_b200_checked.so
-for case in dense sparse bits tile1 tile warp tile16 tile16x4 tall aliased exact serial long4 long3; do
+for case in ${CASES:-dense sparse bits tile1 tile warp tile16 tile16x4 tile16c tall aliased aliased_c exact serial long4 long3 long4_c}; do
   python tools/sanitize_cases.py $case --check > ${out}_checked_${case}.log 2>&1
   echo "checked-build $case exit=$? $(grep -E 'sanitize_case|Error|error' ${out}_checked_${case}.log | tail -2 | tr '\n' ' ')" >> ${out}_summary.txt
 done

@@ -30,25 +30,26 @@ def build(case):
         s = Synth(1)
         x, y, t, p = s.first(25_000, 0)
         return s.width, s.height, s.filtersize, x, y, t, {}
-    if case in ("bits", "tile1", "tile", "warp", "tile16", "tile16x4"):
+    if case in ("bits", "tile1", "tile", "warp", "tile16", "tile16x4", "tile16c"):
         s = Synth(2)
         x, y, t, p = s.first(100_000, 0)
         return s.width, s.height, s.filtersize, x, y, squeeze(t, 4.0), {"pool_variant": case}
     if case == "tall":       # owner tiles without reachable rows (width-1 row bound)
         x, y, t, p = sweeps(20, 160, slopes=((9, 2), (-7, 3)), gap=150)
         return 20, 160, 5, x, y, t.astype(np.uint64), {}
-    if case == "aliased":    # width > height: logical rows >= H alias the next column
+    if case in ("aliased", "aliased_c"):    # width > height: logical rows >= H alias the next column
         x, y, t, p = sweeps(150, 40, slopes=((9, 2), (-7, 3)), gap=150)
-        return 150, 40, 5, x, y, t.astype(np.uint64), {}
+        return 150, 40, 5, x, y, t.astype(np.uint64), {"pool_variant": "tile16c"} if case == "aliased_c" else {}
     if case == "serial":     # FARMS_FLAG_SERIAL_SEMANTICS
         import farms_b200
         s = Synth(1)
         x, y, t, p = s.first(40_000, 0)
         return s.width, s.height, s.filtersize, x, y, t, {"flags": farms_b200.FLAG_SERIAL_SEMANTICS}
-    if case in ("long4", "long3"):  # steady-state density, default kernels, several internal batches
-        s = Synth(4 if case == "long4" else 3)
+    if case in ("long4", "long3", "long4_c"):  # steady-state density, default kernels, several internal batches
+        s = Synth(3 if case == "long3" else 4)
         x, y, t, p = s.first(1_500_000, 0)
-        return s.width, s.height, s.filtersize, x, y, t, {"max_batch": 400_000}
+        return s.width, s.height, s.filtersize, x, y, t, dict({"max_batch": 400_000},
+                                                              **({"pool_variant": "tile16c"} if case == "long4_c" else {}))
     if case == "exact":      # k_pool_any for every event
         import farms_b200
         s = Synth(3)
