@@ -25,6 +25,7 @@
 #include <condition_variable>
 #include <cstring>
 #include <mutex>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -65,7 +66,8 @@ NcclApi *nccl_api() {
       if (api.handle) break;
     }
     if (!api.handle) {
-      api.error = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
+      const char *why = dlerror();  // (a second call would return null: dlerror clears its state)
+      api.error = std::string("cannot load libnccl.so.2: ") + (why ? why : "?");
       return;
     }
 #define SYM(field, name)                                                  \
@@ -260,14 +262,30 @@ int gather_hook(void *user, farms_ctx *c, const FarmsBatchView *v) {
 }
 
 // Agree on the gather path (NCCL transport).  The root describes its destination buffer -- IPC handle of the
-// allocation, offset of dst inside it, its process id and the raw address -- and broadcasts the 128 bytes; every
+// allocation, offset of dst inside it, a token of its process and the raw address -- and broadcasts the 128 bytes; every
 // other rank maps it (cudaIpcOpenMemHandle, cached across calls; the plain address if it shares the root's
 // process).  An all-gather of one flag per rank then settles it: peer memory only if EVERY rank succeeded.
 struct IpcDesc {
   cudaIpcMemHandle_t handle;  // 64 bytes
-  uint64_t offset, address, pid, ok;
+  uint64_t offset, address, process, ok;
 };
 static_assert(sizeof(IpcDesc) <= 128, "IPC descriptor fits the broadcast buffer");
+
+// Identifies this process among the ranks of a node.  Not the pid alone: ranks in different containers (separate
+// pid namespaces) can share a pid, and taking the root's raw address then would be a wild pointer.
+uint64_t process_token() {
+  static const uint64_t token = [] {
+    uint64_t v = ((uint64_t)getpid() << 32) ^ (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count();
+    v ^= (uint64_t)(uintptr_t)&g_groups_mu * 0x9E3779B97F4A7C15ull;
+    try {
+      std::random_device rd;
+      v ^= ((uint64_t)rd() << 32) ^ (uint64_t)rd();
+    } catch (...) {
+    }
+    return v ? v : 1ull;
+  }();
+  return token;
+}
 
 int setup_gather_path(farms_comm *cm, const farms_gather *g) {
   NcclApi *N = nccl_api();
@@ -289,7 +307,7 @@ int setup_gather_path(farms_comm *cm, const farms_gather *g) {
     }
     cudaGetLastError();
     d->address = (uint64_t)(uintptr_t)g->dst;
-    d->pid = (uint64_t)getpid();
+    d->process = process_token();
   }
   CUC(cudaMemcpyAsync(cm->d_ipc, cm->h_ipc, 128, cudaMemcpyHostToDevice, s));
   NC(N->Broadcast(cm->d_ipc, cm->d_ipc, 128, ncclChar, g->root, cm->nccl, s));
@@ -299,7 +317,7 @@ int setup_gather_path(farms_comm *cm, const farms_gather *g) {
   uint64_t mine = 1;
   if (cm->rank != g->root) {
     mine = 0;
-    if (d->pid == (uint64_t)getpid()) {  // root is a thread of this process: its address is ours
+    if (d->process == process_token()) {  // root is a thread of this process: its address is ours
       cm->peer_dst = (float *)(uintptr_t)d->address;
       mine = 1;
     } else if (d->ok) {
@@ -378,19 +396,31 @@ int farms_comm_create(farms_comm **out, farms_ctx *ctx, int nranks, int rank, co
   if (nranks > 1 && cm->local) {
     uint64_t key;
     memcpy(&key, id128, sizeof key);
-    std::lock_guard<std::mutex> lk(g_groups_mu);
-    for (auto &kv : g_groups)
-      if (kv.first == key) cm->group = kv.second;
-    if (!cm->group) {
-      cm->group = new LocalGroup();
-      cm->group->nranks = nranks;
-      cm->group->surf_t.assign(nranks, nullptr);
-      cm->group->surf_hit.assign(nranks, nullptr);
-      cm->group->meta.assign((size_t)nranks * 4, 0);
-      g_groups.emplace_back(key, cm->group);
+    bool mismatch = false;
+    {
+      std::lock_guard<std::mutex> lk(g_groups_mu);
+      LocalGroup *found = nullptr;
+      for (auto &kv : g_groups)
+        if (kv.first == key) found = kv.second;
+      if (!found) {
+        found = new LocalGroup();
+        found->nranks = nranks;
+        found->surf_t.assign(nranks, nullptr);
+        found->surf_hit.assign(nranks, nullptr);
+        found->meta.assign((size_t)nranks * 4, 0);
+        g_groups.emplace_back(key, found);
+      }
+      if (found->nranks == nranks) {
+        cm->group = found;
+        found->refs++;
+      } else {
+        mismatch = true;  // (bail takes the registry lock itself: not from inside this scope)
+      }
     }
-    if (cm->group->nranks != nranks) return bail(FARMS_ERR_ARG);
-    cm->group->refs++;
+    if (mismatch) {
+      farms_fail(ctx, FARMS_ERR_ARG, "the group with this id was created for a different number of ranks");
+      return bail(FARMS_ERR_ARG);
+    }
   } else if (nranks > 1) {
     NcclApi *N = nccl_api();
     if (!N->error.empty()) {
