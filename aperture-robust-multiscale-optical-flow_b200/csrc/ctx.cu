@@ -18,27 +18,19 @@
 
 #include "farms_ctx.cuh"
 
-namespace {
-
-int fail(farms_ctx *c, int code, const char *fmt, ...) {
+static int vfail(farms_ctx *c, int code, const char *fmt, va_list ap) {
   char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
   vsnprintf(buf, sizeof buf, fmt, ap);
-  va_end(ap);
   if (c) c->err = buf;
   return code;
 }
 
-}  // namespace
-
+// records the message for farms_last_error and returns the status code (shared with comm.cu)
 int farms_fail(farms_ctx *c, int code, const char *fmt, ...) {
-  char buf[512];
   va_list ap;
   va_start(ap, fmt);
-  vsnprintf(buf, sizeof buf, fmt, ap);
+  code = vfail(c, code, fmt, ap);
   va_end(ap);
-  if (c) c->err = buf;
   return code;
 }
 
@@ -48,7 +40,7 @@ namespace {
   do {                                                                                                    \
     cudaError_t e_ = (call);                                                                              \
     if (e_ != cudaSuccess)                                                                                \
-      return fail(c, e_ == cudaErrorMemoryAllocation ? FARMS_ERR_NOMEM : FARMS_ERR_CUDA, "%s: %s (%s:%d)", \
+      return farms_fail(c, e_ == cudaErrorMemoryAllocation ? FARMS_ERR_NOMEM : FARMS_ERR_CUDA, "%s: %s (%s:%d)", \
                   #call, cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
   } while (0)
 
@@ -303,14 +295,14 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   *L += 3;
   CU(cudaStreamSynchronize(s));
   // (k_ingest clamps an out-of-range event to pixel (0,0), so the kernels above were safe to run)
-  if (((int *)c->h_small)[8]) return fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
+  if (((int *)c->h_small)[8]) return farms_fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
   const size_t ts = c->h_small[48];
   const uint32_t last_M = c->h_small[49];
   // more than HALO_CAP events inside the pooling window (+ slack): truncating the halo would silently lose
   // contributors for the next batch, so this is an error (timestamps in the wrong unit, or a pathological burst) --
   // raised before the pooling stage, whose cost grows with the number of events per pixel inside the window
   if (m - ts > HALO_CAP)
-    return fail(c, FARMS_ERR_STATE, "%zu events within the last %u us exceed the %zu-event history kept across batches",
+    return farms_fail(c, FARMS_ERR_STATE, "%zu events within the last %u us exceed the %zu-event history kept across batches",
                 m - ts, window, HALO_CAP);
   if ((rc = collect_stage_times(c, stage_ms))) return rc;  // of the previous batch: its events have all completed
   if (c->serial) {
@@ -355,7 +347,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
   // never there: a time slice's halo).  A new event whose timestamp steps back further than the slack could have
   // had contributors in it, so the result would depend on where the batches were cut: an error, not a silent loss.
   if (c->history_cut && c->h_small[10] > window - FARMS_KILL_OLD_FLOW_TIME)
-    return fail(c, FARMS_ERR_STATE,
+    return farms_fail(c, FARMS_ERR_STATE,
                 "a timestamp runs %u us behind the stream's maximum, more than reorder_slack_us = %u allows across "
                 "a batch boundary (raise reorder_slack_us or max_batch)",
                 c->h_small[10], window - FARMS_KILL_OLD_FLOW_TIME);
@@ -367,7 +359,7 @@ int run_batch(farms_ctx *c, int set, const uint16_t *dx, const uint16_t *dy, con
     g.tile_shift++;
   }
   const size_t ncells = nslabs * (size_t)g.ntx * g.nty;
-  if (ncells >= (1ull << 31)) return fail(c, FARMS_ERR_NOMEM, "pooling index too large (%zu cells)", ncells);
+  if (ncells >= (1ull << 31)) return farms_fail(c, FARMS_ERR_NOMEM, "pooling index too large (%zu cells)", ncells);
   if ((rc = ensure(c, c->cell_start, (ncells + 1) * sizeof(uint32_t)))) return rc;
   CU(cudaMemsetAsync(c->cell_start.p, 0, (ncells + 1) * sizeof(uint32_t), s));
   launch_cell_keys(w.ex, w.ey, w.em, w.flags, w.len, m, g, (uint32_t)ncells, w.keyA, w.valA, w.slab_ids, w.slab_first, s);
@@ -458,8 +450,8 @@ int farms_process_impl(farms_ctx *c, const uint16_t *x, const uint16_t *y, const
   if (!c) return FARMS_ERR_ARG;
   c->err.clear();
   if (n == 0) return FARMS_OK;
-  if (!x || !y || !t) return fail(c, FARMS_ERR_ARG, "null event array");
-  if (n_skip > n) return fail(c, FARMS_ERR_ARG, "n_skip exceeds n");
+  if (!x || !y || !t) return farms_fail(c, FARMS_ERR_ARG, "null event array");
+  if (n_skip > n) return farms_fail(c, FARMS_ERR_ARG, "n_skip exceeds n");
   if (n_skip) c->history_cut = true;  // a time slice: what lies before its halo is not here
   CU(cudaSetDevice(c->cfg.device));
   cudaStream_t s = c->stream;
@@ -575,14 +567,11 @@ int farms_process_impl(farms_ctx *c, const uint16_t *x, const uint16_t *y, const
 #ifdef FARMS_CHECKED
   {
     const unsigned int a = farms_chk_index(s), b = farms_chk_planefit(s), d = farms_chk_pooling(s);
-    if (a | b | d) return fail(c, FARMS_ERR_STATE, "self-check failed: index %u, plane fit %u, pooling %u (csrc/*.cu FARMS_CHK codes)", a, b, d);
+    if (a | b | d) return farms_fail(c, FARMS_ERR_STATE, "self-check failed: index %u, plane fit %u, pooling %u (csrc/*.cu FARMS_CHK codes)", a, b, d);
   }
 #endif
   return FARMS_OK;
 }
-
-namespace {
-}  // namespace
 
 extern "C" {
 
@@ -796,7 +785,7 @@ int farms_reset(farms_ctx *c) {
 
 int farms_set_t0(farms_ctx *c, uint64_t t0) {
   if (!c) return FARMS_ERR_ARG;
-  if (c->total_events) return fail(c, FARMS_ERR_STATE, "farms_set_t0 after events were processed");
+  if (c->total_events) return farms_fail(c, FARMS_ERR_STATE, "farms_set_t0 after events were processed");
   c->t0 = t0;
   c->have_t0 = true;
   return FARMS_OK;
@@ -838,14 +827,14 @@ static int slice_surface_finish(farms_ctx *c, uint32_t *d_last_t, uint8_t *d_hit
   k_publish<<<1, 32, 0, c->stream>>>(c->h_small + 8, (const uint32_t *)c->d_err, 1);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
-  if (((int *)c->h_small)[8]) return fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
+  if (((int *)c->h_small)[8]) return farms_fail(c, FARMS_ERR_RANGE, "event outside the %dx%d sensor", c->W, c->H);
   return FARMS_OK;
 }
 
 int farms_slice_surface(farms_ctx *c, const uint16_t *d_x, const uint16_t *d_y, const uint64_t *d_t, uint64_t n,
                         uint64_t t0, uint32_t *d_last_t, uint8_t *d_hit) {
   if (!c || !d_last_t || !d_hit || (n && (!d_x || !d_y || !d_t))) return FARMS_ERR_ARG;
-  if (n >= (1ull << 32) - 1) return fail(c, FARMS_ERR_ARG, "slice too long");
+  if (n >= (1ull << 32) - 1) return farms_fail(c, FARMS_ERR_ARG, "slice too long");
   CU(cudaSetDevice(c->cfg.device));
   int rc;
   if ((rc = slice_surface_accumulate(c, d_x, d_y, d_t, n, 0, t0, true))) return rc;
@@ -857,7 +846,7 @@ int farms_slice_surface(farms_ctx *c, const uint16_t *d_x, const uint16_t *d_y, 
 int farms_slice_surface_host(farms_ctx *c, const uint16_t *x, const uint16_t *y, const uint64_t *t, uint64_t n,
                              uint64_t t0, uint32_t *last_t, uint8_t *hit) {
   if (!c || !last_t || !hit || (n && (!x || !y || !t))) return FARMS_ERR_ARG;
-  if (n >= (1ull << 32) - 1) return fail(c, FARMS_ERR_ARG, "slice too long");
+  if (n >= (1ull << 32) - 1) return farms_fail(c, FARMS_ERR_ARG, "slice too long");
   CU(cudaSetDevice(c->cfg.device));
   int rc;
   const size_t piece = 4u << 20;
