@@ -11,6 +11,9 @@
  * UNMODIFIED reference sources compiled against oracle/shim/ (Eigen3 and Boost headers are absent
  * from the image).  The FP64 operation order inside Eigen (At*A, determinant, A2*At*Y) is therefore
  * the shim's, not real Eigen's: that slice of parity is unpinned (see DESIGN.md "Oracle").
+ * The serial mode (farms_oracle_set_serial: the reference's default driver vFlowManager::run, which writes no
+ * file) is pinned against what the reference's own computeLocalFlow / computeTrueFlow returned inside run(),
+ * recorded by the call probe oracle/serial_probe.cpp (tests/golden/make_golden_serial.py).
  */
 #ifndef FARMS_ORACLE_H
 #define FARMS_ORACLE_H

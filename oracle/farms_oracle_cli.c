@@ -3,7 +3,8 @@
  * 11-column batch format (vFlow.cpp:436-440; ostream default == "%g"), so it can be diffed against
  * the tier-1 build's "<base>_FARMSOut_batch.txt".
  * usage: farms_oracle_cli <width> <height> <filtersize> <inlierCheck> <base> [numEvents]
- * FARMS_ORACLE_FAST=1 selects the fast pooling mode (farms_oracle_set_fast). */
+ * FARMS_ORACLE_FAST=1 selects the fast pooling mode (farms_oracle_set_fast), FARMS_ORACLE_SERIAL=1 the semantics of
+ * the reference's default driver vFlowManager::run (farms_oracle_set_serial; row 0 is the line that only sets t0). */
 #include <stdio.h>
 #include <stdlib.h>
 #include <time.h>
@@ -35,6 +36,7 @@ int main(int argc, char **argv) {
   o.valid = malloc(n); o.best_window = malloc(n);
   farms_oracle *orc = farms_oracle_create(W, H, fs, inl);
   if (getenv("FARMS_ORACLE_FAST") && atoi(getenv("FARMS_ORACLE_FAST")) && farms_oracle_set_fast(orc, 1)) return 1;
+  if (getenv("FARMS_ORACLE_SERIAL") && atoi(getenv("FARMS_ORACLE_SERIAL")) && farms_oracle_set_serial(orc, 1)) return 1;
   struct timespec a, b;
   clock_gettime(CLOCK_MONOTONIC, &a);
   int rc = farms_oracle_process(orc, x, y, t, p, n, &o);

@@ -83,3 +83,17 @@ LONG_SYNTH_CASES = {
     "synth_cfg3_346x260_fs7_2M": (3, 2_000_000, 0),
     "synth_cfg4_1280x720_2M": (4, 2_000_000, 0),
 }
+
+# The reference's DEFAULT driver (vFlowManager::run, --SERIAL 1), observed through the call probe of
+# oracle/serial_probe.cpp: name -> (width, height, filtersize, inlierCheck, builder).  width > height only on surfaces
+# of >= 16,384 pixels (see TEXT_CASES about heap-sized ones: the reference reads past the end of its vectors there).
+SERIAL_CASES = {
+    "serial_sweeps_30x40_fs5": (30, 40, 5, 5, lambda: sweeps(30, 40, slopes=((25, 9), (-6, 9), (11, -7)), jitter=2, gap=120)),
+    "serial_sweeps_20x24_fs3_inl3": (20, 24, 3, 3, lambda: sweeps(20, 24)),
+    "serial_sweeps_18x30_fs7": (18, 30, 7, 5, lambda: sweeps(18, 30, jitter=1)),
+    "serial_sweeps_200x100_fs5": (200, 100, 5, 5, lambda: sweeps(200, 100, slopes=((9, 4), (-6, 10)), gap=300, drop=0.1)),
+}
+# ... and on a synthetic benchmark scene: name -> (config, n events, stream start us); SHA-256 of the rows only
+SERIAL_SYNTH_CASES = {
+    "serial_synth_cfg2_304x240": (2, 60000, 0),
+}

@@ -271,7 +271,8 @@ def test_tall_sensors_fast_path(w, h, variant):
 def test_serial_semantics_match_the_oracle_serial_mode(config, n, max_batch):
     """FARMS_FLAG_SERIAL_SEMANTICS = the reference's default driver vFlowManager::run (src/vFlow.cpp:465-826): first
     event only sets t0 (raw time left in lastEventTime), lastEventTime written after pooling.  The reference writes
-    nothing in that mode, so the check is against the oracle's restatement of it (parity unpinned for this mode)."""
+    nothing in that mode, so the check is against the oracle's restatement of it, which test_oracle_golden.py pins to
+    what the reference's own functions returned inside run() (oracle/serial_probe.cpp)."""
     import farms_b200
     s, x, y, t, p = synth_stream(config, n, 0)
     ref = run_oracle(s.width, s.height, s.filtersize, 5, x, y, t, p, serial=True)

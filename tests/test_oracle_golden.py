@@ -9,10 +9,12 @@ import numpy as np
 import pytest
 
 from helpers import ROOT, run_oracle
-from kat_streams import HASH_CASES, LONG_SYNTH_CASES, SYNTH_CASES, TEXT_CASES, sweeps, write_txt
+from kat_streams import (HASH_CASES, LONG_SYNTH_CASES, SERIAL_CASES, SERIAL_SYNTH_CASES, SYNTH_CASES, TEXT_CASES, sweeps,
+                         write_txt)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 META = json.load(open(os.path.join(GOLDEN, "golden.json")))
+META_SERIAL = json.load(open(os.path.join(GOLDEN, "golden_serial.json")))
 CLI = os.path.join(ROOT, "oracle", "farms_oracle_cli")
 
 
@@ -22,11 +24,11 @@ def _cli():
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "farms_oracle_cli"])
 
 
-def oracle_text(tmp_path, name, w, h, fs, inl, x, y, t, p, fast=False):
+def oracle_text(tmp_path, name, w, h, fs, inl, x, y, t, p, fast=False, serial=False):
     base = str(tmp_path / name)
     write_txt(base + ".txt", x, y, t, p)
     subprocess.run([CLI, str(w), str(h), str(fs), str(inl), base], check=True, capture_output=True,
-                   env=dict(os.environ, FARMS_ORACLE_FAST="1" if fast else "0"))
+                   env=dict(os.environ, FARMS_ORACLE_FAST="1" if fast else "0", FARMS_ORACLE_SERIAL="1" if serial else "0"))
     return open(base + "_FARMSOut_oracle.txt", "rb").read()
 
 
@@ -231,3 +233,52 @@ def test_serial_mode_of_the_oracle_against_an_independent_pooling(serial):
         b = Oracle(w, h, 5, 5).process(x, y, t, p)
         both = v & b["valid"].astype(bool)
         assert np.count_nonzero(r["global_r"][both] != b["global_r"][both]) > 10
+
+
+# ---------------------------------------------------------------------------------------------------
+# The serial mode against the reference's DEFAULT driver: vFlowManager::run writes no file, so its results were
+# recorded through the call probe of oracle/serial_probe.cpp (tests/golden/make_golden_serial.py).
+# ---------------------------------------------------------------------------------------------------
+def _serial_rows(tmp_path, name, w, h, fs, inl, x, y, t, p):
+    got = oracle_text(tmp_path, name, w, h, fs, inl, x, y, t, p, serial=True).decode().splitlines()
+    assert got[0].split()[4:] == ["0"] * 7  # the line that only sets t0 (src/vFlow.cpp:531-558)
+    k = META_SERIAL[name]["rows"]           # run() stops at numEvents <= filesize / 18 (:511); the oracle does not
+    return got[1:1 + k]
+
+
+@pytest.mark.parametrize("name", sorted(SERIAL_CASES))
+def test_serial_mode_golden(name, tmp_path):
+    """Event by event what the reference's own computeLocalFlow / computeTrueFlow returned inside run()."""
+    w, h, fs, inl, build = SERIAL_CASES[name]
+    got = _serial_rows(tmp_path, name, w, h, fs, inl, *build())
+    m = META_SERIAL[name]
+    assert len(got) == m["rows"]
+    assert sum(1 for r in got if float(r.split()[4]) > 0) == m["valid"] > 0.5 * m["rows"]
+    path = os.path.join(GOLDEN, name + ".ref.txt")
+    if os.path.exists(path):
+        assert got == open(path).read().splitlines()
+    assert hashlib.sha256(("\n".join(got) + "\n").encode()).hexdigest() == m["sha256"]
+
+
+@pytest.mark.parametrize("name", sorted(SERIAL_SYNTH_CASES))
+def test_serial_mode_golden_on_a_benchmark_scene(name, tmp_path):
+    from farms_synth import Synth
+    cfg, n, start = SERIAL_SYNTH_CASES[name]
+    s = Synth(cfg)
+    x, y, t, p = s.first(n, start)
+    inp = np.stack([x.astype(np.int64), y.astype(np.int64), t.astype(np.int64), p.astype(np.int64)], 1)
+    m = META_SERIAL[name]
+    assert hashlib.sha256(inp.tobytes()).hexdigest() == m["input_sha256"], "generator changed"
+    got = _serial_rows(tmp_path, name, s.width, s.height, s.filtersize, 5, x, y, t, p)
+    assert sum(1 for r in got if float(r.split()[4]) > 0) == m["valid"]
+    assert hashlib.sha256(("\n".join(got) + "\n").encode()).hexdigest() == m["sha256"]
+
+
+def test_serial_mode_differs_from_the_batch_driver_on_the_golden_streams(tmp_path):
+    """The two drivers really disagree on these streams (else the goldens above would pin nothing new)."""
+    name = "serial_sweeps_30x40_fs5"
+    w, h, fs, inl, build = SERIAL_CASES[name]
+    x, y, t, p = build()
+    ser = _serial_rows(tmp_path, name, w, h, fs, inl, x, y, t, p)
+    bat = oracle_text(tmp_path, name + "_b", w, h, fs, inl, x, y, t, p).decode().splitlines()[1:1 + len(ser)]
+    assert sum(a != b for a, b in zip(ser, bat)) > 20
