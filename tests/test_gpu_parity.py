@@ -148,7 +148,7 @@ def test_alternative_pooling_kernels_match_oracle_and_exact_kernel(impl):
 @pytest.mark.parametrize("squeeze", [2.5, 6.0])
 def test_locally_dense_streams_overflowing_the_staging_slots(squeeze):
     """Time-compressed 1280x720 stream: 2.5x the event density overflows the 512-record slots of the first
-    pooling pass (the flagged second pass with 768-record slots takes those rounds), 6x overflows both (the
+    pooling pass (the flagged second pass with 960-record slots takes those rounds), 6x overflows both (the
     general kernel takes them).  Every route must give the exact kernel's scales and the oracle's numbers."""
     import farms_b200
     s, x, y, t, p = synth_stream(4, 700_000, 2000)
@@ -200,8 +200,8 @@ def _oracle_long(config, n):
 @pytest.mark.parametrize("config,n,variant,first", LONG)
 def test_steady_state_parity_with_the_oracle(config, n, variant, first):
     """1-2 M-event prefixes: at 1280x720 the valid fraction only reaches its steady 45-54 % after ~1 M events, and
-    only then do slabs hold enough flow events for launch_pooling to pick k_pool_tile<8,512,2,2> -- the
-    instantiation the benchmark times.  The kernels that ran and the number of events each path pooled are read
+    only then do slabs hold enough flow events for launch_pooling to pick the dense instantiation
+    (k_pool_tile16<8,512,3,2> for the default variant) -- the one the benchmark times.  The kernels that ran and the number of events each path pooled are read
     back from farms_timings and asserted, so this is the benchmarked path against the oracle, not a self-check."""
     import farms_b200
     s, x, y, t, ref = _oracle_long(config, n)
@@ -222,7 +222,7 @@ def test_steady_state_parity_with_the_oracle(config, n, variant, first):
 @pytest.mark.parametrize("variant", ["tile", "warp", "tile16x4", "tile16x3", "tile16c"])
 def test_dense_stream_second_pass_and_general_kernel_against_the_oracle(variant):
     """Time-compressed 1280x720 stream (2.5x the density): the 512-record slots of the first pass overflow for a
-    good share of the rounds, so the flagged second pass <16,768,4,1> and k_pool_any both pool a substantial number
+    good share of the rounds, so the flagged second pass (<16,960,4,1> / <16,768,4,1>) and k_pool_any both pool a substantial number
     of events -- all three routes against the oracle in one run."""
     import farms_b200
     s, x, y, t, p = synth_stream(4, 1_200_000, 0)

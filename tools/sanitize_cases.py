@@ -22,11 +22,11 @@ def squeeze(t, f):
 def build(case):
     from farms_synth import Synth
     from kat_streams import sweeps
-    if case == "dense":      # k_pool_tile<8,512,2,2> + flagged second pass <16,768,4,1> + k_pool_any
+    if case == "dense":      # k_pool_tile16<8,512,3,2> + flagged second pass <16,960,4,1> + k_pool_any
         s = Synth(2)
         x, y, t, p = s.first(150_000, 0)
         return s.width, s.height, s.filtersize, x, y, squeeze(t, 8.0), {}
-    if case == "sparse":     # k_pool_tile<8,320,4,2>
+    if case == "sparse":     # k_pool_tile16<8,416,4,2>
         s = Synth(1)
         x, y, t, p = s.first(25_000, 0)
         return s.width, s.height, s.filtersize, x, y, t, {}
