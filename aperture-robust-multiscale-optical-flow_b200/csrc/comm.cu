@@ -9,9 +9,10 @@
 // root rank batch by batch while the next batch computes.
 //
 // Two transports behind one interface:
-//   NCCL   one process (or host thread) per GPU; ncclAllGather for the surfaces, ncclSend/ncclRecv per batch for
-//          the outputs.  libnccl.so.2 is loaded on first use (dlopen), so the single-GPU library has no NCCL
-//          dependency.
+//   NCCL   one process (or host thread) per GPU; ncclAllGather for the surfaces; the outputs go to the root batch
+//          by batch as copy-engine writes into its buffer mapped over CUDA IPC (peer memory over NVLink), or with
+//          ncclSend/ncclRecv where that mapping is not available.  libnccl.so.2 is loaded on first use (dlopen),
+//          so the single-GPU library has no NCCL dependency.
 //   LOCAL  all ranks are host threads of one process (the FARMS_Flow command line): the ranks publish their device
 //          buffers in a shared table and copy between devices directly (cudaMemcpyAsync over NVLink peer access),
 //          outputs are written straight into the root's buffer.  Also what lets a one-GPU box test the whole
