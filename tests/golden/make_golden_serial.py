@@ -12,7 +12,13 @@ k + 1 of the stream: the first line of a recording only sets t0 (:531-558) and c
   python tests/golden/make_golden_serial.py          (needs /root/reference for the build only)
 
 Cases of up to 3000 rows keep the rows (<name>.ref.txt), all keep their SHA-256; golden_serial.json also records
-how many lines run() consumed, which pins its `numEvents <= filesize / 18` rule (:511) for the CLI."""
+how many lines run() consumed, which pins its `numEvents <= filesize / 18` rule (:511) for the CLI.
+
+The same probe also sits in front of computeGrads(subsurf, cen, ..): under the BATCH driver (--SERIAL 0) its log
+gives, per event, the inlier count the plane fit returned (:1352-1369) and which of the 9 candidate windows won
+(:870-910) -- two intermediate results that no output file of the reference carries, but that the parity tests of
+the GPU path compare bit for bit (farms_out.inliers / best_window).  They go to <name>.fit.ref.txt as
+"<inliers> <window>" per event ("0 -1" when no window fits inside the sensor and computeGrads is never reached)."""
 import hashlib
 import json
 import math
@@ -26,7 +32,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")]
 import numpy as np  # noqa: E402
-from kat_streams import SERIAL_CASES, SERIAL_SYNTH_CASES, write_txt  # noqa: E402
+from kat_streams import FIT_SYNTH_CASES, SERIAL_CASES, SERIAL_SYNTH_CASES, TEXT_CASES, write_txt  # noqa: E402
 
 REF = os.path.join(ROOT, "oracle", "_ref", "FARMS_Flow_serial")
 
@@ -49,6 +55,8 @@ def run_probe(w, h, fs, inl, x, y, t, p, d, name):
 
     for ln in open(log):
         f = ln.split()
+        if f[0] == "G":  # (plane-fit intermediates: see run_probe_fit)
+            continue
         if f[0] == "L":  # computeLocalFlow() of the next event (:629)
             flush()
             k += 1
@@ -71,6 +79,26 @@ def run_probe(w, h, fs, inl, x, y, t, p, d, name):
                                                             theta, scale)
     flush()
     return rows, os.path.getsize(base + ".txt"), ask
+
+
+def run_probe_fit(w, h, fs, inl, x, y, t, p, d, name):
+    """Batch driver behind the probe -> one "<inliers> <window>" row per event."""
+    base = os.path.join(d, name + "_fit")
+    write_txt(base + ".txt", x, y, t, p)
+    log = base + ".probe"
+    subprocess.run([REF, "--width", str(w), "--height", str(h), "--filtersize", str(fs), "--inlierCheck", str(inl),
+                    "--filename", base, "--SERIAL", "0"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE,
+                   env=dict(os.environ, FARMS_SERIAL_PROBE_OUT=log))
+    rows, grads = [], "0 -1"
+    for ln in open(log):
+        f = ln.split()
+        if f[0] == "G":    # inside computeLocalFlow, before it returns
+            grads = "%d %d" % (int(f[1]), int(f[2]))
+        elif f[0] == "L":
+            rows.append(grads)
+            grads = "0 -1"
+    assert len(rows) == len(x)
+    return rows
 
 
 def summary(rows, fsize, ask):
@@ -100,6 +128,23 @@ def main():
             m["input_sha256"] = hashlib.sha256(np.stack([x.astype(np.int64), y.astype(np.int64), t.astype(np.int64),
                                                           p.astype(np.int64)], 1).tobytes()).hexdigest()
             meta[name] = m
+        fit = {}
+        for name, (w, h, fs, inl, build) in TEXT_CASES.items():
+            rows = run_probe_fit(w, h, fs, inl, *build(), d, name)
+            raw = ("\n".join(rows) + "\n").encode()
+            open(os.path.join(HERE, name + ".fit.ref.txt"), "wb").write(raw)
+            fit[name] = {"rows": len(rows), "fitted": sum(1 for r in rows if not r.endswith("-1")),
+                         "sha256": hashlib.sha256(raw).hexdigest()}
+        for name, (cfg, n, start) in FIT_SYNTH_CASES.items():
+            s = Synth(cfg)
+            x, y, t, p = s.first(n, start)
+            rows = run_probe_fit(s.width, s.height, s.filtersize, 5, x, y, t, p, d, name)
+            raw = ("\n".join(rows) + "\n").encode()
+            fit[name] = {"rows": len(rows), "fitted": sum(1 for r in rows if not r.endswith("-1")),
+                         "sha256": hashlib.sha256(raw).hexdigest()}
+    for k, v in fit.items():
+        print(k, v["rows"], v["fitted"], v["sha256"][:12])
+    json.dump(fit, open(os.path.join(HERE, "golden_fit.json"), "w"), indent=1, sort_keys=True)
     for k, v in meta.items():
         # run() reads the first line, then numEvents + 1 more with numEvents capped at filesize / 18 (:511, :565)
         assert v["rows"] == min(min(v["num_events_asked"], v["input_bytes"] // 18) + 1, v["input_lines"] - 1), (k, v)

@@ -97,3 +97,9 @@ SERIAL_CASES = {
 SERIAL_SYNTH_CASES = {
     "serial_synth_cfg2_304x240": (2, 60000, 0),
 }
+# plane-fit intermediates (inlier count, winning window) of the batch driver through the same probe; TEXT_CASES keep
+# their rows, these keep a SHA-256: name -> (config, n events, stream start us)
+FIT_SYNTH_CASES = {
+    "fit_synth_cfg2_304x240": (2, 40000, 0),
+    "fit_synth_cfg3_346x260_fs7": (3, 40000, 0),
+}

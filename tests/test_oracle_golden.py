@@ -9,12 +9,13 @@ import numpy as np
 import pytest
 
 from helpers import ROOT, run_oracle
-from kat_streams import (HASH_CASES, LONG_SYNTH_CASES, SERIAL_CASES, SERIAL_SYNTH_CASES, SYNTH_CASES, TEXT_CASES, sweeps,
-                         write_txt)
+from kat_streams import (FIT_SYNTH_CASES, HASH_CASES, LONG_SYNTH_CASES, SERIAL_CASES, SERIAL_SYNTH_CASES, SYNTH_CASES,
+                         TEXT_CASES, sweeps, write_txt)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 META = json.load(open(os.path.join(GOLDEN, "golden.json")))
 META_SERIAL = json.load(open(os.path.join(GOLDEN, "golden_serial.json")))
+META_FIT = json.load(open(os.path.join(GOLDEN, "golden_fit.json")))
 CLI = os.path.join(ROOT, "oracle", "farms_oracle_cli")
 
 
@@ -282,3 +283,37 @@ def test_serial_mode_differs_from_the_batch_driver_on_the_golden_streams(tmp_pat
     ser = _serial_rows(tmp_path, name, w, h, fs, inl, x, y, t, p)
     bat = oracle_text(tmp_path, name + "_b", w, h, fs, inl, x, y, t, p).decode().splitlines()[1:1 + len(ser)]
     assert sum(a != b for a, b in zip(ser, bat)) > 20
+
+
+# ---------------------------------------------------------------------------------------------------
+# Plane-fit intermediates the reference's files do not carry: the inlier count computeGrads returned and the window
+# computeLocalFlow chose, recorded per event through the same probe under the batch driver.
+# ---------------------------------------------------------------------------------------------------
+def _oracle_fit_rows(tmp_path, name, w, h, fs, inl, x, y, t, p):
+    base = str(tmp_path / name)
+    write_txt(base + ".txt", x, y, t, p)
+    subprocess.run([CLI, str(w), str(h), str(fs), str(inl), base], check=True, capture_output=True,
+                   env=dict(os.environ, FARMS_ORACLE_DIAG="1"))
+    rows = [ln.split() for ln in open(base + "_FARMSOut_oracle_diag.txt")]  # valid best_window inliers det
+    return ["%s %s" % (r[2], r[1]) for r in rows]
+
+
+@pytest.mark.parametrize("name", sorted(TEXT_CASES))
+def test_inlier_counts_and_windows_golden(name, tmp_path):
+    w, h, fs, inl, build = TEXT_CASES[name]
+    got = _oracle_fit_rows(tmp_path, name, w, h, fs, inl, *build())
+    ref = open(os.path.join(GOLDEN, name + ".fit.ref.txt")).read().splitlines()
+    assert len(ref) == META_FIT[name]["rows"]
+    assert got == ref
+    assert len({r.split()[1] for r in ref}) >= 3  # several different windows win on these streams
+
+
+@pytest.mark.parametrize("name", sorted(FIT_SYNTH_CASES))
+def test_inlier_counts_and_windows_golden_on_benchmark_scenes(name, tmp_path):
+    from farms_synth import Synth
+    cfg, n, start = FIT_SYNTH_CASES[name]
+    s = Synth(cfg)
+    x, y, t, p = s.first(n, start)
+    got = _oracle_fit_rows(tmp_path, name, s.width, s.height, s.filtersize, 5, x, y, t, p)
+    assert len(got) == META_FIT[name]["rows"]
+    assert hashlib.sha256(("\n".join(got) + "\n").encode()).hexdigest() == META_FIT[name]["sha256"]
