@@ -1,3 +1,5 @@
+# A/B of a pooling variant against the library's default on a B200 box, with its parity tests and self-check cases:
+#   bash tools/ab_variant.sh            (the run recorded in profiles/r4_xcull_ab.txt: pool_variant "tile16c")
 B="python bench.py --events 60000000 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-extras"
 for v in "" tile16c; do
   $B --pool-variant "$v" > gpurun_out/r4b_ab_$v.json 2> gpurun_out/r4b_ab_$v.err
