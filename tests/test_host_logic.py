@@ -188,3 +188,21 @@ def test_viewer_reads_the_reference_output_format(capsys):
     out = capsys.readouterr().out
     assert "192 events, 184 with flow" in out
     assert "      70.0      184" in out and "circular spread: local 0.0 deg, global 0.0 deg" in out
+
+
+@pytest.mark.parametrize("w,h,kw", [(20, 24, {}), (36, 20, dict(slopes=((9, 4), (-6, 10), (7, -5)), gap=200))])
+def test_summed_area_table_pooling_prototype_is_exact(w, h, kw):
+    """tools/sat_pooling_prototype.py (the algorithm DESIGN.md section 9 sizes as the next step, not the product):
+    per-slab summed-area tables corrected by the slab's own births and deaths give the oracle's scale for every event,
+    including on a width > height sensor where rows alias the next column."""
+    from helpers import run_oracle
+    from kat_streams import sweeps
+    from sat_pooling_prototype import pool_sat
+    x, y, t, p = sweeps(w, h, **kw)
+    o = run_oracle(w, h, 5, 5, x, y, t, p)
+    gr, gth, sc, st = pool_sat(w, h, x, y, o["t_rel"], o["local_r"], o["local_theta"], o["valid"])
+    v = o["valid"].astype(bool)
+    assert v.sum() > 1000 and st["slabs"] > 5
+    assert np.array_equal(sc[v], o["scale"][v])
+    assert np.all(np.abs(gr[v] - o["global_r"][v]) <= 1e-10 * o["global_r"][v])
+    assert np.all(np.abs(np.angle(np.exp(1j * (gth[v] - o["global_theta"][v])))) <= 1e-10)
