@@ -206,3 +206,13 @@ def test_summed_area_table_pooling_prototype_is_exact(w, h, kw):
     assert np.array_equal(sc[v], o["scale"][v])
     assert np.all(np.abs(gr[v] - o["global_r"][v]) <= 1e-10 * o["global_r"][v])
     assert np.all(np.abs(np.angle(np.exp(1j * (gth[v] - o["global_theta"][v])))) <= 1e-10)
+
+
+@pytest.mark.parametrize("header", ["farms_b200.h", "farms_textio.h"])
+def test_public_headers_are_plain_c(header, tmp_path):
+    """The drop-in boundary is a C ABI: the headers must compile as strict C99 (and as C++11) on their own."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "%s"\nint main(void) { return 0; }\n' % os.path.join(ROOT, "include", header))
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", str(src)], check=True)
+    subprocess.run(["g++", "-std=c++11", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", str(src)],
+                   check=True)
