@@ -32,17 +32,8 @@ def _rows_close(got, ref, cols_exact=(0, 1, 2, 3, 10)):
     return True
 
 
-@pytest.mark.parametrize("name", sorted(TEXT_CASES))
-def test_cli_matches_reference_output_file(name, tmp_path):
-    """FARMS_Flow writes <filename>_FARMSOut_batch.txt like the reference's batch mode (src/vFlow.cpp:131, 438)."""
-    w, h, fs, inl, build = TEXT_CASES[name]
-    base = str(tmp_path / name)
-    write_txt(base + ".txt", *build())
-    out = subprocess.run([CLI, "--width", str(w), "--height", str(h), "--filtersize", str(fs), "--inlierCheck", str(inl),
-                          "--filename", base, "--SERIAL", "0"], capture_output=True, text=True)
-    assert out.returncode == 0, out.stderr
-    assert "[Benchmark Main]" in out.stdout
-    got = open(base + "_FARMSOut_batch.txt").read().splitlines()
+def _assert_matches_golden_text(got, name):
+    """11-column rows against tests/golden/<name>.ref.txt (the reference's own file)."""
     ref = open(os.path.join(GOLDEN, name + ".ref.txt")).read().splitlines()
     assert len(got) == len(ref)
     exact = sum(a == b for a, b in zip(got, ref))
@@ -62,6 +53,20 @@ def test_cli_matches_reference_output_file(name, tmp_path):
     if not name.startswith("kat_plane"):
         assert len(flips) <= 0.02 * len(ref)
         assert exact >= 0.97 * len(ref)
+
+
+@pytest.mark.parametrize("name", sorted(TEXT_CASES))
+def test_cli_matches_reference_output_file(name, tmp_path):
+    """FARMS_Flow writes <filename>_FARMSOut_batch.txt like the reference's batch mode (src/vFlow.cpp:131, 438)."""
+    w, h, fs, inl, build = TEXT_CASES[name]
+    base = str(tmp_path / name)
+    write_txt(base + ".txt", *build())
+    out = subprocess.run([CLI, "--width", str(w), "--height", str(h), "--filtersize", str(fs), "--inlierCheck", str(inl),
+                          "--filename", base, "--SERIAL", "0"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "[Benchmark Main]" in out.stdout
+    got = open(base + "_FARMSOut_batch.txt").read().splitlines()
+    _assert_matches_golden_text(got, name)
     # the 8-column file the README documents: columns 1-6, 9, 10
     got8 = open(base + "_FARMSOut_.txt").read().splitlines()
     assert [" ".join(np.array(r.split())[[0, 1, 2, 3, 4, 5, 8, 9]]) for r in got] == got8
@@ -435,3 +440,22 @@ def test_timestamp_step_back_beyond_the_slack_is_an_error_across_batches():
     assert e.value.code == farms_b200.ERR_STATE and "reorder_slack_us" in str(e.value)
     wide = farms_b200.Farms(s.width, s.height, s.filtersize, 5, max_batch=20000, reorder_slack_us=6000).process(x, y, t2)
     assert_parity(compare(wide, ref, "three batches, slack 6000 us"))
+
+
+DROPIN = os.path.join(ROOT, "oracle", "_ref", "FARMS_Flow_dropin")
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN), reason="oracle/_ref/FARMS_Flow_dropin is built where /root/reference exists")
+@pytest.mark.parametrize("name", ["kat_sweeps_20x24_fs5", "kat_sweeps_18x30_fs7"])
+def test_reference_main_runs_the_b200_path_through_the_dropin_binding(name, tmp_path):
+    """The drop-in, literally: the reference's UNMODIFIED main.cpp and vFlowManager (oracle/_ref/libfarms_ref.so) with
+    examples/vFlowB200.cpp -- the binding INTEGRATION.md shows, a runFileCopy over the C ABI -- linked in front.  Its
+    flags, banners and output file are the reference's; the numbers come from the GPU."""
+    w, h, fs, inl, build = TEXT_CASES[name]
+    base = str(tmp_path / name)
+    write_txt(base + ".txt", *build())
+    out = subprocess.run([DROPIN, "--width", str(w), "--height", str(h), "--filtersize", str(fs), "--inlierCheck", str(inl),
+                          "--filename", base, "--SERIAL", "0"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-500:]
+    assert "Running batch" in out.stdout and "[Benchmark Main]" in out.stdout
+    _assert_matches_golden_text(open(base + "_FARMSOut_batch.txt").read().splitlines(), name)

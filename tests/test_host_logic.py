@@ -218,13 +218,16 @@ def test_public_headers_are_plain_c(header, tmp_path):
                    check=True)
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/include"), reason="needs the reference's headers")
-def test_integration_snippet_compiles_against_the_reference_headers(tmp_path):
-    """INTEGRATION.md section 2 shows the binding a maintainer would add to the reference (a replacement body for
-    vFlowManager::runFileCopy over the C ABI): it must at least compile against the reference's own vFlow.h."""
+def test_integration_snippet_is_the_tested_example():
+    """INTEGRATION.md section 2 shows examples/vFlowB200.cpp verbatim (the file `make -C oracle dropin` builds and the
+    GPU suite runs behind the reference's own main)."""
     text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     code = re.search(r"```cpp\n(// src/vFlowB200\.cpp.*?)```", text, re.S).group(1)
-    src = tmp_path / "vFlowB200.cpp"
-    src.write_text(code.replace('#include "../include/vFlow.h"', '#include "vFlow.h"'))
-    subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-w", "-I/root/reference/include",
-                    "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "include"), str(src)], check=True)
+    assert code == open(os.path.join(ROOT, "examples", "vFlowB200.cpp")).read()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/include"), reason="needs the reference's headers")
+def test_dropin_example_compiles_against_the_reference_headers():
+    subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-w", "-I/root/reference/src", "-I/root/reference/include",
+                    "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "vFlowB200.cpp")], check=True)
